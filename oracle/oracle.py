@@ -1,0 +1,340 @@
+"""ctypes front-end to oracle/pgsgd_oracle.c (the CPU restatement of the reference's PG-SGD).
+
+TEST INFRASTRUCTURE ONLY — see oracle/__init__.py.  Parity status: pinned against the reference
+itself (tests/test_oracle_pinned.py, scripts/pin_oracle.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpgsgd_oracle.so")
+_SRC = os.path.join(_HERE, "pgsgd_oracle.c")
+_HDR = os.path.join(_HERE, "pgsgd_oracle.h")
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (strict IEEE: no fast-math, no FMA contraction)."""
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(_SRC), os.path.getmtime(_HDR)):
+        return _SO
+    cmd = ["gcc", "-O2", "-std=c99", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", _SO, _SRC, "-lm"]
+    subprocess.run(cmd, check=True)
+    return _SO
+
+
+class _Graph(C.Structure):
+    _fields_ = [("node_count", C.c_uint64), ("path_count", C.c_uint64), ("step_count", C.c_uint64),
+                ("node_len", C.c_void_p), ("path_first_step", C.c_void_p), ("step_node", C.c_void_p),
+                ("step_rev", C.c_void_p), ("step_pos", C.c_void_p), ("step_perm", C.c_void_p)]
+
+
+class _Config(C.Structure):
+    _fields_ = [("iter_max", C.c_uint64), ("iter_with_max_learning_rate", C.c_uint64), ("min_term_updates", C.c_uint64),
+                ("delta", C.c_double), ("eps", C.c_double), ("eta_max", C.c_double), ("theta", C.c_double),
+                ("space", C.c_uint64), ("space_max", C.c_uint64), ("space_quantization_step", C.c_uint64),
+                ("cooling_start", C.c_double), ("seed", C.c_uint64)]
+
+
+class _Rng(C.Structure):
+    _fields_ = [("s", C.c_uint64 * 4)]
+
+
+TERM_DTYPE = np.dtype([("step_index", "<u8"), ("path", "<u8"), ("rank_a", "<u8"), ("rank_b", "<u8"),
+                       ("node_a", "<u4"), ("node_b", "<u4"), ("rev_a", "u1"), ("rev_b", "u1"), ("flip_a", "u1"),
+                       ("flip_b", "u1"), ("end_a", "u1"), ("end_b", "u1"), ("_pad0", "u1", (2,)),
+                       ("pos_a", "<u8"), ("pos_b", "<u8"), ("zipf", "u1"), ("_pad1", "u1", (7,))])
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        L = _lib
+        L.orc_rng_seed.argtypes = [C.POINTER(_Rng), C.c_uint64]
+        L.orc_rng_next.argtypes = [C.POINTER(_Rng)]
+        L.orc_rng_next.restype = C.c_uint64
+        L.orc_uniform.argtypes = [C.POINTER(_Rng), C.c_uint64]
+        L.orc_uniform.restype = C.c_uint64
+        L.orc_canonical.argtypes = [C.POINTER(_Rng)]
+        L.orc_canonical.restype = C.c_double
+        L.orc_fast_precise_pow.argtypes = [C.c_double, C.c_double]
+        L.orc_fast_precise_pow.restype = C.c_double
+        L.orc_zeta.argtypes = [C.c_uint64, C.c_double]
+        L.orc_zeta.restype = C.c_double
+        L.orc_dirty_zipf.argtypes = [C.POINTER(_Rng), C.c_uint64, C.c_double, C.c_double]
+        L.orc_dirty_zipf.restype = C.c_uint64
+        L.orc_schedule.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_void_p]
+        L.orc_zetas.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, C.c_void_p, C.c_uint64]
+        L.orc_zetas.restype = C.c_uint64
+        L.orc_sample_term.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                      C.POINTER(_Rng), C.c_void_p]
+        L.orc_sample_term.restype = C.c_int
+        for name in ("orc_layout_2d",):
+            getattr(L, name).argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_void_p, C.c_void_p]
+            getattr(L, name).restype = C.c_uint64
+        L.orc_layout_2d_f32.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_void_p]
+        L.orc_layout_2d_f32.restype = C.c_uint64
+        L.orc_sort_1d.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_void_p, C.c_void_p]
+        L.orc_sort_1d.restype = C.c_uint64
+        L.orc_replay_single.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_int, C.c_uint64, C.c_uint64, C.c_double,
+                                        C.c_double, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_replay_single.restype = C.c_uint64
+        L.orc_path_stress_2d.argtypes = [C.POINTER(_Graph), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
+        L.orc_path_stress_2d.restype = C.c_double
+        L.orc_path_stress_1d.argtypes = [C.POINTER(_Graph), C.c_void_p, C.c_uint64, C.c_uint64]
+        L.orc_path_stress_1d.restype = C.c_double
+        assert C.sizeof(_Config) == 96
+    return _lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class Config:
+    """Mirror of the reference's PG-SGD parameter list (path_sgd_layout.hpp:37-56)."""
+    iter_max: int = 30
+    iter_with_max_learning_rate: int = 0
+    min_term_updates: int = 0
+    delta: float = 0.0
+    eps: float = 0.01
+    eta_max: float = 0.0
+    theta: float = 0.99
+    space: int = 0
+    space_max: int = 1000
+    space_quantization_step: int = 100
+    cooling_start: float = 0.5
+    seed: int = 9399220
+
+    def c(self) -> _Config:
+        return _Config(self.iter_max, self.iter_with_max_learning_rate, self.min_term_updates, self.delta, self.eps,
+                       self.eta_max, self.theta, self.space, self.space_max, self.space_quantization_step,
+                       self.cooling_start, self.seed)
+
+
+class Graph:
+    """Path-major flattened graph held as numpy arrays (kept alive for the C side)."""
+
+    def __init__(self, node_len, path_first_step, step_node, step_rev, step_pos=None, step_perm=None):
+        self.node_len = np.ascontiguousarray(node_len, dtype=np.uint32)
+        self.path_first_step = np.ascontiguousarray(path_first_step, dtype=np.uint64)
+        self.step_node = np.ascontiguousarray(step_node, dtype=np.uint32)
+        self.step_rev = np.ascontiguousarray(step_rev, dtype=np.uint8)
+        if step_pos is None:
+            step_pos = positions_from_lengths(self.node_len, self.path_first_step, self.step_node)
+        self.step_pos = np.ascontiguousarray(step_pos, dtype=np.uint64)
+        self.step_perm = None if step_perm is None else np.ascontiguousarray(step_perm, dtype=np.uint64)
+        self.N = int(self.node_len.size)
+        self.P = int(self.path_first_step.size - 1)
+        self.S = int(self.step_node.size)
+
+    @classmethod
+    def from_arrays(cls, arrs, use_xp_perm: bool = False):
+        perm = None
+        if use_xp_perm:
+            # XP's node-major sampling table: step_index -> (path id, 1-based rank) (xp.cpp:143-144)
+            first = arrs["path_first_step"]
+            pid = arrs["xp_npi_iv"].astype(np.int64)
+            path_index = {int(v): i for i, v in enumerate(arrs["xp_path_id"])}
+            pidx = np.array([path_index[int(v)] for v in pid], dtype=np.uint64)
+            perm = first[pidx] + arrs["xp_nr_iv"] - 1
+        return cls(arrs["node_len"], arrs["path_first_step"], arrs["step_node"], arrs["step_rev"], arrs["step_pos"], perm)
+
+    def with_perm(self, perm):
+        return Graph(self.node_len, self.path_first_step, self.step_node, self.step_rev, self.step_pos, perm)
+
+    def c(self) -> _Graph:
+        return _Graph(self.N, self.P, self.S, _ptr(self.node_len), _ptr(self.path_first_step), _ptr(self.step_node),
+                      _ptr(self.step_rev), _ptr(self.step_pos), _ptr(self.step_perm))
+
+    @property
+    def step_counts(self):
+        return np.diff(self.path_first_step.astype(np.int64))
+
+    @property
+    def max_path_steps(self) -> int:
+        return int(self.step_counts.max()) if self.P else 0
+
+    @property
+    def max_path_bp(self) -> int:
+        best = 0
+        for p in range(self.P):
+            a, b = int(self.path_first_step[p]), int(self.path_first_step[p + 1])
+            if b > a:
+                best = max(best, int(self.step_pos[b - 1]) + int(self.node_len[self.step_node[b - 1]]))
+        return best
+
+
+def positions_from_lengths(node_len, path_first_step, step_node) -> np.ndarray:
+    """step_pos[s] = bp offset of step s's node start within its path (XPPath ctor, xp.cpp:607-616)."""
+    lens = node_len[step_node].astype(np.uint64)
+    csum = np.cumsum(lens, dtype=np.uint64)
+    pos = np.empty_like(csum)
+    pos[0:1] = 0
+    pos[1:] = csum[:-1]
+    first = np.asarray(path_first_step[:-1], dtype=np.int64)
+    counts = np.diff(np.asarray(path_first_step, dtype=np.int64))
+    nonempty = counts > 0
+    base = np.zeros(len(first), dtype=np.uint64)
+    base[nonempty] = pos[first[nonempty]]
+    return pos - np.repeat(base, counts)
+
+
+def default_layout_config(g: Graph, **kw) -> Config:
+    """`odgi layout` defaults (layout_main.cpp:198-266)."""
+    ms = g.max_path_steps
+    c = Config(iter_max=30, min_term_updates=10 * g.S, eta_max=float(ms) * float(ms), space=ms, space_max=1000,
+               space_quantization_step=100)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def default_sort_config(g: Graph, **kw) -> Config:
+    """`odgi sort -Y` defaults (sort_main.cpp:313-414)."""
+    ms = g.max_path_steps
+    space = g.max_path_bp
+    space_max = 100
+    max_dists = max(space_max + 1, 100)
+    q = max(2, int(np.ceil((space - space_max) / (max_dists - space_max))))
+    c = Config(iter_max=100, min_term_updates=g.S, eta_max=float(ms) * float(ms), space=space, space_max=space_max,
+               space_quantization_step=q)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def schedule(cfg: Config) -> np.ndarray:
+    etas = np.zeros(cfg.iter_max + 1, dtype=np.float64)
+    lib().orc_schedule(cfg.eta_max, cfg.iter_max, cfg.iter_with_max_learning_rate, cfg.eps, _ptr(etas))
+    return etas
+
+
+def zetas(cfg: Config) -> np.ndarray:
+    n = lib().orc_zetas(cfg.space, cfg.space_max, cfg.space_quantization_step, cfg.theta, None, 0)
+    z = np.zeros(n, dtype=np.float64)
+    lib().orc_zetas(cfg.space, cfg.space_max, cfg.space_quantization_step, cfg.theta, _ptr(z), n)
+    return z
+
+
+def layout_init(g: Graph, seed: int = 42, noise: bool = True):
+    """'d' initialisation (layout_main.cpp:322-328): X = cumulative bp, Y ~ N(0, sqrt(2N)).
+    The reference seeds its mt19937 from std::random_device; parity runs inject this seeded one."""
+    N = g.N
+    X = np.zeros(2 * N, dtype=np.float64)
+    csum = np.cumsum(g.node_len.astype(np.uint64))
+    X[1::2] = csum
+    X[2::2] = csum[:-1]
+    if noise:
+        rng = np.random.Generator(np.random.MT19937(seed))
+        Y = rng.normal(0.0, np.sqrt(2.0 * N), size=2 * N)
+    else:
+        Y = np.zeros(2 * N, dtype=np.float64)
+    return X, Y
+
+
+def sort_init(g: Graph) -> np.ndarray:
+    """1D initialisation: X[rank] = cumulative bp of the node order (path_sgd.cpp:63-69)."""
+    csum = np.cumsum(g.node_len.astype(np.uint64))
+    X = np.zeros(g.N, dtype=np.float64)
+    X[1:] = csum[:-1]
+    return X
+
+
+def layout_2d(g: Graph, cfg: Config, X, Y, n_streams: int = 1) -> int:
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    gc, cc = g.c(), cfg.c()
+    n = lib().orc_layout_2d(C.byref(gc), C.byref(cc), n_streams, _ptr(X), _ptr(Y))
+    return int(n), X, Y
+
+
+def layout_2d_f32(g: Graph, cfg: Config, xy, n_streams: int = 1):
+    xy = np.ascontiguousarray(xy, dtype=np.float32)
+    gc, cc = g.c(), cfg.c()
+    n = lib().orc_layout_2d_f32(C.byref(gc), C.byref(cc), n_streams, _ptr(xy))
+    return int(n), xy
+
+
+def sort_1d(g: Graph, cfg: Config, X, n_streams: int = 1, frozen=None):
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    fz = None if frozen is None else np.ascontiguousarray(frozen, dtype=np.uint8)
+    gc, cc = g.c(), cfg.c()
+    n = lib().orc_sort_1d(C.byref(gc), C.byref(cc), n_streams, _ptr(fz), _ptr(X))
+    return int(n), X
+
+
+def replay_single(g: Graph, cfg: Config, dims: int, n_terms: int, switch_at: int, eta0: float, eta1: float,
+                  cooling0: bool, cooling1: bool, theta1: float, X=None, Y=None, want_terms: bool = True):
+    terms = np.zeros(n_terms, dtype=TERM_DTYPE) if want_terms else None
+    gc, cc = g.c(), cfg.c()
+    lib().orc_replay_single(C.byref(gc), C.byref(cc), dims, n_terms, switch_at, eta0, eta1, int(cooling0), int(cooling1),
+                            theta1, _ptr(X), _ptr(Y), _ptr(terms))
+    return terms
+
+
+def sample_terms(g: Graph, cfg: Config, dims: int, cooling: bool, n_terms: int, stream: int = 0, theta_zipf=None):
+    """The first n_terms draws of worker stream `stream` (seed + stream), including the 1-step-path
+    skips as rows with valid == 0."""
+    L = lib()
+    z = zetas(cfg)
+    rng = _Rng()
+    L.orc_rng_seed(C.byref(rng), cfg.seed + stream)
+    terms = np.zeros(n_terms, dtype=TERM_DTYPE)
+    valid = np.zeros(n_terms, dtype=np.uint8)
+    gc, cc = g.c(), cfg.c()
+    th = cfg.theta if theta_zipf is None else theta_zipf
+    base = terms.ctypes.data
+    for k in range(n_terms):
+        valid[k] = L.orc_sample_term(C.byref(gc), C.byref(cc), _ptr(z), dims, int(cooling), th, C.byref(rng),
+                                     C.c_void_p(base + k * TERM_DTYPE.itemsize))
+    return terms, valid
+
+
+def path_stress_2d(g: Graph, X, Y, n_pairs: int = 1_000_000, seed: int = 12345) -> float:
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    gc = g.c()
+    return float(lib().orc_path_stress_2d(C.byref(gc), _ptr(X), _ptr(Y), n_pairs, seed))
+
+
+def path_stress_1d(g: Graph, X, n_pairs: int = 1_000_000, seed: int = 12345) -> float:
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    gc = g.c()
+    return float(lib().orc_path_stress_1d(C.byref(gc), _ptr(X), n_pairs, seed))
+
+
+def xy_to_XY(xy: np.ndarray):
+    """float4-per-node device layout {x0,y0,x1,y1} -> reference X/Y indexed 2*node+end."""
+    a = np.asarray(xy).reshape(-1, 4)
+    X = np.empty(2 * a.shape[0], dtype=np.float64)
+    Y = np.empty_like(X)
+    X[0::2], Y[0::2], X[1::2], Y[1::2] = a[:, 0], a[:, 1], a[:, 2], a[:, 3]
+    return X, Y
+
+
+def XY_to_xy(X, Y, dtype=np.float32) -> np.ndarray:
+    N = len(X) // 2
+    a = np.empty((N, 4), dtype=dtype)
+    a[:, 0], a[:, 1], a[:, 2], a[:, 3] = X[0::2], Y[0::2], X[1::2], Y[1::2]
+    return a.reshape(-1)
+
+
+def order_from_x(x: np.ndarray, component: Optional[np.ndarray] = None) -> np.ndarray:
+    """path_linear_sgd_order's sort (path_sgd.cpp:650-658): by (weak component, pos, handle integer).
+    NB the reference clears weak_components_map before reading it (path_sgd.cpp:588), so on a
+    single-component graph — and in practice on every graph — the component key is constant; pass
+    component=None to mirror that.  Returns node ranks in sorted order."""
+    n = len(x)
+    comp = np.zeros(n, dtype=np.uint64) if component is None else np.asarray(component, dtype=np.uint64)
+    handle = np.arange(n, dtype=np.uint64) << np.uint64(1)
+    return np.lexsort((handle, np.asarray(x, dtype=np.float64), comp)).astype(np.uint64)

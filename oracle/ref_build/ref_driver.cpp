@@ -18,6 +18,7 @@
 //   ref_driver dump   <in.gfa> <out.arr>                        flattened graph + XP tables
 //   ref_driver layout <in.gfa> <init.arr|-> <out.arr> [k=v...]  2D PG-SGD (X,Y injected from init.arr)
 //   ref_driver sort   <in.gfa> <out.arr> [k=v...]               1D PG-SGD (+ order)
+//   ref_driver schedule <eta_max> <iter_max> <iter_lr> <eps>     the reference schedule as hex floats
 // keys: threads iter_max iter_lr updates_x (U = updates_x * sum steps) updates (absolute U) delta eps
 //       eta_max theta space space_max space_q cooling order(0/1)
 #include <atomic>
@@ -128,7 +129,7 @@ static void flatten(const graph_t& g, const std::vector<path_handle_t>& paths, s
 static int cmd_dump(int argc, char** argv) {
     if (argc < 4) return 2;
     Loaded L;
-    load(argv[2], 2, L, true);
+    load(argv[2], 1, L, true);  // 1 thread: the per-node step slots (hence XP's node-major order) depend on loader interleaving
     std::vector<uint32_t> node_len, step_node;
     std::vector<uint64_t> path_first, step_pos;
     std::vector<uint8_t> step_rev;
@@ -139,7 +140,10 @@ static int cmd_dump(int argc, char** argv) {
     std::vector<uint64_t> xp_nr(nr.size()), xp_npi(npi.size());
     for (uint64_t i = 0; i < nr.size(); ++i) { xp_nr[i] = nr[i]; xp_npi[i] = npi[i]; }
     std::vector<uint64_t> xp_pos, xp_handle, xp_path_id, xp_path_len;
+    std::vector<uint8_t> path_names;  // '\n'-joined, in path order
     for (auto& p : L.paths) {
+        for (char ch : L.graph.get_path_name(p)) path_names.push_back((uint8_t) ch);
+        path_names.push_back((uint8_t) '\n');
         uint64_t c = L.xp.get_path_step_count(p);
         xp_path_id.push_back(as_integer(p));
         xp_path_len.push_back(L.xp.get_path_length(p));
@@ -163,6 +167,7 @@ static int cmd_dump(int argc, char** argv) {
     w.add("xp_handle_of_step", xp_handle);
     w.add("xp_path_id", xp_path_id);
     w.add("xp_path_length", xp_path_len);
+    w.add("path_names", path_names);
     w.close();
     std::cout << "{\"nodes\": " << node_len.size() << ", \"paths\": " << L.paths.size() << ", \"steps\": " << step_node.size() << "}" << std::endl;
     return 0;
@@ -277,6 +282,18 @@ static int cmd_sort(int argc, char** argv) {
     return 0;
 }
 
+// prints the reference's learning-rate schedule (path_sgd_layout.cpp:433-468) as exact hex floats
+static int cmd_schedule(int argc, char** argv) {
+    if (argc < 6) return 2;
+    double eta_max = std::stod(argv[2]);
+    uint64_t iter_max = std::stoull(argv[3]), iter_lr = std::stoull(argv[4]);
+    double eps = std::stod(argv[5]);
+    double w_min = (double) 1.0 / (double) (eta_max);  // as the caller computes it, path_sgd_layout.cpp:75
+    std::vector<double> etas = algorithms::path_linear_sgd_layout_schedule(w_min, 1.0, iter_max, iter_lr, eps);
+    for (double e : etas) std::printf("%a\n", e);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) { std::cerr << "usage: ref_driver dump|layout|sort ..." << std::endl; return 2; }
     std::string cmd = argv[1];
@@ -284,6 +301,7 @@ int main(int argc, char** argv) {
         if (cmd == "dump") return cmd_dump(argc, argv);
         if (cmd == "layout") return cmd_layout(argc, argv);
         if (cmd == "sort") return cmd_sort(argc, argv);
+        if (cmd == "schedule") return cmd_schedule(argc, argv);
     } catch (const std::exception& e) {
         std::cerr << "[ref_driver] error: " << e.what() << std::endl;
         return 1;
