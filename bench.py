@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — M node-pair SGD updates/s of the 2D PG-SGD hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|mid|small|chr6.C4|DRB1-3123] [--impl ours|reference]
+
+A "step" is one cooling-schedule iteration of `odgi layout` = ONE persistent-grid kernel launch that
+performs min_term_updates = 10 * S term updates (layout_main.cpp:258).  Default workload "c4": the synthetic
+90-haplotype chr6-MHC-scale graph of BASELINE config 4 (~5.5e6 nodes, ~4.2e8 path steps; odgi_b200/synth.py,
+seed 42) — the configuration north_star quotes the metric on and the largest single-GPU one; its 6.7 GB of
+step records do not fit the 126 MB L2, so every timed step reads its inputs from HBM (no flush needed).
+
+value  : whole-job updates/s with the graph + coordinates resident in HBM; device time from CUDA events on the
+         stream the kernels run on (pgsgd_stats.seconds_iterations), max over ranks.
+e2e    : the same metric through the reference-facing C-ABI sequence with HOST buffers (what odgi's shim calls):
+         flatten-to-device upload of the graph from pinned host memory, coordinate upload, the same K steps,
+         coordinate download — host wall clock, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_UPDATE_2D = 80  # algorithmic bytes per 2D term update
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def pinned_like(a: np.ndarray) -> np.ndarray:
+    """copy into pinned host memory (torch is only the allocator here)"""
+    import torch
+    t = torch.empty(a.shape, dtype=getattr(torch, {"uint8": "uint8", "uint32": "int32", "uint64": "int64", "float64": "float64",
+                                                  "float32": "float32"}[a.dtype.name]), pin_memory=True)
+    v = t.numpy().view(a.dtype)
+    v[...] = a
+    return v, t  # the caller keeps t alive
+
+
+def make_workload(name: str):
+    import odgi_b200
+    from odgi_b200 import synth
+    if name in synth.PRESETS:
+        g = synth.preset(name, seed=42)
+        desc = f"synthetic '{name}' (odgi_b200/synth.py seed 42)"
+    else:
+        g = odgi_b200.load_graph_arrays(os.path.join(ROOT, "tests", "golden", f"{name}.graph.arr.gz"))
+        desc = f"test/{name}.gfa (flattened fixture)"
+    return g, desc
+
+
+def cpu_baseline(workload: str, threads: int, seconds_budget: float = 25.0):
+    """Reference CPU implementation on the host cores, on a bounded sample of the workload.
+    kind 'reference' = the unmodified reference compiled into oracle/_ref (std::thread workers, -Ofast);
+    falls back to kind 'port' (the oracle's C restatement, one core) when oracle/_ref was not built."""
+    from odgi_b200 import synth
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver_fast")
+    if not os.path.exists(ref):
+        ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if workload in synth.PRESETS:
+        n_sites, n_paths = synth.PRESETS[workload]
+        n_sites = min(n_sites, 30_000)  # bounded sample: same generator, same haplotype count, fewer sites
+        g = synth.generate(n_sites, n_paths, seed=42)
+        sample = f"same generator, {n_paths} paths x {n_sites} sites (S={g.S}), 2 iterations of 10*S updates"
+    else:
+        import odgi_b200
+        g = odgi_b200.load_graph_arrays(os.path.join(ROOT, "tests", "golden", f"{workload}.graph.arr.gz"))
+        sample = f"the whole graph (S={g.S}), 2 iterations of 10*S updates"
+    if os.path.exists(ref):
+        with tempfile.TemporaryDirectory() as tmp:
+            gfa = os.path.join(tmp, "sample.gfa")
+            synth.write_gfa(g, gfa)
+            out = os.path.join(tmp, "o.arr")
+            r = subprocess.run([ref, "layout", gfa, "-", out, f"threads={threads}", "iter_max=2"], cwd=tmp, capture_output=True,
+                               text=True, timeout=600)
+            if r.returncode == 0:
+                info = json.loads(r.stdout.strip().splitlines()[-1])
+                return {"value": info["updates_per_sec"] / 1e6, "unit": "M updates/s", "cores": threads, "kind": "reference",
+                        "sample": sample + f"; {os.path.basename(ref)} (reference sources, -Ofast)", "seconds": info["seconds"]}
+    from oracle import oracle as orc
+    go = orc.Graph(g.node_len, g.path_first_step, g.step_node, g.step_rev)
+    cfg = orc.default_layout_config(go, iter_max=2)
+    X, Y = orc.layout_init(go, 42)
+    t0 = time.time()
+    n, _, _ = orc.layout_2d(go, cfg, X, Y, n_streams=1)
+    dt = time.time() - t0
+    return {"value": n / dt / 1e6, "unit": "M updates/s", "cores": 1, "kind": "port", "sample": sample + "; oracle C restatement", "seconds": dt}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    g, desc = make_workload(args.workload) if args.workload not in ("c4", "mid") else (None, None)
+    # each step = one iteration over a bounded sample; (steps + warmup) iterations in one reference invocation
+    t0 = time.time()
+    cb = cpu_baseline(args.workload, threads)
+    line = {"impl": "reference", "metric": "M node-pair SGD updates/sec", "value": cb["value"], "unit": "M updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "sample": cb["sample"]},
+            "cpu_baseline": {"value": cb["value"], "unit": cb["unit"], "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
+            "e2e": {"value": cb["value"], "unit": "M updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.time() - t0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=0)
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import odgi_b200
+    from odgi_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and not (world == 1 and args.gpus == 1):
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    import torch
+    if not torch.cuda.is_available() or odgi_b200.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback on the hot path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    g, desc = make_workload(args.workload)
+    W, K = args.warmup, args.steps
+    iter_max = max(30, W + K)
+    cfg = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags)
+    X0, Y0 = odgi_b200.layout_init(g, seed=42)
+    U = cfg.min_term_updates
+
+    uid = None
+    if world > 1:
+        obj = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        uid = obj[0]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident measurement ("value") ----
+    e = odgi_b200.Engine(g, device=local_rank)
+    if uid is not None:
+        e.attach_comm(uid, world, rank)
+    e.set_coords_2d(X0, Y0)
+    barrier()
+    e.run_range(cfg, 2, 0, W)                      # W untimed warm-up steps (iterations 0..W-1 of the schedule)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.time()
+    st = e.run_range(cfg, 2, W, W + K)             # exactly K timed steps
+    torch.cuda.synchronize()
+    wall = time.time() - t0
+    barrier()
+    clocks = sampler.stop()
+    dev_s = max_over_ranks(st["seconds_iterations"])
+    assert st["iterations_run"] == K and st["kernel_launches"] == K
+    total_updates = K * U
+    value = total_updates / dev_s / 1e6
+    Xf, Yf = e.get_coords_2d()
+    finite = bool(np.all(np.isfinite(Xf)) and np.all(np.isfinite(Yf)))
+    dev_bytes = e.device_bytes
+    e.close()
+
+    # ---- end-to-end through the C-ABI with host buffers ("e2e") ----
+    e2e = None
+    if not args.no_e2e:
+        keep = []
+        def pin(a):
+            v, t = pinned_like(a)
+            keep.append(t)
+            return v
+        gp = capi.FlatGraph(pin(g.node_len), pin(g.path_first_step), pin(g.step_node), None if g.step_rev is None else pin(g.step_rev),
+                            None if g.step_pos is None else pin(g.step_pos))
+        Xp, Yp = pin(X0), pin(Y0)
+        cfg_e = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags)
+        barrier()
+        t0 = time.time()
+        e2 = odgi_b200.Engine(gp, device=local_rank)        # flatten-to-device upload
+        if uid is not None:
+            obj = [capi.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0)
+            e2.attach_comm(obj[0], world, rank)
+        e2.set_coords_2d(Xp, Yp)                            # coordinate upload
+        st2 = e2.run_range(cfg_e, 2, 0, K)                  # the same number of steps
+        Xo, Yo = e2.get_coords_2d()                         # result download
+        t_e2e = max_over_ranks(time.time() - t0)
+        h2d = st2["h2d_bytes"]
+        e2.close()
+        e2e = {"value": K * U / t_e2e / 1e6, "unit": "M updates/s", "h2d_bytes_per_step": h2d / K,
+               "d2h_bytes_per_step": 4 * g.N * 8 / K, "seconds": t_e2e, "steps_in_call": K,
+               "note": "one engine lifetime: graph flatten+upload from pinned host memory, coords up, K steps, coords down; host wall clock"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    step_s = dev_s / K
+    achieved = (U / world) * BYTES_PER_UPDATE_2D / step_s / 1e9   # per-GPU kernel: its share of the step's updates
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(args.workload)
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = cpu_baseline(args.workload, os.cpu_count() or 1)
+        except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
+            cb = {"value": None, "unit": "M updates/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    line = {
+        "metric": "M node-pair SGD updates/sec", "value": value, "unit": "M updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic" if args.workload in ("c4", "mid", "small", "tiny") else "reference test graph (flattened fixture)",
+        "config": {"workload": args.workload, "description": desc, "nodes": g.N, "paths": g.P, "steps_in_graph": g.S,
+                   "updates_per_step": U, "iter_max": iter_max, "timed_iterations": [W, W + K], "batch": args.batch or 4,
+                   "l2_policy": "inputs larger than L2" if g.S * 16 > 126e6 else "L2-resident graph (plumbing config)",
+                   "parallelism": f"replicated coords, term updates split over {world} GPU(s), 1 NCCL all-reduce/step" if world > 1 else "1 GPU",
+                   "device_bytes": dev_bytes, "coords_finite": finite},
+        "gpu_launches": K * world,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "bytes_per_update": BYTES_PER_UPDATE_2D,
+                     "kernel": "pgsgd_iter_kernel<2,BATCH,smem_paths>", "kernel_ms": step_s * 1e3},
+        "clocks": clocks, "wall_s_timed_region": wall,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if cb:
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

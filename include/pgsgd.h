@@ -1,0 +1,158 @@
+/* pgsgd.h — C-ABI of the B200-native path-guided SGD (PG-SGD) engine.
+ *
+ * This is the drop-in boundary for odgi's GPU layout path.  Every entry point is `extern "C"` with
+ * plain pointers and sizes; the reference interface each one replaces is cited (paths relative to the
+ * odgi tree).  The odgi-side C++ shim that calls these (same signatures as the reference's
+ * path_linear_sgd_layout_gpu / a new path_linear_sgd_gpu) is odgi_b200/host/odgi_shim.cpp; the
+ * binding a maintainer adds is shown in INTEGRATION.md.
+ *
+ * Memory: host arrays are caller-owned.  Device memory is owned by the opaque engine handle.
+ * Errors: every function returns PGSGD_OK (0) or a negative status; pgsgd_last_error() gives the
+ * message (thread-local).  There is NO CPU fallback: without a usable CUDA device every compute entry
+ * point fails with PGSGD_ERR_CUDA.
+ */
+#ifndef PGSGD_H
+#define PGSGD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGSGD_VERSION 100 /* 0.1.0 */
+
+typedef enum pgsgd_status {
+    PGSGD_OK = 0,
+    PGSGD_ERR_ARG = -1,      /* bad argument / inconsistent graph view */
+    PGSGD_ERR_CUDA = -2,     /* CUDA runtime error (incl. "no device") */
+    PGSGD_ERR_NCCL = -3,     /* NCCL error */
+    PGSGD_ERR_NOMEM = -4,    /* host or device allocation failed */
+    PGSGD_ERR_STATE = -5,    /* call sequence error (e.g. run before coordinates were set) */
+    PGSGD_ERR_UNOPT = -6     /* graph ids are not compacted 1..N (reference: src/cuda/layout.cu:320-323) */
+} pgsgd_status;
+
+/* Flattened, path-major view of an odgi graph.  Replaces what cuda::gpu_layout builds for itself in
+ * managed memory (src/cuda/layout.cu:325-410: node_t[], path_t[], path_element_t[]) and what the CPU
+ * workers read through xp::XP (src/algorithms/xp.cpp:375-436).
+ *   node rank   = node id - 1                              (src/odgi.cpp:35-42, graph must be optimized)
+ *   step s of path p lives at index path_first_step[p] + rank_in_path
+ *   step_pos    = 0-based bp offset of the step's node start in its path == XP get_position_of_step
+ *                 (xp.cpp:393-397); may be NULL, then it is derived from node_len (xp.cpp:607-616)
+ *   step_rev    = 1 when the step traverses the node in reverse (handle is_reverse); may be NULL (all forward)
+ */
+typedef struct pgsgd_graph_view {
+    uint64_t node_count;              /* N */
+    uint64_t path_count;              /* P */
+    uint64_t step_count;              /* S = path_first_step[P] */
+    const uint32_t* node_len;         /* [N] sequence length of each node, bp */
+    const uint64_t* path_first_step;  /* [P+1] prefix sums of per-path step counts */
+    const uint32_t* step_node;        /* [S] node rank of each step */
+    const uint8_t*  step_rev;         /* [S] or NULL */
+    const uint64_t* step_pos;         /* [S] or NULL */
+} pgsgd_graph_view;
+
+/* PG-SGD parameters: the argument list of algorithms::path_linear_sgd_layout[_gpu]
+ * (src/algorithms/path_sgd_layout.hpp:37-79) / path_linear_sgd (src/algorithms/path_sgd.cpp:12-31),
+ * i.e. a superset of cuda::layout_config_t (src/cuda/layout.h:65-77). */
+typedef struct pgsgd_config {
+    uint64_t iter_max;                     /* 2D runs iter_max iterations, 1D runs iter_max+1 (path_sgd.cpp:181) */
+    uint64_t iter_with_max_learning_rate;
+    uint64_t min_term_updates;             /* term updates per iteration (whole job, all GPUs) */
+    double   delta;                        /* early stop threshold on max |Delta| per iteration; 0 = never */
+    double   eps;
+    double   eta_max;
+    double   theta;                        /* Zipf exponent */
+    uint64_t space;                        /* max Zipf jump, in steps */
+    uint64_t space_max;
+    uint64_t space_quantization_step;
+    double   cooling_start;                /* first cooling iteration = floor(cooling_start * iter_max) */
+    uint64_t seed;                         /* worker stream t is seeded seed + t; reference: 9399220 (path_sgd_layout.cpp:168) */
+    uint32_t n_streams;                    /* device worker streams (one per GPU thread); 0 = fill the GPU */
+    uint32_t batch;                        /* terms a stream keeps in flight (1, 2 or 4); 0 = default.
+                                              batch 1 applies a stream's terms strictly in order */
+    uint32_t flags;                        /* PGSGD_FLAG_* */
+    uint32_t reserved;
+} pgsgd_config;
+
+#define PGSGD_FLAG_ATOMIC_ADD   1u  /* accumulate updates with red.global.add instead of Hogwild stores */
+#define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
+
+typedef struct pgsgd_stats {
+    uint64_t iterations_run;
+    uint64_t term_updates;                 /* counted term updates performed by this rank */
+    double   seconds_iterations;           /* device time of the iteration loop (CUDA events), this rank */
+    double   seconds_upload;               /* flatten-to-device + coordinate upload */
+    double   seconds_download;
+    double   last_delta_max;               /* max |Delta| of the last iteration (only tracked when delta > 0) */
+    uint64_t kernel_launches;              /* SGD kernel launches */
+    uint64_t h2d_bytes, d2h_bytes;
+} pgsgd_stats;
+
+typedef struct pgsgd_engine pgsgd_engine;   /* opaque: device-resident graph + coordinates + RNG streams */
+
+const char* pgsgd_last_error(void);
+int         pgsgd_version(void);
+int         pgsgd_device_count(void);       /* 0 when no usable CUDA device */
+
+/* ---- one-shot entry points (host buffers in, host buffers out) ------------------------------------
+ * 2D: replaces  void cuda::gpu_layout(layout_config_t, const odgi::graph_t&, std::vector<std::atomic<double>>& X,
+ *               std::vector<std::atomic<double>>& Y)                       (src/cuda/layout.h:80, layout.cu:290-476)
+ *     X, Y: [2N] in/out, index 2*node_rank + end — the reference's graph_X/graph_Y layout
+ *     (src/subcommand/layout_main.cpp:268-330; path_sgd_layout.cpp:322-323).
+ * 1D: GPU counterpart of  std::vector<double> path_linear_sgd(...)          (src/algorithms/path_sgd.cpp:12-464)
+ *     X: [N] in/out (the reference initialises X itself, path_sgd.cpp:63-69; pass x_is_initialised = 0
+ *     to get that initialisation here), frozen: [N] or NULL = target_nodes of `odgi sort -H` (path_sgd.cpp:290-302). */
+int pgsgd_layout_2d(const pgsgd_graph_view* g, const pgsgd_config* cfg, double* X, double* Y, pgsgd_stats* stats);
+int pgsgd_sort_1d(const pgsgd_graph_view* g, const pgsgd_config* cfg, const uint8_t* frozen, int x_is_initialised,
+                  double* X, pgsgd_stats* stats);
+
+/* ---- engine API (graph stays resident in HBM; used by the one-shot calls, by bench.py and by multi-GPU runs) ---- */
+int  pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** out);
+void pgsgd_engine_destroy(pgsgd_engine* e);
+int  pgsgd_engine_device(const pgsgd_engine* e);
+uint64_t pgsgd_engine_device_bytes(const pgsgd_engine* e);
+
+int pgsgd_engine_set_coords_2d(pgsgd_engine* e, const double* X, const double* Y);     /* [2N] each */
+int pgsgd_engine_get_coords_2d(pgsgd_engine* e, double* X, double* Y);
+int pgsgd_engine_set_coords_2d_f32(pgsgd_engine* e, const float* xy);                   /* [4N] {x0,y0,x1,y1} per node */
+int pgsgd_engine_get_coords_2d_f32(pgsgd_engine* e, float* xy);
+int pgsgd_engine_set_coords_1d(pgsgd_engine* e, const double* X);                       /* [N]; NULL = cumulative-bp init */
+int pgsgd_engine_get_coords_1d(pgsgd_engine* e, double* X);
+int pgsgd_engine_set_frozen_1d(pgsgd_engine* e, const uint8_t* frozen);                 /* [N] or NULL */
+
+/* Run the whole schedule (all iterations) on the engine's device; multi-GPU when a communicator is attached. */
+int pgsgd_engine_run_2d(pgsgd_engine* e, const pgsgd_config* cfg, pgsgd_stats* stats);
+int pgsgd_engine_run_1d(pgsgd_engine* e, const pgsgd_config* cfg, pgsgd_stats* stats);
+/* Iterations [iter_begin, iter_end) of the schedule cfg defines (dims = 2 or 1): lets a caller interleave its own
+ * work (snapshots as `odgi layout -u` takes them, progress, timing) between cooling-schedule steps.  The worker
+ * streams are seeded when iter_begin == 0 and continue otherwise. */
+int pgsgd_engine_run_range(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end,
+                           pgsgd_stats* stats);
+
+/* Multi-GPU (one process per GPU): replicate coordinates, split each iteration's term updates across
+ * ranks, combine with one NCCL all-reduce per iteration.  unique_id is the 128-byte ncclUniqueId obtained
+ * by rank 0 from pgsgd_comm_unique_id and distributed by the caller (torch.distributed / MPI / a file). */
+int pgsgd_comm_unique_id(uint8_t id_out[128]);
+int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int n_ranks, int rank);
+
+/* ---- verification hooks (used by tests; they exercise exactly the device code the runs use) ---- */
+/* The first n_terms draws of worker stream `stream`, produced by the device sampler.  dims = 2 or 1;
+ * cooling / theta_zipf as the iteration would set them.  Outputs are [n_terms] each (any may be NULL);
+ * valid[k] = 0 marks a draw that hit a 1-step path (not counted, path_sgd_layout.cpp:190-192). */
+int pgsgd_engine_sample_terms(pgsgd_engine* e, const pgsgd_config* cfg, int dims, int cooling, double theta_zipf,
+                              uint64_t stream, uint64_t n_terms, uint64_t* step_index, uint32_t* path, uint64_t* rank_a,
+                              uint64_t* rank_b, uint32_t* node_a, uint32_t* node_b, uint64_t* pos_a, uint64_t* pos_b,
+                              uint8_t* end_a, uint8_t* end_b, uint8_t* valid);
+
+/* ---- host-side helpers that mirror reference host code (pure CPU, no device needed) ---- */
+/* learning-rate schedule: path_linear_sgd_layout_schedule (path_sgd_layout.cpp:433-468); writes iter_max+1 */
+int pgsgd_schedule(const pgsgd_config* cfg, double* etas_out);
+/* Zipf zeta table (path_sgd_layout.cpp:87-97); returns the entry count, fills up to cap entries */
+uint64_t pgsgd_zetas(const pgsgd_config* cfg, double* zetas_out, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGSGD_H */

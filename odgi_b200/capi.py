@@ -1,0 +1,351 @@
+"""ctypes binding of the C-ABI (include/pgsgd.h) — the same binding a C/C++ host makes.
+
+There is deliberately no fallback here: if libpgsgd_b200.so is missing or no CUDA device is usable the
+calls raise.  Nothing in this package imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgsgd_b200.so")
+
+PGSGD_FLAG_ATOMIC_ADD = 1
+PGSGD_FLAG_SUM_DELTAS = 2
+
+
+class PgsgdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pgsgd error {code}: {msg}")
+        self.code = code
+
+
+class GraphView(C.Structure):
+    _fields_ = [("node_count", C.c_uint64), ("path_count", C.c_uint64), ("step_count", C.c_uint64),
+                ("node_len", C.c_void_p), ("path_first_step", C.c_void_p), ("step_node", C.c_void_p),
+                ("step_rev", C.c_void_p), ("step_pos", C.c_void_p)]
+
+
+class ConfigC(C.Structure):
+    _fields_ = [("iter_max", C.c_uint64), ("iter_with_max_learning_rate", C.c_uint64), ("min_term_updates", C.c_uint64),
+                ("delta", C.c_double), ("eps", C.c_double), ("eta_max", C.c_double), ("theta", C.c_double),
+                ("space", C.c_uint64), ("space_max", C.c_uint64), ("space_quantization_step", C.c_uint64),
+                ("cooling_start", C.c_double), ("seed", C.c_uint64), ("n_streams", C.c_uint32), ("batch", C.c_uint32),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class StatsC(C.Structure):
+    _fields_ = [("iterations_run", C.c_uint64), ("term_updates", C.c_uint64), ("seconds_iterations", C.c_double),
+                ("seconds_upload", C.c_double), ("seconds_download", C.c_double), ("last_delta_max", C.c_double),
+                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/pgsgd.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "pgsgd_last_error", "pgsgd_version", "pgsgd_device_count", "pgsgd_layout_2d", "pgsgd_sort_1d",
+    "pgsgd_engine_create", "pgsgd_engine_destroy", "pgsgd_engine_device", "pgsgd_engine_device_bytes",
+    "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
+    "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
+    "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
+    "pgsgd_engine_attach_comm", "pgsgd_engine_sample_terms", "pgsgd_schedule", "pgsgd_zetas",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PgsgdError(-2, f"{LIB_PATH} is missing: build it with `python -m odgi_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        vp, u64, i32, dbl = C.c_void_p, C.c_uint64, C.c_int, C.c_double
+        L.pgsgd_last_error.restype = C.c_char_p
+        L.pgsgd_version.restype = i32
+        L.pgsgd_device_count.restype = i32
+        L.pgsgd_layout_2d.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), vp, vp, C.POINTER(StatsC)]
+        L.pgsgd_sort_1d.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), vp, i32, vp, C.POINTER(StatsC)]
+        L.pgsgd_engine_create.argtypes = [C.POINTER(GraphView), i32, C.POINTER(vp)]
+        L.pgsgd_engine_destroy.argtypes = [vp]
+        L.pgsgd_engine_destroy.restype = None
+        L.pgsgd_engine_device.argtypes = [vp]
+        L.pgsgd_engine_device_bytes.argtypes = [vp]
+        L.pgsgd_engine_device_bytes.restype = u64
+        for n in ("pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d"):
+            getattr(L, n).argtypes = [vp, vp, vp]
+        for n in ("pgsgd_engine_set_coords_2d_f32", "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d",
+                  "pgsgd_engine_get_coords_1d", "pgsgd_engine_set_frozen_1d"):
+            getattr(L, n).argtypes = [vp, vp]
+        for n in ("pgsgd_engine_run_2d", "pgsgd_engine_run_1d"):
+            getattr(L, n).argtypes = [vp, C.POINTER(ConfigC), C.POINTER(StatsC)]
+        L.pgsgd_engine_run_range.argtypes = [vp, C.POINTER(ConfigC), i32, u64, u64, C.POINTER(StatsC)]
+        L.pgsgd_comm_unique_id.argtypes = [vp]
+        L.pgsgd_engine_attach_comm.argtypes = [vp, vp, i32, i32]
+        L.pgsgd_engine_sample_terms.argtypes = [vp, C.POINTER(ConfigC), i32, i32, dbl, u64, u64] + [vp] * 11
+        L.pgsgd_schedule.argtypes = [C.POINTER(ConfigC), vp]
+        L.pgsgd_zetas.argtypes = [C.POINTER(ConfigC), vp, u64]
+        L.pgsgd_zetas.restype = u64
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise PgsgdError(rc, lib().pgsgd_last_error().decode())
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class Config:
+    """Argument list of the reference's path_linear_sgd_layout[_gpu] / path_linear_sgd
+    (path_sgd_layout.hpp:37-79, path_sgd.cpp:12-31) plus the device knobs."""
+    iter_max: int = 30
+    iter_with_max_learning_rate: int = 0
+    min_term_updates: int = 0
+    delta: float = 0.0
+    eps: float = 0.01
+    eta_max: float = 0.0
+    theta: float = 0.99
+    space: int = 0
+    space_max: int = 1000
+    space_quantization_step: int = 100
+    cooling_start: float = 0.5
+    seed: int = 9399220
+    n_streams: int = 0
+    batch: int = 0
+    flags: int = 0
+
+    def c(self) -> ConfigC:
+        return ConfigC(self.iter_max, self.iter_with_max_learning_rate, self.min_term_updates, self.delta, self.eps,
+                       self.eta_max, self.theta, self.space, self.space_max, self.space_quantization_step,
+                       self.cooling_start, self.seed, self.n_streams, self.batch, self.flags, 0)
+
+
+@dataclass
+class FlatGraph:
+    """Host-side flattened graph (path-major SoA), the input of the C-ABI."""
+    node_len: np.ndarray
+    path_first_step: np.ndarray
+    step_node: np.ndarray
+    step_rev: Optional[np.ndarray] = None
+    step_pos: Optional[np.ndarray] = None
+    path_names: list = field(default_factory=list)
+
+    def __post_init__(self):
+        self.node_len = np.ascontiguousarray(self.node_len, dtype=np.uint32)
+        self.path_first_step = np.ascontiguousarray(self.path_first_step, dtype=np.uint64)
+        self.step_node = np.ascontiguousarray(self.step_node, dtype=np.uint32)
+        if self.step_rev is not None:
+            self.step_rev = np.ascontiguousarray(self.step_rev, dtype=np.uint8)
+        if self.step_pos is not None:
+            self.step_pos = np.ascontiguousarray(self.step_pos, dtype=np.uint64)
+
+    @property
+    def N(self) -> int:
+        return int(self.node_len.size)
+
+    @property
+    def P(self) -> int:
+        return int(self.path_first_step.size - 1)
+
+    @property
+    def S(self) -> int:
+        return int(self.step_node.size)
+
+    @property
+    def max_path_steps(self) -> int:
+        return int(np.diff(self.path_first_step.astype(np.int64)).max()) if self.P else 0
+
+    @property
+    def max_path_bp(self) -> int:
+        """longest path in bp (`odgi sort` uses it as the Zipf space, sort_main.cpp:387)"""
+        lens = self.node_len[self.step_node].astype(np.uint64)
+        csum = np.concatenate([[0], np.cumsum(lens, dtype=np.uint64)])
+        f = self.path_first_step.astype(np.int64)
+        return int((csum[f[1:]] - csum[f[:-1]]).max()) if self.P else 0
+
+    def view(self) -> GraphView:
+        return GraphView(self.N, self.P, self.S, _ptr(self.node_len), _ptr(self.path_first_step), _ptr(self.step_node),
+                         _ptr(self.step_rev), _ptr(self.step_pos))
+
+
+def layout_defaults(g: FlatGraph, **kw) -> Config:
+    """`odgi layout` defaults (layout_main.cpp:198-266): 30 iterations of 10*S updates, eta_max = max_steps^2,
+    Zipf space = max path steps, space_max 1000, quantization 100, cooling 0.5."""
+    ms = g.max_path_steps
+    c = Config(iter_max=30, min_term_updates=10 * g.S, eta_max=float(ms) * float(ms), space=ms, space_max=1000,
+               space_quantization_step=100)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def sort_defaults(g: FlatGraph, **kw) -> Config:
+    """`odgi sort -Y` defaults (sort_main.cpp:313-414): 100(+1) iterations of 1*S updates, Zipf space = longest
+    path in bp, space_max 100, quantization step derived so that about 100 zeta entries exist."""
+    ms = g.max_path_steps
+    space = g.max_path_bp
+    space_max = 100
+    max_dists = max(space_max + 1, 100)
+    q = max(2, int(np.ceil((space - space_max) / (max_dists - space_max))))
+    c = Config(iter_max=100, min_term_updates=g.S, eta_max=float(ms) * float(ms), space=space, space_max=space_max,
+               space_quantization_step=q)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def device_count() -> int:
+    return int(lib().pgsgd_device_count())
+
+
+def schedule(cfg: Config) -> np.ndarray:
+    etas = np.zeros(cfg.iter_max + 1, dtype=np.float64)
+    cc = cfg.c()
+    _check(lib().pgsgd_schedule(C.byref(cc), _ptr(etas)))
+    return etas
+
+
+def zetas(cfg: Config) -> np.ndarray:
+    cc = cfg.c()
+    n = lib().pgsgd_zetas(C.byref(cc), None, 0)
+    z = np.zeros(n, dtype=np.float64)
+    lib().pgsgd_zetas(C.byref(cc), _ptr(z), n)
+    return z
+
+
+class Engine:
+    """Device-resident graph + coordinates (pgsgd_engine)."""
+
+    def __init__(self, g: FlatGraph, device: int = 0):
+        self.g = g
+        self._h = C.c_void_p()
+        gv = g.view()
+        _check(lib().pgsgd_engine_create(C.byref(gv), device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().pgsgd_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def device_bytes(self) -> int:
+        return int(lib().pgsgd_engine_device_bytes(self._h))
+
+    def set_coords_2d(self, X, Y):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        assert X.size == 2 * self.g.N and Y.size == 2 * self.g.N
+        _check(lib().pgsgd_engine_set_coords_2d(self._h, _ptr(X), _ptr(Y)))
+
+    def get_coords_2d(self):
+        X = np.empty(2 * self.g.N, dtype=np.float64)
+        Y = np.empty(2 * self.g.N, dtype=np.float64)
+        _check(lib().pgsgd_engine_get_coords_2d(self._h, _ptr(X), _ptr(Y)))
+        return X, Y
+
+    def set_coords_2d_f32(self, xy):
+        xy = np.ascontiguousarray(xy, dtype=np.float32)
+        assert xy.size == 4 * self.g.N
+        _check(lib().pgsgd_engine_set_coords_2d_f32(self._h, _ptr(xy)))
+
+    def get_coords_2d_f32(self):
+        xy = np.empty(4 * self.g.N, dtype=np.float32)
+        _check(lib().pgsgd_engine_get_coords_2d_f32(self._h, _ptr(xy)))
+        return xy
+
+    def set_coords_1d(self, X=None):
+        if X is not None:
+            X = np.ascontiguousarray(X, dtype=np.float64)
+            assert X.size == self.g.N
+        _check(lib().pgsgd_engine_set_coords_1d(self._h, _ptr(X)))
+
+    def get_coords_1d(self):
+        X = np.empty(self.g.N, dtype=np.float64)
+        _check(lib().pgsgd_engine_get_coords_1d(self._h, _ptr(X)))
+        return X
+
+    def set_frozen_1d(self, frozen):
+        f = None if frozen is None else np.ascontiguousarray(frozen, dtype=np.uint8)
+        _check(lib().pgsgd_engine_set_frozen_1d(self._h, _ptr(f)))
+
+    def run_2d(self, cfg: Config) -> dict:
+        st, cc = StatsC(), cfg.c()
+        _check(lib().pgsgd_engine_run_2d(self._h, C.byref(cc), C.byref(st)))
+        return st.as_dict()
+
+    def run_1d(self, cfg: Config) -> dict:
+        st, cc = StatsC(), cfg.c()
+        _check(lib().pgsgd_engine_run_1d(self._h, C.byref(cc), C.byref(st)))
+        return st.as_dict()
+
+    def run_range(self, cfg: Config, dims: int, iter_begin: int, iter_end: int) -> dict:
+        st, cc = StatsC(), cfg.c()
+        _check(lib().pgsgd_engine_run_range(self._h, C.byref(cc), dims, iter_begin, iter_end, C.byref(st)))
+        return st.as_dict()
+
+    def attach_comm(self, unique_id: bytes, n_ranks: int, rank: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().pgsgd_engine_attach_comm(self._h, buf, n_ranks, rank))
+
+    def sample_terms(self, cfg: Config, dims: int, cooling: bool, n_terms: int, stream: int = 0, theta_zipf=None):
+        out = {"step_index": np.zeros(n_terms, np.uint64), "path": np.zeros(n_terms, np.uint32),
+               "rank_a": np.zeros(n_terms, np.uint64), "rank_b": np.zeros(n_terms, np.uint64),
+               "node_a": np.zeros(n_terms, np.uint32), "node_b": np.zeros(n_terms, np.uint32),
+               "pos_a": np.zeros(n_terms, np.uint64), "pos_b": np.zeros(n_terms, np.uint64),
+               "end_a": np.zeros(n_terms, np.uint8), "end_b": np.zeros(n_terms, np.uint8),
+               "valid": np.zeros(n_terms, np.uint8)}
+        cc = cfg.c()
+        th = cfg.theta if theta_zipf is None else theta_zipf
+        _check(lib().pgsgd_engine_sample_terms(self._h, C.byref(cc), dims, int(cooling), th, stream, n_terms,
+                                               *[_ptr(out[k]) for k in ("step_index", "path", "rank_a", "rank_b", "node_a",
+                                                                        "node_b", "pos_a", "pos_b", "end_a", "end_b", "valid")]))
+        return out
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    _check(lib().pgsgd_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def layout_2d(g: FlatGraph, cfg: Config, X, Y):
+    """One-shot pgsgd_layout_2d: host buffers in/out (the call odgi's shim makes)."""
+    X = np.ascontiguousarray(X, dtype=np.float64).copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).copy()
+    st, cc, gv = StatsC(), cfg.c(), g.view()
+    _check(lib().pgsgd_layout_2d(C.byref(gv), C.byref(cc), _ptr(X), _ptr(Y), C.byref(st)))
+    return X, Y, st.as_dict()
+
+
+def sort_1d(g: FlatGraph, cfg: Config, X=None, frozen=None):
+    """One-shot pgsgd_sort_1d."""
+    init = X is not None
+    X = np.ascontiguousarray(X, dtype=np.float64).copy() if init else np.zeros(g.N, dtype=np.float64)
+    f = None if frozen is None else np.ascontiguousarray(frozen, dtype=np.uint8)
+    st, cc, gv = StatsC(), cfg.c(), g.view()
+    _check(lib().pgsgd_sort_1d(C.byref(gv), C.byref(cc), _ptr(f), int(init), _ptr(X), C.byref(st)))
+    return X, st.as_dict()

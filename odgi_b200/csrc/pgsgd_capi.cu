@@ -1,0 +1,722 @@
+// pgsgd_capi.cu — the C-ABI (include/pgsgd.h): engine lifetime, schedule, launches, NCCL combine.
+//
+// Host-side logic mirrored from the reference (cited inline): the learning-rate schedule
+// (path_sgd_layout.cpp:433-468), the Zipf zeta table (path_sgd_layout.cpp:87-97), the iteration / cooling
+// state machine (path_sgd_layout.cpp:120-163, path_sgd.cpp:161-203, layout.cu:442-447) and the flattening
+// that cuda::gpu_layout does for itself (layout.cu:325-410).
+#include "../../include/pgsgd.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include "pgsgd_kernels.cuh"
+
+using namespace pgsgd;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t _e = (call);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return fail(_e == cudaErrorMemoryAllocation ? PGSGD_ERR_NOMEM : PGSGD_ERR_CUDA, "%s:%d: %s: %s", \
+                        __FILE__, __LINE__, #call, cudaGetErrorString(_e));                                   \
+    } while (0)
+
+#define NC(call)                                                                                         \
+    do {                                                                                                 \
+        ncclResult_t _r = (call);                                                                        \
+        if (_r != ncclSuccess)                                                                           \
+            return fail(PGSGD_ERR_NCCL, "%s:%d: %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(_r)); \
+    } while (0)
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// dirtyzipf::fast_precise_pow on the host (deps/dirtyzipf/dirty_zipfian_int_distribution.h:82-104); the
+// device twin is pgsgd::fast_precise_pow in pgsgd_device.cuh
+double host_fast_precise_pow(double a, double b) {
+    int e = (int) b;
+    union { double d; int x[2]; } u;
+    u.d = a;
+    u.x[1] = (int) ((b - e) * (u.x[1] - 1072632447) + 1072632447);
+    u.x[0] = 0;
+    double r = 1.0;
+    while (e) {
+        if (e & 1) r *= a;
+        a *= a;
+        e >>= 1;
+    }
+    return r * u.d;
+}
+
+uint64_t zeta_table_size(const pgsgd_config& c) {
+    return (c.space <= c.space_max ? c.space : c.space_max + (c.space - c.space_max) / c.space_quantization_step + 1) + 1;
+}
+
+ZipfConst make_zipf_const(double theta) {
+    ZipfConst z;
+    z.theta = theta;
+    z.one_minus_theta = 1 - theta;
+    z.alpha = 1 / (1 - theta);
+    z.zeta2 = host_fast_precise_pow(1.0 / 1, theta) + host_fast_precise_pow(1.0 / 2, theta);  // zeta(2, theta)
+    z.thresh2 = 1.0 + host_fast_precise_pow(0.5, theta);
+    return z;
+}
+
+int check_config(const pgsgd_config* c) {
+    if (!c) return fail(PGSGD_ERR_ARG, "config is NULL");
+    if (c->iter_max == 0) return fail(PGSGD_ERR_ARG, "iter_max must be > 0");
+    if (c->space_quantization_step == 0) return fail(PGSGD_ERR_ARG, "space_quantization_step must be > 0");
+    if (!(c->theta > 0.0 && c->theta < 1.0)) return fail(PGSGD_ERR_ARG, "theta must be in (0,1)");
+    if (!(c->eta_max > 0.0)) return fail(PGSGD_ERR_ARG, "eta_max must be > 0");
+    if (c->batch != 0 && c->batch != 1 && c->batch != 2 && c->batch != 4) return fail(PGSGD_ERR_ARG, "batch must be 0, 1, 2 or 4");
+    return PGSGD_OK;
+}
+
+}  // namespace
+
+struct pgsgd_engine {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t N = 0, P = 0, S = 0;
+    uint64_t max_path_steps = 0;
+    bool any_multi_step_path = false;
+    StepRec* d_steps = nullptr;
+    uint64_t* d_path_first = nullptr;
+    float* d_xy = nullptr;        // 2D coordinates
+    float* d_xy_prev = nullptr;   // multi-GPU sum-of-deltas scratch
+    double* d_x1d = nullptr;      // 1D coordinates
+    double* d_x1d_prev = nullptr;
+    uint8_t* d_frozen = nullptr;
+    double* d_zetas = nullptr;
+    uint64_t zetas_cap = 0;
+    uint64_t* d_rng = nullptr;
+    uint64_t rng_stride = 0;
+    uint64_t rng_streams = 0;     // streams seeded by the run in progress
+    unsigned int* d_delta = nullptr;
+    unsigned long long* d_counted = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<double> h_x1d_default;  // cumulative bp of the node order (path_sgd.cpp:63-69)
+    bool have_2d = false, have_1d = false;
+    uint64_t bytes = 0;
+    double seconds_upload = 0;
+    uint64_t h2d_bytes = 0;
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(pgsgd_engine* e, T** p, uint64_t count) {
+    if (count == 0) count = 1;
+    cudaError_t err = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+    if (err != cudaSuccess) return fail(PGSGD_ERR_NOMEM, "cudaMalloc of %llu bytes failed: %s", (unsigned long long) (count * sizeof(T)), cudaGetErrorString(err));
+    e->bytes += count * sizeof(T);
+    return PGSGD_OK;
+}
+
+int ensure_zetas(pgsgd_engine* e, const std::vector<double>& z) {
+    if (z.size() > e->zetas_cap) {
+        if (e->d_zetas) cudaFree(e->d_zetas);
+        e->d_zetas = nullptr;
+        int rc = dev_alloc(e, &e->d_zetas, z.size());
+        if (rc) return rc;
+        e->zetas_cap = z.size();
+    }
+    CU(cudaMemcpyAsync(e->d_zetas, z.data(), z.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    return PGSGD_OK;
+}
+
+int ensure_rng(pgsgd_engine* e, uint64_t n_streams) {
+    if (n_streams > e->rng_stride) {
+        if (e->d_rng) cudaFree(e->d_rng);
+        e->d_rng = nullptr;
+        int rc = dev_alloc(e, &e->d_rng, 4 * n_streams);
+        if (rc) return rc;
+        e->rng_stride = n_streams;
+    }
+    return PGSGD_OK;
+}
+
+std::vector<double> build_zetas(const pgsgd_config& c) {
+    // path_sgd_layout.cpp:87-97
+    std::vector<double> zetas(zeta_table_size(c), 0.0);
+    double zeta_tmp = 0.0;
+    for (uint64_t i = 1; i < c.space + 1; i++) {
+        zeta_tmp += host_fast_precise_pow(1.0 / i, c.theta);
+        if (i <= c.space_max) zetas[i] = zeta_tmp;
+        if (i >= c.space_max && (i - c.space_max) % c.space_quantization_step == 0) {
+            zetas[c.space_max + 1 + (i - c.space_max) / c.space_quantization_step] = zeta_tmp;
+        }
+    }
+    return zetas;
+}
+
+std::vector<double> build_schedule(const pgsgd_config& c) {
+    // path_linear_sgd_layout_schedule (path_sgd_layout.cpp:433-468) with w_min = 1/eta_max, w_max = 1 (:75-84)
+    const double w_min = (double) 1.0 / (double) (c.eta_max);
+    const double w_max = 1.0;
+    const double eta_max = 1.0 / w_min;
+    const double eta_min = c.eps / w_max;
+    const double lambda = log(eta_max / eta_min) / ((double) c.iter_max - 1);
+    std::vector<double> etas;
+    etas.reserve(c.iter_max + 1);
+    for (int64_t t = 0; t <= (int64_t) c.iter_max; t++) {
+        etas.push_back(eta_max * exp(-lambda * (double) (std::llabs(t - (int64_t) c.iter_with_max_learning_rate))));
+    }
+    return etas;
+}
+
+// the iteration loop shared by 2D and 1D
+// iterations [iter_begin, iter_end) of the schedule cfg defines; iter_end == UINT64_MAX means "to the end"
+int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end, pgsgd_stats* stats) {
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (dims == 2 && !e->have_2d) return fail(PGSGD_ERR_STATE, "2D coordinates were not set (pgsgd_engine_set_coords_2d)");
+    if (dims == 1 && !e->have_1d) return fail(PGSGD_ERR_STATE, "1D coordinates were not set (pgsgd_engine_set_coords_1d)");
+    CU(cudaSetDevice(e->device));
+    pgsgd_stats st;
+    memset(&st, 0, sizeof(st));
+    st.seconds_upload = e->seconds_upload;
+    st.h2d_bytes = e->h2d_bytes;
+    // the reference does nothing when no path has more than one step (path_sgd_layout.cpp:64-74)
+    if (!e->any_multi_step_path) {
+        if (stats) *stats = st;
+        return PGSGD_OK;
+    }
+    if (cfg->space == 0) return fail(PGSGD_ERR_ARG, "space must be > 0");
+
+    const std::vector<double> etas = build_schedule(*cfg);
+    const std::vector<double> zetas = build_zetas(*cfg);
+    rc = ensure_zetas(e, zetas);
+    if (rc) return rc;
+
+    const uint64_t first_cooling_iteration = (uint64_t) std::floor(cfg->cooling_start * (double) cfg->iter_max);
+    uint64_t n_iters = dims == 1 ? cfg->iter_max + 1 : cfg->iter_max;  // path_sgd.cpp:181 vs path_sgd_layout.cpp:140
+    if (iter_end < n_iters) n_iters = iter_end;
+    if (iter_begin > n_iters) return fail(PGSGD_ERR_ARG, "iter_begin %llu is past the end of the schedule", (unsigned long long) iter_begin);
+
+    // this rank's share of every iteration's term updates
+    const uint64_t U = cfg->min_term_updates;
+    const uint64_t U_rank = U / e->n_ranks + ((uint64_t) e->rank < U % e->n_ranks ? 1 : 0);
+
+    // launch shape: a whole number of resident waves of the persistent grid
+    const int batch = cfg->batch ? (int) cfg->batch : 4;
+    const int block = 256;
+    const size_t smem_need = (e->P + 1) * sizeof(uint64_t);
+    const bool smem_paths = smem_need <= 200 * 1024;
+    const size_t smem = smem_paths ? smem_need : 0;
+    int blocks_per_sm = 0;
+    CU(iteration_occupancy(dims, batch, block, smem, smem_paths, &blocks_per_sm));
+    if (blocks_per_sm < 1) return fail(PGSGD_ERR_CUDA, "iteration kernel does not fit on an SM (smem %zu)", smem);
+    uint64_t n_streams = cfg->n_streams;
+    if (n_streams == 0) {
+        n_streams = (uint64_t) e->sm_count * blocks_per_sm * block;
+        // tiny graphs: keep at least ~64 terms per stream so the launch is not all prologue
+        const uint64_t want = (U_rank + 63) / 64;
+        if (want < n_streams) n_streams = ((want + block - 1) / block) * block;
+        if (n_streams == 0) n_streams = block;
+    }
+    LaunchShape shape;
+    shape.block = n_streams < (uint64_t) block ? (int) ((n_streams + 31) / 32 * 32) : block;
+    shape.grid = (int) ((n_streams + shape.block - 1) / shape.block);
+    shape.smem = smem;
+
+    if (iter_begin == 0 || e->rng_streams != n_streams) {
+        if (iter_begin != 0) return fail(PGSGD_ERR_STATE, "continuing a schedule needs the same n_streams as the call that started it");
+        rc = ensure_rng(e, n_streams);
+        if (rc) return rc;
+        // worker stream t of rank r is the reference's worker thread (r * n_streams + t): seed + tid (path_sgd_layout.cpp:168)
+        CU(launch_seed_streams(e->d_rng, e->rng_stride, n_streams, cfg->seed + (uint64_t) e->rank * n_streams, e->stream));
+        e->rng_streams = n_streams;
+    }
+    CU(cudaMemsetAsync(e->d_counted, 0, sizeof(unsigned long long), e->stream));
+
+    const bool track_delta = cfg->delta > 0;
+    const bool sum_deltas = e->comm && (cfg->flags & PGSGD_FLAG_SUM_DELTAS);
+    if (sum_deltas) {
+        if (dims == 2 && !e->d_xy_prev) { rc = dev_alloc(e, &e->d_xy_prev, 4 * e->N); if (rc) return rc; }
+        if (dims == 1 && !e->d_x1d_prev) { rc = dev_alloc(e, &e->d_x1d_prev, e->N); if (rc) return rc; }
+    }
+
+    IterParams p;
+    memset(&p, 0, sizeof(p));
+    p.sp.path_first = e->d_path_first;
+    p.sp.zetas = e->d_zetas;
+    p.sp.step_count = e->S;
+    p.sp.path_count = (uint32_t) e->P;
+    p.sp.space = cfg->space;
+    p.sp.space_max = cfg->space_max;
+    p.sp.space_q = cfg->space_quantization_step;
+    p.steps = e->d_steps;
+    p.xy = e->d_xy;
+    p.x1d = e->d_x1d;
+    p.frozen = dims == 1 ? e->d_frozen : nullptr;
+    p.rng = e->d_rng;
+    p.rng_stride = e->rng_stride;
+    p.n_streams = n_streams;
+    p.quota_base = U_rank / n_streams;
+    p.quota_rem = U_rank % n_streams;
+    p.delta_max_bits = track_delta ? e->d_delta : nullptr;
+    p.counted = e->d_counted;
+    p.flags = cfg->flags;
+    p.smem_paths = smem_paths ? 1u : 0u;
+
+    CU(cudaEventRecord(e->ev0, e->stream));
+    uint64_t iter = iter_begin;
+    for (; iter < n_iters; ++iter) {
+        p.eta = etas[iter];
+        double theta_zipf = cfg->theta;
+        if (dims == 1) {
+            p.sp.cooling = iter > first_cooling_iteration;   // path_sgd.cpp:194
+            if (p.sp.cooling) theta_zipf = 0.001;            // adj_theta (path_sgd.cpp:195,246); zetas keep the original theta
+        } else {
+            p.sp.cooling = iter >= first_cooling_iteration;  // path_sgd_layout.cpp:153 (adj_theta is unused in 2D, :213)
+        }
+        p.sp.zipf = make_zipf_const(theta_zipf);
+        if (track_delta) CU(cudaMemsetAsync(e->d_delta, 0, sizeof(unsigned int), e->stream));
+        if (sum_deltas) {
+            if (dims == 2) CU(cudaMemcpyAsync(e->d_xy_prev, e->d_xy, 4 * e->N * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+            else CU(cudaMemcpyAsync(e->d_x1d_prev, e->d_x1d, e->N * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+        }
+        CU(launch_iteration(dims, batch, p, shape, e->stream));
+        ++st.kernel_launches;
+        if (e->comm) {
+            // one collective per cooling-schedule step: coordinates are replicated, term updates are sharded
+            if (dims == 2) {
+                if (sum_deltas) {
+                    CU(launch_sub_f32(e->d_xy, e->d_xy, e->d_xy_prev, 4 * e->N, e->stream));
+                    NC(ncclAllReduce(e->d_xy, e->d_xy, 4 * e->N, ncclFloat, ncclSum, e->comm, e->stream));
+                    CU(launch_add_f32(e->d_xy, e->d_xy, e->d_xy_prev, 4 * e->N, e->stream));
+                } else {
+                    NC(ncclAllReduce(e->d_xy, e->d_xy, 4 * e->N, ncclFloat, ncclAvg, e->comm, e->stream));
+                }
+            } else {
+                if (sum_deltas) {
+                    CU(launch_sub_f64(e->d_x1d, e->d_x1d, e->d_x1d_prev, e->N, e->stream));
+                    NC(ncclAllReduce(e->d_x1d, e->d_x1d, e->N, ncclDouble, ncclSum, e->comm, e->stream));
+                    CU(launch_add_f64(e->d_x1d, e->d_x1d, e->d_x1d_prev, e->N, e->stream));
+                } else {
+                    NC(ncclAllReduce(e->d_x1d, e->d_x1d, e->N, ncclDouble, ncclAvg, e->comm, e->stream));
+                }
+            }
+            if (track_delta) NC(ncclAllReduce(e->d_delta, e->d_delta, 1, ncclUint32, ncclMax, e->comm, e->stream));
+        }
+        if (track_delta) {
+            // early stop (checker_lambda: path_sgd_layout.cpp:142, path_sgd.cpp:183): Delta_max <= delta
+            unsigned int bits = 0;
+            CU(cudaMemcpyAsync(&bits, e->d_delta, sizeof(bits), cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaStreamSynchronize(e->stream));
+            float dm;
+            memcpy(&dm, &bits, sizeof(dm));
+            st.last_delta_max = dm;
+            if (iter + 1 < n_iters && (double) dm <= cfg->delta) { ++iter; break; }
+        }
+    }
+    CU(cudaEventRecord(e->ev1, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    unsigned long long counted = 0;
+    CU(cudaMemcpy(&counted, e->d_counted, sizeof(counted), cudaMemcpyDeviceToHost));
+    st.iterations_run = iter - iter_begin;
+    st.term_updates = counted;
+    st.seconds_iterations = ms * 1e-3;
+    if (stats) *stats = st;
+    return PGSGD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pgsgd_last_error(void) { return g_last_error.c_str(); }
+int pgsgd_version(void) { return PGSGD_VERSION; }
+
+int pgsgd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pgsgd_schedule(const pgsgd_config* cfg, double* etas_out) {
+    if (!cfg || !etas_out || cfg->iter_max == 0) return fail(PGSGD_ERR_ARG, "pgsgd_schedule: bad arguments");
+    std::vector<double> etas = build_schedule(*cfg);
+    memcpy(etas_out, etas.data(), etas.size() * sizeof(double));
+    return PGSGD_OK;
+}
+
+uint64_t pgsgd_zetas(const pgsgd_config* cfg, double* zetas_out, uint64_t cap) {
+    if (!cfg || cfg->space_quantization_step == 0) return 0;
+    const uint64_t n = zeta_table_size(*cfg);
+    if (zetas_out) {
+        std::vector<double> z = build_zetas(*cfg);
+        memcpy(zetas_out, z.data(), (n < cap ? n : cap) * sizeof(double));
+    }
+    return n;
+}
+
+int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** out) {
+    if (!g || !out) return fail(PGSGD_ERR_ARG, "pgsgd_engine_create: NULL argument");
+    *out = nullptr;
+    if (!g->node_len || !g->path_first_step || (!g->step_node && g->step_count)) return fail(PGSGD_ERR_ARG, "graph view has NULL arrays");
+    if (g->node_count == 0) return fail(PGSGD_ERR_ARG, "graph has no nodes");
+    if (g->node_count >= (1ull << 31)) return fail(PGSGD_ERR_ARG, "more than 2^31-1 nodes are not supported by the 32-bit handle field");
+    if (g->path_count >= (1ull << 32)) return fail(PGSGD_ERR_ARG, "too many paths");
+    if (g->path_first_step[0] != 0 || g->path_first_step[g->path_count] != g->step_count)
+        return fail(PGSGD_ERR_ARG, "path_first_step must start at 0 and end at step_count");
+    uint64_t max_steps = 0;
+    bool any_multi = false;
+    for (uint64_t p = 0; p < g->path_count; ++p) {
+        if (g->path_first_step[p + 1] < g->path_first_step[p]) return fail(PGSGD_ERR_ARG, "path_first_step is not monotone at path %llu", (unsigned long long) p);
+        const uint64_t c = g->path_first_step[p + 1] - g->path_first_step[p];
+        if (c > max_steps) max_steps = c;
+        if (c > 1) any_multi = true;
+    }
+    int ndev = pgsgd_device_count();
+    if (ndev == 0) return fail(PGSGD_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(PGSGD_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    const double t0 = now_s();
+    pgsgd_engine* e = new pgsgd_engine();
+    e->device = device;
+    e->N = g->node_count; e->P = g->path_count; e->S = g->step_count;
+    e->max_path_steps = max_steps;
+    e->any_multi_step_path = any_multi;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    int rc = PGSGD_OK;
+    auto bail = [&](int code) { pgsgd_engine_destroy(e); return code; };
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(PGSGD_ERR_CUDA, "cudaStreamCreate failed"));
+    if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) return bail(fail(PGSGD_ERR_CUDA, "cudaEventCreate failed"));
+
+    // validate node ranks and derive the per-path bp offsets when the caller did not supply them (xp.cpp:607-616)
+    std::vector<uint64_t> pos_host;
+    const uint64_t* pos = g->step_pos;
+    for (uint64_t s = 0; s < g->step_count; ++s) {
+        if (g->step_node[s] >= g->node_count) return bail(fail(PGSGD_ERR_UNOPT, "step %llu refers to node rank %u >= node_count: ids are not compacted 1..N", (unsigned long long) s, g->step_node[s]));
+    }
+    if (!pos) {
+        pos_host.resize(g->step_count);
+        for (uint64_t p = 0; p < g->path_count; ++p) {
+            uint64_t off = 0;
+            for (uint64_t s = g->path_first_step[p]; s < g->path_first_step[p + 1]; ++s) {
+                pos_host[s] = off;
+                off += g->node_len[g->step_node[s]];
+            }
+        }
+        pos = pos_host.data();
+    }
+    // 1D default initialisation, kept on the host until asked for
+    e->h_x1d_default.resize(e->N);
+    {
+        uint64_t len = 0;
+        for (uint64_t r = 0; r < e->N; ++r) { e->h_x1d_default[r] = (double) len; len += g->node_len[r]; }
+    }
+
+    if ((rc = dev_alloc(e, &e->d_steps, e->S))) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_path_first, e->P + 1))) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_delta, 1))) return bail(rc);
+    if ((rc = dev_alloc(e, &e->d_counted, 1))) return bail(rc);
+    auto cu_bail = [&](cudaError_t err, const char* what) {
+        return bail(fail(PGSGD_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err)));
+    };
+    cudaError_t err;
+    if ((err = cudaMemcpyAsync(e->d_path_first, g->path_first_step, (e->P + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) return cu_bail(err, "upload path_first_step");
+    e->h2d_bytes += (e->P + 1) * sizeof(uint64_t);
+
+    // flatten-to-device: SoA chunks are staged and packed into 16-byte step records by a device kernel
+    uint32_t* d_node_len = nullptr;
+    if (cudaMalloc(&d_node_len, e->N * sizeof(uint32_t)) != cudaSuccess) return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc node_len staging failed"));
+    if ((err = cudaMemcpyAsync(d_node_len, g->node_len, e->N * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) { cudaFree(d_node_len); return cu_bail(err, "upload node_len"); }
+    e->h2d_bytes += e->N * sizeof(uint32_t);
+    const uint64_t CH = 1ull << 26;  // 64 Mi steps per staging chunk (832 MiB of SoA)
+    const uint64_t ch = e->S < CH ? (e->S ? e->S : 1) : CH;
+    uint32_t* d_sn = nullptr; uint8_t* d_sr = nullptr; uint64_t* d_sp = nullptr;
+    bool ok = cudaMalloc(&d_sn, ch * 4) == cudaSuccess && cudaMalloc(&d_sp, ch * 8) == cudaSuccess && (!g->step_rev || cudaMalloc(&d_sr, ch) == cudaSuccess);
+    if (!ok) { cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
+    for (uint64_t off = 0; off < e->S && err == cudaSuccess; off += ch) {
+        const uint64_t n = e->S - off < ch ? e->S - off : ch;
+        err = cudaMemcpyAsync(d_sn, g->step_node + off, n * 4, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_sp, pos + off, n * 8, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev + off, n, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = launch_pack_steps(e->d_steps, d_sn, d_sr, d_sp, d_node_len, n, off, e->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);  // staging buffers and pageable sources are reused
+        e->h2d_bytes += n * (4 + 8 + (g->step_rev ? 1 : 0));
+    }
+    cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr);
+    if (err != cudaSuccess) return cu_bail(err, "flatten-to-device");
+    if ((err = cudaStreamSynchronize(e->stream)) != cudaSuccess) return cu_bail(err, "engine create sync");
+    e->seconds_upload = now_s() - t0;
+    *out = e;
+    return PGSGD_OK;
+}
+
+void pgsgd_engine_destroy(pgsgd_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->comm) ncclCommDestroy(e->comm);
+    cudaFree(e->d_steps); cudaFree(e->d_path_first); cudaFree(e->d_xy); cudaFree(e->d_xy_prev); cudaFree(e->d_x1d);
+    cudaFree(e->d_x1d_prev); cudaFree(e->d_frozen); cudaFree(e->d_zetas); cudaFree(e->d_rng); cudaFree(e->d_delta); cudaFree(e->d_counted);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int pgsgd_engine_device(const pgsgd_engine* e) { return e ? e->device : -1; }
+uint64_t pgsgd_engine_device_bytes(const pgsgd_engine* e) { return e ? e->bytes : 0; }
+
+int pgsgd_engine_set_coords_2d(pgsgd_engine* e, const double* X, const double* Y) {
+    if (!e || !X || !Y) return fail(PGSGD_ERR_ARG, "set_coords_2d: NULL argument");
+    CU(cudaSetDevice(e->device));
+    const double t0 = now_s();
+    if (!e->d_xy) { int rc = dev_alloc(e, &e->d_xy, 4 * e->N); if (rc) return rc; }
+    double *dX = nullptr, *dY = nullptr;
+    CU(cudaMalloc(&dX, 2 * e->N * sizeof(double)));
+    if (cudaMalloc(&dY, 2 * e->N * sizeof(double)) != cudaSuccess) { cudaFree(dX); return fail(PGSGD_ERR_NOMEM, "cudaMalloc failed"); }
+    cudaError_t err = cudaMemcpyAsync(dX, X, 2 * e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(dY, Y, 2 * e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = launch_xy_from_XY(e->d_xy, dX, dY, e->N, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(dX); cudaFree(dY);
+    if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "set_coords_2d: %s", cudaGetErrorString(err));
+    e->have_2d = true;
+    e->h2d_bytes += 4 * e->N * sizeof(double);
+    e->seconds_upload += now_s() - t0;
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_get_coords_2d(pgsgd_engine* e, double* X, double* Y) {
+    if (!e || !X || !Y) return fail(PGSGD_ERR_ARG, "get_coords_2d: NULL argument");
+    if (!e->have_2d) return fail(PGSGD_ERR_STATE, "no 2D coordinates on the device");
+    CU(cudaSetDevice(e->device));
+    double *dX = nullptr, *dY = nullptr;
+    CU(cudaMalloc(&dX, 2 * e->N * sizeof(double)));
+    if (cudaMalloc(&dY, 2 * e->N * sizeof(double)) != cudaSuccess) { cudaFree(dX); return fail(PGSGD_ERR_NOMEM, "cudaMalloc failed"); }
+    cudaError_t err = launch_XY_from_xy(dX, dY, e->d_xy, e->N, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(X, dX, 2 * e->N * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(Y, dY, 2 * e->N * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(dX); cudaFree(dY);
+    if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "get_coords_2d: %s", cudaGetErrorString(err));
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_set_coords_2d_f32(pgsgd_engine* e, const float* xy) {
+    if (!e || !xy) return fail(PGSGD_ERR_ARG, "set_coords_2d_f32: NULL argument");
+    CU(cudaSetDevice(e->device));
+    if (!e->d_xy) { int rc = dev_alloc(e, &e->d_xy, 4 * e->N); if (rc) return rc; }
+    CU(cudaMemcpyAsync(e->d_xy, xy, 4 * e->N * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->have_2d = true;
+    e->h2d_bytes += 4 * e->N * sizeof(float);
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_get_coords_2d_f32(pgsgd_engine* e, float* xy) {
+    if (!e || !xy) return fail(PGSGD_ERR_ARG, "get_coords_2d_f32: NULL argument");
+    if (!e->have_2d) return fail(PGSGD_ERR_STATE, "no 2D coordinates on the device");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(xy, e->d_xy, 4 * e->N * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_set_coords_1d(pgsgd_engine* e, const double* X) {
+    if (!e) return fail(PGSGD_ERR_ARG, "set_coords_1d: NULL engine");
+    CU(cudaSetDevice(e->device));
+    if (!e->d_x1d) { int rc = dev_alloc(e, &e->d_x1d, e->N); if (rc) return rc; }
+    const double* src = X ? X : e->h_x1d_default.data();
+    CU(cudaMemcpyAsync(e->d_x1d, src, e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->have_1d = true;
+    e->h2d_bytes += e->N * sizeof(double);
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_get_coords_1d(pgsgd_engine* e, double* X) {
+    if (!e || !X) return fail(PGSGD_ERR_ARG, "get_coords_1d: NULL argument");
+    if (!e->have_1d) return fail(PGSGD_ERR_STATE, "no 1D coordinates on the device");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(X, e->d_x1d, e->N * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_set_frozen_1d(pgsgd_engine* e, const uint8_t* frozen) {
+    if (!e) return fail(PGSGD_ERR_ARG, "set_frozen_1d: NULL engine");
+    CU(cudaSetDevice(e->device));
+    if (!frozen) {
+        if (e->d_frozen) { cudaFree(e->d_frozen); e->d_frozen = nullptr; }
+        return PGSGD_OK;
+    }
+    if (!e->d_frozen) { int rc = dev_alloc(e, &e->d_frozen, e->N); if (rc) return rc; }
+    CU(cudaMemcpyAsync(e->d_frozen, frozen, e->N, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_run_2d(pgsgd_engine* e, const pgsgd_config* cfg, pgsgd_stats* stats) {
+    if (!e) return fail(PGSGD_ERR_ARG, "run_2d: NULL engine");
+    return run_engine(e, cfg, 2, 0, UINT64_MAX, stats);
+}
+int pgsgd_engine_run_1d(pgsgd_engine* e, const pgsgd_config* cfg, pgsgd_stats* stats) {
+    if (!e) return fail(PGSGD_ERR_ARG, "run_1d: NULL engine");
+    return run_engine(e, cfg, 1, 0, UINT64_MAX, stats);
+}
+int pgsgd_engine_run_range(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end, pgsgd_stats* stats) {
+    if (!e) return fail(PGSGD_ERR_ARG, "run_range: NULL engine");
+    if (dims != 1 && dims != 2) return fail(PGSGD_ERR_ARG, "dims must be 1 or 2");
+    return run_engine(e, cfg, dims, iter_begin, iter_end, stats);
+}
+
+int pgsgd_comm_unique_id(uint8_t id_out[128]) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    NC(ncclGetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int n_ranks, int rank) {
+    if (!e || !unique_id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(PGSGD_ERR_ARG, "attach_comm: bad arguments");
+    CU(cudaSetDevice(e->device));
+    if (e->comm) { ncclCommDestroy(e->comm); e->comm = nullptr; }
+    e->n_ranks = n_ranks;
+    e->rank = rank;
+    if (n_ranks == 1) return PGSGD_OK;
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    NC(ncclCommInitRank(&e->comm, n_ranks, id, rank));
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_sample_terms(pgsgd_engine* e, const pgsgd_config* cfg, int dims, int cooling, double theta_zipf,
+                              uint64_t stream, uint64_t n_terms, uint64_t* step_index, uint32_t* path, uint64_t* rank_a,
+                              uint64_t* rank_b, uint32_t* node_a, uint32_t* node_b, uint64_t* pos_a, uint64_t* pos_b,
+                              uint8_t* end_a, uint8_t* end_b, uint8_t* valid) {
+    if (!e) return fail(PGSGD_ERR_ARG, "sample_terms: NULL engine");
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (dims != 1 && dims != 2) return fail(PGSGD_ERR_ARG, "dims must be 1 or 2");
+    CU(cudaSetDevice(e->device));
+    rc = ensure_zetas(e, build_zetas(*cfg));
+    if (rc) return rc;
+    SamplerParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.path_first = e->d_path_first;
+    sp.zetas = e->d_zetas;
+    sp.step_count = e->S;
+    sp.path_count = (uint32_t) e->P;
+    sp.cooling = cooling ? 1u : 0u;
+    sp.space = cfg->space; sp.space_max = cfg->space_max; sp.space_q = cfg->space_quantization_step;
+    sp.zipf = make_zipf_const(theta_zipf);
+    const uint64_t n = n_terms ? n_terms : 1;
+    uint8_t* d_buf = nullptr;
+    const uint64_t per = 8 * 5 + 4 * 3 + 3;  // bytes per term over all outputs
+    CU(cudaMalloc(&d_buf, n * per + 64));
+    SampleOut o;
+    uint8_t* q = d_buf;
+    o.step_index = (uint64_t*) q; q += 8 * n;
+    o.rank_a = (uint64_t*) q; q += 8 * n;
+    o.rank_b = (uint64_t*) q; q += 8 * n;
+    o.pos_a = (uint64_t*) q; q += 8 * n;
+    o.pos_b = (uint64_t*) q; q += 8 * n;
+    o.path = (uint32_t*) q; q += 4 * n;
+    o.node_a = (uint32_t*) q; q += 4 * n;
+    o.node_b = (uint32_t*) q; q += 4 * n;
+    o.end_a = q; q += n;
+    o.end_b = q; q += n;
+    o.valid = q;
+    cudaError_t err = launch_sample_terms(dims, sp, e->d_steps, cfg->seed + stream, n_terms, o, e->stream);
+    auto back = [&](void* dst, const void* src, size_t bytes) {
+        if (dst && err == cudaSuccess) err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, e->stream);
+    };
+    back(step_index, o.step_index, 8 * n_terms); back(rank_a, o.rank_a, 8 * n_terms); back(rank_b, o.rank_b, 8 * n_terms);
+    back(pos_a, o.pos_a, 8 * n_terms); back(pos_b, o.pos_b, 8 * n_terms); back(path, o.path, 4 * n_terms);
+    back(node_a, o.node_a, 4 * n_terms); back(node_b, o.node_b, 4 * n_terms); back(end_a, o.end_a, n_terms);
+    back(end_b, o.end_b, n_terms); back(valid, o.valid, n_terms);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(d_buf);
+    if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "sample_terms: %s", cudaGetErrorString(err));
+    return PGSGD_OK;
+}
+
+// ---- one-shot entry points -----------------------------------------------------------------------
+
+static int pick_device() {
+    const char* s = getenv("PGSGD_DEVICE");
+    return s ? atoi(s) : 0;
+}
+
+int pgsgd_layout_2d(const pgsgd_graph_view* g, const pgsgd_config* cfg, double* X, double* Y, pgsgd_stats* stats) {
+    if (!X || !Y) return fail(PGSGD_ERR_ARG, "pgsgd_layout_2d: X/Y are NULL");
+    pgsgd_engine* e = nullptr;
+    int rc = pgsgd_engine_create(g, pick_device(), &e);
+    if (rc) return rc;
+    rc = pgsgd_engine_set_coords_2d(e, X, Y);
+    pgsgd_stats st;
+    memset(&st, 0, sizeof(st));
+    if (!rc) rc = pgsgd_engine_run_2d(e, cfg, &st);
+    if (!rc) {
+        const double t0 = now_s();
+        rc = pgsgd_engine_get_coords_2d(e, X, Y);
+        st.seconds_download = now_s() - t0;
+        st.d2h_bytes = 4 * g->node_count * sizeof(double);
+    }
+    pgsgd_engine_destroy(e);
+    if (stats) *stats = st;
+    return rc;
+}
+
+int pgsgd_sort_1d(const pgsgd_graph_view* g, const pgsgd_config* cfg, const uint8_t* frozen, int x_is_initialised, double* X,
+                  pgsgd_stats* stats) {
+    if (!X) return fail(PGSGD_ERR_ARG, "pgsgd_sort_1d: X is NULL");
+    pgsgd_engine* e = nullptr;
+    int rc = pgsgd_engine_create(g, pick_device(), &e);
+    if (rc) return rc;
+    rc = pgsgd_engine_set_coords_1d(e, x_is_initialised ? X : nullptr);
+    if (!rc) rc = pgsgd_engine_set_frozen_1d(e, frozen);
+    pgsgd_stats st;
+    memset(&st, 0, sizeof(st));
+    if (!rc) rc = pgsgd_engine_run_1d(e, cfg, &st);
+    if (!rc) {
+        const double t0 = now_s();
+        rc = pgsgd_engine_get_coords_1d(e, X);
+        st.seconds_download = now_s() - t0;
+        st.d2h_bytes = g->node_count * sizeof(double);
+    }
+    pgsgd_engine_destroy(e);
+    if (stats) *stats = st;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+// pgsgd_device.cuh — device-side building blocks of the B200 PG-SGD kernels (sm_100a).
+//
+//  * Xoshiro256+ / SplitMix64 worker streams       (reference: deps/Xoshiro-cpp/XoshiroCpp.hpp:684-746)
+//  * libstdc++-compatible integer / canonical draws  (bits/uniform_int_dist.h:252-283, bits/random.tcc:3349-3381)
+//  * dirty Zipf with the reference's bit-hack pow     (deps/dirtyzipf/dirty_zipfian_int_distribution.h:82-104,230-243)
+//  * the term sampler shared by the SGD kernels and the verification hook
+//
+// Every floating-point operation whose result feeds an integer decision is written with explicit
+// round-to-nearest intrinsics (__dmul_rn, __dadd_rn, ...) so that nvcc cannot contract it into an FMA:
+// given the same stream seed the device draws the SAME term sequence as a reference CPU worker thread.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pgsgd {
+
+// ---- HBM-resident step record: one 16-byte load per path step -------------------------------------
+//   x = (node_rank << 1) | is_reverse      (== the libhandlegraph handle integer, util.hpp:44-62)
+//   y = node length in bp
+//   z,w = 64-bit bp offset of the node start within its path (== XP positions[rank], xp.cpp:393-397)
+struct __align__(16) StepRec {
+    uint32_t handle;
+    uint32_t len;
+    uint32_t pos_lo;
+    uint32_t pos_hi;
+};
+static_assert(sizeof(StepRec) == 16, "StepRec must be one 128-bit load");
+
+struct Xoshiro {
+    uint64_t s0, s1, s2, s3;
+};
+
+__host__ __device__ __forceinline__ uint64_t splitmix64_next(uint64_t& state) {
+    uint64_t z = (state += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+// Xoshiro256Plus(seed): four SplitMix64 outputs (XoshiroCpp.hpp:729-730)
+__host__ __device__ __forceinline__ void xoshiro_seed(Xoshiro& g, uint64_t seed) {
+    uint64_t sm = seed;
+    g.s0 = splitmix64_next(sm);
+    g.s1 = splitmix64_next(sm);
+    g.s2 = splitmix64_next(sm);
+    g.s3 = splitmix64_next(sm);
+}
+
+// Xoshiro256Plus::operator() (XoshiroCpp.hpp:735-746)
+__device__ __forceinline__ uint64_t xoshiro_next(Xoshiro& g) {
+    const uint64_t result = g.s0 + g.s3;
+    const uint64_t t = g.s1 << 17;
+    g.s2 ^= g.s0;
+    g.s3 ^= g.s1;
+    g.s1 ^= g.s2;
+    g.s0 ^= g.s3;
+    g.s2 ^= t;
+    g.s3 = (g.s3 << 45) | (g.s3 >> 19);
+    return result;
+}
+
+// std::uniform_int_distribution<uint64_t>(0, range-1): Lemire's method on the 128-bit product with
+// the rejection loop (taken with probability range / 2^64)
+__device__ __forceinline__ uint64_t draw_uniform(Xoshiro& g, uint64_t range) {
+    uint64_t x = xoshiro_next(g);
+    uint64_t hi = __umul64hi(x, range);
+    uint64_t lo = x * range;
+    if (lo < range) {
+        const uint64_t threshold = (0 - range) % range;
+        while (lo < threshold) {
+            x = xoshiro_next(g);
+            hi = __umul64hi(x, range);
+            lo = x * range;
+        }
+    }
+    return hi;
+}
+
+// uniform_int_distribution<uint64_t>(0,1): the product's high word is the generator's top bit; the
+// rejection threshold (-2 % 2) is 0, so exactly one draw is consumed
+__device__ __forceinline__ uint32_t draw_flip(Xoshiro& g) { return (uint32_t)(xoshiro_next(g) >> 63); }
+
+// std::generate_canonical<double,53>: double(x) / 2^64, clamped below 1
+__device__ __forceinline__ double draw_canonical(Xoshiro& g) {
+    double r = __dmul_rn(__ull2double_rn(xoshiro_next(g)), 5.421010862427522e-20 /* 2^-64, exact */);
+    if (r >= 1.0) r = __longlong_as_double(0x3FEFFFFFFFFFFFFFLL);  // nextafter(1, 0)
+    return r;
+}
+
+// dirtyzipf::fast_precise_pow — the result is defined by these exact operations, not by pow()
+__device__ __forceinline__ double fast_precise_pow(double a, double b) {
+    int e = __double2int_rz(b);
+    const int hi = __double2hiint(a);
+    const double t = __dadd_rn(__dmul_rn(__dsub_rn(b, (double) e), (double) (hi - 1072632447)), 1072632447.0);
+    const double frac = __hiloint2double(__double2int_rz(t), 0);
+    double r = 1.0;
+    while (e) {
+        if (e & 1) r = __dmul_rn(r, a);
+        a = __dmul_rn(a, a);
+        e >>= 1;
+    }
+    return __dmul_rn(r, frac);
+}
+
+// constants of one Zipf configuration, computed once per iteration on the host with the same bit-hack pow
+struct ZipfConst {
+    double theta;          // exponent handed to the draw (1D cooling: 0.001 with zetas of the original theta)
+    double one_minus_theta;
+    double alpha;          // 1 / (1 - theta)
+    double zeta2;          // zeta(2, theta) as the reference recomputes per draw (dirty_zipfian...h:126-128)
+    double thresh2;        // 1.0 + fast_precise_pow(0.5, theta)
+};
+
+// dirty_zipfian_int_distribution<uint64_t>(1, n, theta, zeta_n)(gen)
+__device__ __forceinline__ uint64_t draw_zipf(Xoshiro& g, uint64_t n, const ZipfConst& zc, double zeta_n) {
+    const double eta = __ddiv_rn(__dsub_rn(1.0, fast_precise_pow(__ddiv_rn(2.0, (double) n), zc.one_minus_theta)),
+                                 __dsub_rn(1.0, __ddiv_rn(zc.zeta2, zeta_n)));
+    const double u = draw_canonical(g);
+    const double uz = __dmul_rn(u, zeta_n);
+    if (uz < 1.0) return 1;
+    if (uz < zc.thresh2) return 2;
+    const double base = __dadd_rn(__dsub_rn(__dmul_rn(eta, u), eta), 1.0);
+    return __double2ull_rz(__dadd_rn(1.0, __dmul_rn((double) n, fast_precise_pow(base, zc.alpha))));
+}
+
+// ---- everything the sampler needs, passed by value to the kernels ---------------------------------
+struct SamplerParams {
+    const uint64_t* path_first;   // [P+1] global copy (used when the table does not fit in shared memory)
+    const double* zetas;          // zeta table (path_sgd_layout.cpp:87-97)
+    uint64_t step_count;          // S
+    uint32_t path_count;          // P
+    uint32_t cooling;             // 1: always take the Zipf branch (path_sgd_layout.cpp:205)
+    uint64_t space, space_max, space_q;
+    ZipfConst zipf;
+};
+
+struct Term {
+    uint64_t ia, ib;      // global step indices of the two steps
+    uint64_t step_index;  // the raw first draw
+    uint32_t path;
+    uint32_t flip_a, flip_b;
+    uint32_t valid;
+};
+
+// largest p with first[p] <= idx (first[P] = S > idx)
+template <typename FirstPtr>
+__device__ __forceinline__ uint32_t find_path(FirstPtr first, uint32_t P, uint64_t idx) {
+    uint32_t lo = 0, hi = P;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (first[mid] <= idx) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// One worker draw — the order of RNG consumption is the reference's (2D: path_sgd_layout.cpp:182-262,
+// 1D: path_sgd.cpp:222-279): step, [coin], [direction coin], Zipf | uniform partner, [end a, end b]
+template <int DIMS, typename FirstPtr>
+__device__ __forceinline__ void draw_term(const SamplerParams& sp, FirstPtr first, Xoshiro& g, Term& t) {
+    const uint64_t step_index = draw_uniform(g, sp.step_count);
+    const uint32_t p = find_path(first, sp.path_count, step_index);
+    const uint64_t f = first[p];
+    const uint64_t count = first[p + 1] - f;
+    t.step_index = step_index;
+    t.path = p;
+    t.flip_a = t.flip_b = 0;
+    t.ia = t.ib = step_index;
+    if (count == 1) {  // `continue` without counting (path_sgd_layout.cpp:190-192)
+        t.valid = 0;
+        return;
+    }
+    t.valid = 1;
+    const uint64_t s_rank = step_index - f;
+    uint64_t rank_b;
+    if (sp.cooling || draw_flip(g)) {
+        const bool backward = (s_rank > 0 && draw_flip(g)) || s_rank == count - 1;
+        const uint64_t room = backward ? s_rank : count - s_rank - 1;
+        const uint64_t jump_space = sp.space < room ? sp.space : room;
+        uint64_t zi = jump_space;
+        if (jump_space > sp.space_max) zi = sp.space_max + (jump_space - sp.space_max) / sp.space_q + 1;
+        const uint64_t z = draw_zipf(g, jump_space, sp.zipf, __ldg(sp.zetas + zi));
+        rank_b = backward ? s_rank - z : s_rank + z;
+    } else {
+        rank_b = draw_uniform(g, count);
+    }
+    t.ib = f + rank_b;
+    if (DIMS == 2) {
+        t.flip_a = draw_flip(g);
+        t.flip_b = draw_flip(g);
+    }
+}
+
+__device__ __forceinline__ uint4 load_step(const StepRec* steps, uint64_t i) {
+    return __ldg(reinterpret_cast<const uint4*>(steps) + i);
+}
+
+__device__ __forceinline__ uint64_t step_pos(const uint4& r) { return ((uint64_t) r.w << 32) | r.z; }
+
+}  // namespace pgsgd

@@ -1,0 +1,423 @@
+// pgsgd_kernels.cu — hand-written sm_100a kernels of the path-guided SGD hot path.
+//
+// Replaces: cuda::gpu_layout_kernel / update_pos_gpu / cuda_rnd_zipf (src/cuda/layout.cu:89-287) and the CPU
+// worker lambdas (src/algorithms/path_sgd_layout.cpp:165-377, src/algorithms/path_sgd.cpp:205-406).
+//
+// Shape of one iteration kernel (one launch per cooling-schedule step):
+//   * persistent grid: a multiple of the SM count, every thread is one reference-style worker stream with its
+//     own register-resident Xoshiro256+ state (loaded/stored once per launch, SoA, coalesced);
+//   * the per-path step offsets live in shared memory (binary search, no global traffic for step -> path);
+//   * every term costs two random 16-byte step-record loads (HBM) and two 8-byte coordinate loads + two 8-byte
+//     coordinate stores (L2-resident for graphs up to ~7M nodes); BATCH independent terms are drawn first and
+//     all their loads issued together, so each thread keeps 2*BATCH HBM requests in flight;
+//   * no tensor cores: the path is integer/byte gather-scatter bound by HBM sector rate and L2.
+#include "pgsgd_kernels.cuh"
+
+#include <cstdio>
+
+namespace pgsgd {
+
+namespace {
+
+__device__ __forceinline__ float2 ld_coord(const float2* p) { return __ldcg(p); }
+__device__ __forceinline__ void st_coord(float2* p, float2 v) { __stcg(p, v); }
+
+template <int BATCH>
+struct MinBlocks {
+    static constexpr int value = BATCH >= 4 ? 2 : (BATCH == 2 ? 3 : 4);
+};
+
+// --------------------------------------------------------------------------------------------------
+// the iteration kernel
+// --------------------------------------------------------------------------------------------------
+template <int DIMS, int BATCH, bool SMEM_PATHS>
+__global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kernel(const __grid_constant__ IterParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long block_counted;
+    const uint64_t* first;
+    if (SMEM_PATHS) {
+        uint64_t* sfirst = reinterpret_cast<uint64_t*>(smem_raw);
+        for (uint32_t i = threadIdx.x; i <= p.sp.path_count; i += blockDim.x) sfirst[i] = p.sp.path_first[i];
+        first = sfirst;
+    } else {
+        first = p.sp.path_first;
+    }
+    if (threadIdx.x == 0) block_counted = 0;
+    __syncthreads();
+
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t done = 0;
+    float delta_max = 0.0f;
+    if (tid < p.n_streams) {
+        Xoshiro g;
+        g.s0 = p.rng[tid];
+        g.s1 = p.rng[p.rng_stride + tid];
+        g.s2 = p.rng[2 * p.rng_stride + tid];
+        g.s3 = p.rng[3 * p.rng_stride + tid];
+        const uint64_t quota = p.quota_base + (tid < p.quota_rem ? 1 : 0);
+        const float eta_f = __double2float_rn(p.eta);
+        const bool atomic_add = (p.flags & 1u) != 0;
+        float2* const xy2 = reinterpret_cast<float2*>(p.xy);
+
+        while (done < quota) {
+            const uint64_t remaining = quota - done;
+            Term t[BATCH];
+            uint4 ra[BATCH], rb[BATCH];
+            // phase 1: draw the batch (RNG + shared-memory binary search only)
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                t[b].valid = 0;
+                if ((uint64_t) b < remaining) draw_term<DIMS>(p.sp, first, g, t[b]);
+            }
+            // phase 2: all step-record loads of the batch in flight together
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                if (t[b].valid) {
+                    ra[b] = load_step(p.steps, t[b].ia);
+                    rb[b] = load_step(p.steps, t[b].ib);
+                }
+            }
+            if (DIMS == 2) {
+                float2 ca[BATCH], cb[BATCH];
+                float2* pa[BATCH];
+                float2* pb[BATCH];
+                float dij[BATCH];
+                // phase 3: integer path distance + coordinate loads
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    if (t[b].valid) {
+                        uint64_t pos_a = step_pos(ra[b]), pos_b = step_pos(rb[b]);
+                        const uint32_t rev_a = ra[b].x & 1u, rev_b = rb[b].x & 1u;
+                        // end choice (path_sgd_layout.cpp:252-269): flip moves to the far end along the path
+                        uint32_t end_a = rev_a, end_b = rev_b;
+                        if (t[b].flip_a) { pos_a += ra[b].y; end_a ^= 1u; }
+                        if (t[b].flip_b) { pos_b += rb[b].y; end_b ^= 1u; }
+                        const uint64_t dpos = pos_a > pos_b ? pos_a - pos_b : pos_b - pos_a;
+                        dij[b] = dpos ? __ull2float_rn(dpos) : 1e-9f;  // term_dist == 0 -> 1e-9 (:283-285)
+                        pa[b] = xy2 + ((uint64_t) (ra[b].x >> 1) * 2 + end_a);
+                        pb[b] = xy2 + ((uint64_t) (rb[b].x >> 1) * 2 + end_b);
+                        ca[b] = ld_coord(pa[b]);
+                        cb[b] = ld_coord(pb[b]);
+                    }
+                }
+                // phase 4: the update (path_sgd_layout.cpp:294-363) in fp32, applied in draw order
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    if (t[b].valid) {
+                        float mu = __fdiv_rn(eta_f, dij[b]);
+                        if (mu > 1.0f) mu = 1.0f;
+                        float dx = __fsub_rn(ca[b].x, cb[b].x);
+                        const float dy = __fsub_rn(ca[b].y, cb[b].y);
+                        if (dx == 0.0f) dx = 1e-9f;
+                        const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+                        const float Delta = __fmul_rn(__fmul_rn(mu, __fsub_rn(mag, dij[b])), 0.5f);
+                        delta_max = fmaxf(delta_max, fabsf(Delta));
+                        const float r = __fdiv_rn(Delta, mag);
+                        const float r_x = __fmul_rn(r, dx);
+                        const float r_y = __fmul_rn(r, dy);
+                        if (atomic_add) {
+                            atomicAdd(pa[b], make_float2(-r_x, -r_y));
+                            atomicAdd(pb[b], make_float2(r_x, r_y));
+                        } else {
+                            const float2 na = make_float2(__fsub_rn(ca[b].x, r_x), __fsub_rn(ca[b].y, r_y));
+                            st_coord(pa[b], na);
+                            // the reference re-reads X[j] after storing X[i]: matters only when both ends alias
+                            const float2 base = (pa[b] == pb[b]) ? na : cb[b];
+                            st_coord(pb[b], make_float2(__fadd_rn(base.x, r_x), __fadd_rn(base.y, r_y)));
+                        }
+                        ++done;
+                    }
+                }
+            } else {
+                double xa[BATCH], xb[BATCH];
+                double* qa[BATCH];
+                double* qb[BATCH];
+                double dij[BATCH];
+                uint32_t upd[BATCH];  // bit0: move a, bit1: move b, bit2: counted
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    upd[b] = 0;
+                    if (t[b].valid) {
+                        const uint32_t na = ra[b].x >> 1, nb = rb[b].x >> 1;
+                        uint32_t u = 3u;
+                        if (p.frozen) {  // odgi sort -H target nodes (path_sgd.cpp:290-297)
+                            if (p.frozen[na]) u &= ~1u;
+                            if (p.frozen[nb]) u &= ~2u;
+                        }
+                        // 1D uses node starts only (path_sgd.cpp:305-306)
+                        const double d = fabs(__dsub_rn(__ull2double_rn(step_pos(ra[b])), __ull2double_rn(step_pos(rb[b]))));
+                        dij[b] = d;
+                        if (u == 0) {
+                            upd[b] = 4u;  // both frozen: counted, nothing moves (:298-302)
+                        } else if (d != 0.0) {  // d == 0: `continue`, not counted (:320-323)
+                            upd[b] = u | 4u;
+                            qa[b] = p.x1d + na;
+                            qb[b] = p.x1d + nb;
+                            xa[b] = __ldcg(qa[b]);
+                            xb[b] = __ldcg(qb[b]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    if (upd[b] & 4u) {
+                        if (upd[b] & 3u) {  // path_sgd.cpp:332-392 in fp64
+                            double mu = __dmul_rn(p.eta, __ddiv_rn(1.0, dij[b]));
+                            if (mu > 1.0) mu = 1.0;
+                            double dx = __dsub_rn(xa[b], xb[b]);
+                            if (dx == 0.0) dx = 1e-9;
+                            const double mag = fabs(dx);
+                            const double Delta = __dmul_rn(__dmul_rn(mu, __dsub_rn(mag, dij[b])), 0.5);
+                            delta_max = fmaxf(delta_max, (float) fabs(Delta));
+                            const double r_x = __dmul_rn(__ddiv_rn(Delta, mag), dx);
+                            if (atomic_add) {
+                                if (upd[b] & 1u) atomicAdd(qa[b], -r_x);
+                                if (upd[b] & 2u) atomicAdd(qb[b], r_x);
+                            } else {
+                                const double na = __dsub_rn(xa[b], r_x);
+                                if (upd[b] & 1u) __stcg(qa[b], na);
+                                const double base = (qa[b] == qb[b] && (upd[b] & 1u)) ? na : xb[b];
+                                if (upd[b] & 2u) __stcg(qb[b], __dadd_rn(base, r_x));
+                            }
+                        }
+                        ++done;
+                    }
+                }
+            }
+        }
+        p.rng[tid] = g.s0;
+        p.rng[p.rng_stride + tid] = g.s1;
+        p.rng[2 * p.rng_stride + tid] = g.s2;
+        p.rng[3 * p.rng_stride + tid] = g.s3;
+    }
+
+    // per-block bookkeeping: one global atomic per block
+    unsigned long long wsum = done;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&block_counted, wsum);
+    if (p.delta_max_bits) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) delta_max = fmaxf(delta_max, __shfl_xor_sync(0xffffffffu, delta_max, o));
+        if ((threadIdx.x & 31) == 0) atomicMax(p.delta_max_bits, __float_as_uint(delta_max));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && block_counted) atomicAdd(p.counted, block_counted);
+}
+
+__global__ void seed_streams_kernel(uint64_t* rng, uint64_t stride, uint64_t n, uint64_t seed_base) {
+    const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    Xoshiro g;
+    xoshiro_seed(g, seed_base + t);
+    rng[t] = g.s0;
+    rng[stride + t] = g.s1;
+    rng[2 * stride + t] = g.s2;
+    rng[3 * stride + t] = g.s3;
+}
+
+__global__ void pack_steps_kernel(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* pos,
+                                  const uint32_t* node_len, uint64_t n, uint64_t out_offset) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t node = step_node[i];
+    StepRec r;
+    r.handle = (node << 1) | (step_rev ? (uint32_t) (step_rev[i] != 0) : 0u);
+    r.len = node_len[node];
+    const uint64_t p = pos[i];
+    r.pos_lo = (uint32_t) p;
+    r.pos_hi = (uint32_t) (p >> 32);
+    out[out_offset + i] = r;
+}
+
+__global__ void xy_from_XY_kernel(float4* xy, const double* X, const double* Y, uint64_t n) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xy[i] = make_float4((float) X[2 * i], (float) Y[2 * i], (float) X[2 * i + 1], (float) Y[2 * i + 1]);
+}
+
+__global__ void XY_from_xy_kernel(double* X, double* Y, const float4* xy, uint64_t n) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = xy[i];
+    X[2 * i] = v.x; Y[2 * i] = v.y; X[2 * i + 1] = v.z; Y[2 * i + 1] = v.w;
+}
+
+template <typename T>
+__global__ void scale_kernel(T* a, uint64_t n, T s) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] *= s;
+}
+template <typename T, int SIGN>
+__global__ void addsub_kernel(T* out, const T* a, const T* b, uint64_t n) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = SIGN > 0 ? a[i] + b[i] : a[i] - b[i];
+}
+
+// verification hook: one thread replays a stream with the SAME draw_term the SGD kernels use
+template <int DIMS>
+__global__ void sample_terms_kernel(SamplerParams sp, const StepRec* steps, uint64_t seed, uint64_t n_terms, SampleOut out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Xoshiro g;
+    xoshiro_seed(g, seed);
+    for (uint64_t k = 0; k < n_terms; ++k) {
+        Term t;
+        draw_term<DIMS>(sp, sp.path_first, g, t);
+        const uint64_t f = sp.path_first[t.path];
+        uint64_t pos_a = 0, pos_b = 0;
+        uint32_t node_a = 0, node_b = 0, end_a = 0, end_b = 0;
+        if (t.valid) {
+            const uint4 ra = load_step(steps, t.ia), rb = load_step(steps, t.ib);
+            pos_a = step_pos(ra); pos_b = step_pos(rb);
+            node_a = ra.x >> 1; node_b = rb.x >> 1;
+            end_a = ra.x & 1u; end_b = rb.x & 1u;
+            if (DIMS == 2) {
+                if (t.flip_a) { pos_a += ra.y; end_a ^= 1u; }
+                if (t.flip_b) { pos_b += rb.y; end_b ^= 1u; }
+            } else {
+                end_a = end_b = 0;
+            }
+        }
+        if (out.step_index) out.step_index[k] = t.step_index;
+        if (out.path) out.path[k] = t.path;
+        if (out.rank_a) out.rank_a[k] = t.ia - f;
+        if (out.rank_b) out.rank_b[k] = t.ib - f;
+        if (out.node_a) out.node_a[k] = node_a;
+        if (out.node_b) out.node_b[k] = node_b;
+        if (out.pos_a) out.pos_a[k] = pos_a;
+        if (out.pos_b) out.pos_b[k] = pos_b;
+        if (out.end_a) out.end_a[k] = (uint8_t) end_a;
+        if (out.end_b) out.end_b[k] = (uint8_t) end_b;
+        if (out.valid) out.valid[k] = (uint8_t) t.valid;
+    }
+}
+
+template <int DIMS, int BATCH>
+cudaError_t launch_iter_t(const IterParams& p, const LaunchShape& s, cudaStream_t stream) {
+    if (p.smem_paths) {
+        auto k = pgsgd_iter_kernel<DIMS, BATCH, true>;
+        if (s.smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
+            if (e != cudaSuccess) return e;
+        }
+        k<<<s.grid, s.block, s.smem, stream>>>(p);
+    } else {
+        pgsgd_iter_kernel<DIMS, BATCH, false><<<s.grid, s.block, 0, stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+template <int DIMS, int BATCH>
+cudaError_t occupancy_t(int block, size_t smem, bool smem_paths, int* out) {
+    if (smem_paths) {
+        auto k = pgsgd_iter_kernel<DIMS, BATCH, true>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, block, smem);
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, pgsgd_iter_kernel<DIMS, BATCH, false>, block, 0);
+}
+
+inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n + block - 1) / block); }
+
+}  // namespace
+
+cudaError_t launch_seed_streams(uint64_t* rng, uint64_t rng_stride, uint64_t n, uint64_t seed_base, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    seed_streams_kernel<<<grid_for(n, 256), 256, 0, stream>>>(rng, rng_stride, n, seed_base);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_iteration(int dims, int batch, const IterParams& p, const LaunchShape& shape, cudaStream_t stream) {
+    if (dims == 2) {
+        switch (batch) {
+            case 1: return launch_iter_t<2, 1>(p, shape, stream);
+            case 2: return launch_iter_t<2, 2>(p, shape, stream);
+            case 4: return launch_iter_t<2, 4>(p, shape, stream);
+        }
+    } else if (dims == 1) {
+        switch (batch) {
+            case 1: return launch_iter_t<1, 1>(p, shape, stream);
+            case 2: return launch_iter_t<1, 2>(p, shape, stream);
+            case 4: return launch_iter_t<1, 4>(p, shape, stream);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t iteration_occupancy(int dims, int batch, int block, size_t smem, bool smem_paths, int* blocks_per_sm) {
+    if (dims == 2) {
+        switch (batch) {
+            case 1: return occupancy_t<2, 1>(block, smem, smem_paths, blocks_per_sm);
+            case 2: return occupancy_t<2, 2>(block, smem, smem_paths, blocks_per_sm);
+            case 4: return occupancy_t<2, 4>(block, smem, smem_paths, blocks_per_sm);
+        }
+    } else if (dims == 1) {
+        switch (batch) {
+            case 1: return occupancy_t<1, 1>(block, smem, smem_paths, blocks_per_sm);
+            case 2: return occupancy_t<1, 2>(block, smem, smem_paths, blocks_per_sm);
+            case 4: return occupancy_t<1, 4>(block, smem, smem_paths, blocks_per_sm);
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pack_steps(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* step_pos,
+                              const uint32_t* node_len, uint64_t n, uint64_t out_offset, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    pack_steps_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, step_node, step_rev, step_pos, node_len, n, out_offset);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    xy_from_XY_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(xy), X, Y, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_XY_from_xy(double* X, double* Y, const float* xy, uint64_t n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    XY_from_xy_kernel<<<grid_for(n, 256), 256, 0, stream>>>(X, Y, reinterpret_cast<const float4*>(xy), n);
+    return cudaGetLastError();
+}
+cudaError_t launch_scale_f32(float* a, uint64_t n, float s, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    scale_kernel<float><<<grid_for(n, 256), 256, 0, stream>>>(a, n, s);
+    return cudaGetLastError();
+}
+cudaError_t launch_scale_f64(double* a, uint64_t n, double s, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    scale_kernel<double><<<grid_for(n, 256), 256, 0, stream>>>(a, n, s);
+    return cudaGetLastError();
+}
+cudaError_t launch_sub_f32(float* out, const float* a, const float* b, uint64_t n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    addsub_kernel<float, -1><<<grid_for(n, 256), 256, 0, stream>>>(out, a, b, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_add_f32(float* out, const float* a, const float* b, uint64_t n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    addsub_kernel<float, 1><<<grid_for(n, 256), 256, 0, stream>>>(out, a, b, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_sub_f64(double* out, const double* a, const double* b, uint64_t n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    addsub_kernel<double, -1><<<grid_for(n, 256), 256, 0, stream>>>(out, a, b, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_add_f64(double* out, const double* a, const double* b, uint64_t n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    addsub_kernel<double, 1><<<grid_for(n, 256), 256, 0, stream>>>(out, a, b, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample_terms(int dims, const SamplerParams& sp, const StepRec* steps, uint64_t seed, uint64_t n_terms,
+                                const SampleOut& out, cudaStream_t stream) {
+    if (dims == 2) sample_terms_kernel<2><<<1, 32, 0, stream>>>(sp, steps, seed, n_terms, out);
+    else if (dims == 1) sample_terms_kernel<1><<<1, 32, 0, stream>>>(sp, steps, seed, n_terms, out);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+}  // namespace pgsgd

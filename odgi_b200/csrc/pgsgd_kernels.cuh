@@ -1,0 +1,67 @@
+// pgsgd_kernels.cuh — launch-side declarations shared by pgsgd_kernels.cu and pgsgd_capi.cu
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "pgsgd_device.cuh"
+
+namespace pgsgd {
+
+// Parameters of one SGD iteration launch (one cooling-schedule step), passed by value.
+struct IterParams {
+    SamplerParams sp;
+    const StepRec* steps;       // [S] 16-byte step records, HBM resident
+    float* xy;                  // 2D: [4N] {x0,y0,x1,y1} per node (one float2 per node end)
+    double* x1d;                // 1D: [N]
+    const uint8_t* frozen;      // 1D: [N] or nullptr
+    uint64_t* rng;              // [4][rng_stride] Xoshiro256+ state of every worker stream (SoA)
+    uint64_t rng_stride;
+    uint64_t n_streams;         // worker streams launched (one per thread)
+    uint64_t quota_base;        // each stream performs quota_base (+1 for stream < quota_rem) counted updates
+    uint64_t quota_rem;
+    double eta;                 // learning rate of this iteration
+    unsigned int* delta_max_bits;  // max |Delta| as ordered float bits, or nullptr when not tracked
+    unsigned long long* counted;   // total counted updates (atomicAdd once per block)
+    uint32_t flags;             // PGSGD_FLAG_ATOMIC_ADD
+    uint32_t smem_paths;        // 1: path_first table staged in shared memory
+};
+
+struct LaunchShape {
+    int block;           // threads per block
+    int grid;            // blocks
+    size_t smem;         // dynamic shared memory bytes
+};
+
+// seeds worker streams [0, n) with seed_base + global_stream_offset + t
+cudaError_t launch_seed_streams(uint64_t* rng, uint64_t rng_stride, uint64_t n, uint64_t seed_base, cudaStream_t stream);
+
+// one iteration of 2D / 1D PG-SGD
+cudaError_t launch_iteration(int dims, int batch, const IterParams& p, const LaunchShape& shape, cudaStream_t stream);
+// occupancy query for the kernel variant (resident blocks per SM for the given block size / smem)
+cudaError_t iteration_occupancy(int dims, int batch, int block, size_t smem, bool smem_paths, int* blocks_per_sm);
+
+// packs SoA step arrays into StepRec records on the device
+cudaError_t launch_pack_steps(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* step_pos,
+                              const uint32_t* node_len, uint64_t n, uint64_t out_offset, cudaStream_t stream);
+
+// coordinate format conversion: reference X/Y (double, index 2*node+end) <-> device float4-per-node
+cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n_nodes, cudaStream_t stream);
+cudaError_t launch_XY_from_xy(double* X, double* Y, const float* xy, uint64_t n_nodes, cudaStream_t stream);
+// 1D default initialisation: X[rank] = cumulative bp (path_sgd.cpp:63-69) from an exclusive scan done on the host side
+// multi-GPU helpers
+cudaError_t launch_scale_f32(float* a, uint64_t n, float s, cudaStream_t stream);
+cudaError_t launch_scale_f64(double* a, uint64_t n, double s, cudaStream_t stream);
+cudaError_t launch_sub_f32(float* out, const float* a, const float* b, uint64_t n, cudaStream_t stream);   // out = a - b
+cudaError_t launch_add_f32(float* out, const float* a, const float* b, uint64_t n, cudaStream_t stream);   // out = a + b
+cudaError_t launch_sub_f64(double* out, const double* a, const double* b, uint64_t n, cudaStream_t stream);
+cudaError_t launch_add_f64(double* out, const double* a, const double* b, uint64_t n, cudaStream_t stream);
+
+// verification hook: first n_terms draws of one stream, produced by the same device sampler
+struct SampleOut {
+    uint64_t* step_index; uint32_t* path; uint64_t* rank_a; uint64_t* rank_b; uint32_t* node_a; uint32_t* node_b;
+    uint64_t* pos_a; uint64_t* pos_b; uint8_t* end_a; uint8_t* end_b; uint8_t* valid;
+};
+cudaError_t launch_sample_terms(int dims, const SamplerParams& sp, const StepRec* steps, uint64_t seed, uint64_t n_terms,
+                                const SampleOut& out, cudaStream_t stream);
+
+}  // namespace pgsgd

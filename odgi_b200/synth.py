@@ -1,0 +1,128 @@
+"""Synthetic pangenome graphs in flattened form (SURVEY.md §8d generator spec).
+
+A backbone of `n_sites` sites; every `bubble_every`-th site is a bubble with 2-4 alleles (one node per
+allele), the others have one node.  Node length is 1 bp w.p. 0.55, else 1 + Geom(mean 24) capped at 1024
+(mean ~ 12 bp, SNP-dense like PGGB graphs).  Each of `n_paths` haplotypes walks all sites choosing alleles
+i.i.d. with per-site frequencies ~ Dirichlet-ish; a few segments per path are inverted (reverse-orientation
+steps) or tandem-duplicated x2-5 (cycles).  Node ids are compact 1..N by construction.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .capi import FlatGraph
+
+PRESETS = {
+    # name: (n_sites, n_paths)        nodes ~ 1.2 * n_sites, steps ~ 1.01 * n_sites * n_paths
+    "tiny": (2_000, 8),
+    "small": (50_000, 16),
+    "mid": (500_000, 90),             # ~6e5 nodes, ~4.5e7 steps  (0.7 GB of step records: beyond L2)
+    "c4": (4_600_000, 90),            # ~5.5e6 nodes, ~4.2e8 steps (BASELINE config 4: 90-haplotype chr6-MHC scale)
+}
+
+
+def generate(n_sites: int, n_paths: int, seed: int = 42, bubble_every: int = 10, inv_per_mbp: float = 0.5,
+             dup_per_mbp: float = 0.2, with_pos: bool = False) -> FlatGraph:
+    rng = np.random.Generator(np.random.PCG64(seed))
+    # alleles per site
+    k = np.ones(n_sites, dtype=np.int64)
+    bub = np.arange(bubble_every // 2, n_sites, bubble_every)
+    k[bub] = rng.integers(2, 5, size=bub.size)
+    site_first = np.zeros(n_sites + 1, dtype=np.int64)
+    np.cumsum(k, out=site_first[1:])
+    N = int(site_first[-1])
+    # node lengths
+    node_len = np.ones(N, dtype=np.uint32)
+    longer = rng.random(N) >= 0.55
+    node_len[longer] = 1 + np.minimum(rng.geometric(1.0 / 24.0, size=int(longer.sum())), 1023).astype(np.uint32)
+    # per-bubble allele frequency thresholds (U-shaped minor allele frequencies)
+    maf = rng.beta(0.5, 0.5, size=bub.size) * 0.5
+
+    mean_len = float(node_len.mean())
+    site_bp = 1e6 / mean_len  # sites per Mbp
+    step_node_parts, step_rev_parts, counts = [], [], []
+    for _ in range(n_paths):
+        allele = np.zeros(n_sites, dtype=np.int64)
+        u = rng.random(bub.size)
+        # minor alleles share `maf` evenly; allele 0 is the major one
+        minor = u < maf
+        kk = k[bub] - 1
+        allele[bub] = np.where(minor, 1 + np.minimum((u / np.maximum(maf, 1e-12) * kk).astype(np.int64), kk - 1), 0)
+        nodes = (site_first[:-1] + allele).astype(np.uint32)
+        rev = np.zeros(n_sites, dtype=np.uint8)
+        # structural events: a handful of 1-50 kb segments, inverted or tandem-duplicated
+        n_inv = rng.poisson(inv_per_mbp * n_sites / site_bp)
+        n_dup = rng.poisson(dup_per_mbp * n_sites / site_bp)
+        events = []
+        for kind, cnt in (("inv", n_inv), ("dup", n_dup)):
+            for _e in range(cnt):
+                seg = max(2, int(rng.integers(1_000, 50_000) / mean_len))
+                if seg >= n_sites:
+                    continue
+                s = int(rng.integers(0, n_sites - seg))
+                events.append((s, s + seg, kind, int(rng.integers(2, 6))))
+        events.sort()
+        idx_parts, cur = [], 0
+        rev_mask_parts = []
+        for s, e, kind, copies in events:
+            if s < cur:
+                continue  # overlapping event: skip
+            idx_parts.append(np.arange(cur, s))
+            rev_mask_parts.append(np.zeros(s - cur, dtype=np.uint8))
+            if kind == "inv":
+                idx_parts.append(np.arange(e - 1, s - 1, -1))
+                rev_mask_parts.append(np.ones(e - s, dtype=np.uint8))
+            else:
+                idx_parts.append(np.tile(np.arange(s, e), copies))
+                rev_mask_parts.append(np.zeros((e - s) * copies, dtype=np.uint8))
+            cur = e
+        idx_parts.append(np.arange(cur, n_sites))
+        rev_mask_parts.append(np.zeros(n_sites - cur, dtype=np.uint8))
+        idx = np.concatenate(idx_parts)
+        step_node_parts.append(nodes[idx])
+        step_rev_parts.append(rev[idx] | np.concatenate(rev_mask_parts))
+        counts.append(idx.size)
+    path_first = np.zeros(n_paths + 1, dtype=np.uint64)
+    np.cumsum(np.array(counts, dtype=np.uint64), out=path_first[1:])
+    step_node = np.concatenate(step_node_parts)
+    step_rev = np.concatenate(step_rev_parts)
+    g = FlatGraph(node_len, path_first, step_node, step_rev, None, [f"hap{i}" for i in range(n_paths)])
+    if with_pos:
+        lens = node_len[step_node].astype(np.uint64)
+        csum = np.cumsum(lens, dtype=np.uint64)
+        pos = np.empty_like(csum)
+        pos[0] = 0
+        pos[1:] = csum[:-1]
+        base = pos[path_first[:-1].astype(np.int64)]
+        g.step_pos = pos - np.repeat(base, np.array(counts))
+    return g
+
+
+def preset(name: str, seed: int = 42, with_pos: bool = False) -> FlatGraph:
+    n_sites, n_paths = PRESETS[name]
+    return generate(n_sites, n_paths, seed=seed, with_pos=with_pos)
+
+
+def write_gfa(g: FlatGraph, path: str) -> None:
+    """GFA1 with placeholder sequences (only lengths matter to PG-SGD): lets the unmodified reference load a
+    synthetic graph.  Edges are the adjacencies the paths use."""
+    with open(path, "w") as f:
+        f.write("H\tVN:Z:1.0\n")
+        for i, ln in enumerate(g.node_len):
+            f.write(f"S\t{i + 1}\t{'A' * int(ln)}\n")
+        edges = set()
+        first = g.path_first_step.astype(np.int64)
+        rev = g.step_rev if g.step_rev is not None else np.zeros(g.S, dtype=np.uint8)
+        for p in range(g.P):
+            a, b = int(first[p]), int(first[p + 1])
+            n, r = g.step_node[a:b].astype(np.int64) + 1, rev[a:b]
+            for j in range(b - a - 1):
+                edges.add((int(n[j]), int(r[j]), int(n[j + 1]), int(r[j + 1])))
+        for (u, ur, v, vr) in sorted(edges):
+            f.write(f"L\t{u}\t{'-' if ur else '+'}\t{v}\t{'-' if vr else '+'}\t0M\n")
+        for p in range(g.P):
+            a, b = int(first[p]), int(first[p + 1])
+            n, r = g.step_node[a:b].astype(np.int64) + 1, rev[a:b]
+            steps = ",".join(f"{int(x)}{'-' if y else '+'}" for x, y in zip(n, r))
+            name = g.path_names[p] if p < len(g.path_names) else f"path{p}"
+            f.write(f"P\t{name}\t{steps}\t*\n")

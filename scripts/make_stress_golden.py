@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Reference stress bands: runs the UNMODIFIED reference (oracle/_ref/ref_driver) with default
+`odgi layout` / `odgi sort -Y` parameters several times (different thread counts => different Hogwild
+interleavings) from the same injected initialisation, measures the sampled path stress of each result
+with the oracle's definition, and stores mean / sd under tests/golden/stress_reference.json.
+
+Authoring container only (needs /root/reference + oracle/_ref)."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from odgi_b200.arrays import read_arrays, write_arrays  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+TEST = "/root/reference/test"
+GOLD = os.path.join(ROOT, "tests", "golden")
+N_PAIRS, SEED = 1_000_000, 12345
+THREADS = [1, 2, 4, 8, 8, 8]
+
+
+def main():
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in ("DRB1-3123", "chr6.C4"):
+            g = orc.Graph.from_arrays(read_arrays(os.path.join(GOLD, f"{name}.graph.arr.gz")))
+            X0, Y0 = orc.layout_init(g, seed=42)
+            init = os.path.join(tmp, "init.arr")
+            write_arrays(init, {"X": X0, "Y": Y0})
+            vals = []
+            for t in THREADS:
+                res = os.path.join(tmp, "o.arr")
+                subprocess.run([REF, "layout", os.path.join(TEST, name + ".gfa"), init, res, f"threads={t}"], check=True, cwd=tmp, capture_output=True)
+                r = read_arrays(res)
+                vals.append(orc.path_stress_2d(g, r["X"], r["Y"], N_PAIRS, SEED))
+            s0 = orc.path_stress_2d(g, X0, Y0, N_PAIRS, SEED)
+            out[f"{name}.layout2d"] = {"mean": float(np.mean(vals)), "sd": float(np.std(vals, ddof=1)), "values": vals, "threads": THREADS,
+                                       "initial": s0, "n_pairs": N_PAIRS, "seed": SEED, "init_seed": 42}
+            print(name, "2D", out[f"{name}.layout2d"])
+        for name in ("LPA", "DRB1-3123"):
+            g = orc.Graph.from_arrays(read_arrays(os.path.join(GOLD, f"{name}.graph.arr.gz")))
+            vals = []
+            for t in THREADS:
+                res = os.path.join(tmp, "o1.arr")
+                subprocess.run([REF, "sort", os.path.join(TEST, name + ".gfa"), res, f"threads={t}"], check=True, cwd=tmp, capture_output=True)
+                r = read_arrays(res)
+                vals.append(orc.path_stress_1d(g, r["X"], N_PAIRS, SEED))
+            s0 = orc.path_stress_1d(g, orc.sort_init(g), N_PAIRS, SEED)
+            out[f"{name}.sort1d"] = {"mean": float(np.mean(vals)), "sd": float(np.std(vals, ddof=1)), "values": vals, "threads": THREADS,
+                                     "initial": s0, "n_pairs": N_PAIRS, "seed": SEED}
+            print(name, "1D", out[f"{name}.sort1d"])
+    with open(os.path.join(GOLD, "stress_reference.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

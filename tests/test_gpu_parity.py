@@ -1,0 +1,192 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle, on a real B200.
+
+Levels, strongest first:
+  1. sampler: the device draws the SAME terms as a reference worker thread with the same seed — bit-exact on every
+     integer field (step index, path, ranks, nodes, end choice, end-adjusted bp positions);
+  2. arithmetic: with one worker stream and batch 1 (strict order) the device coordinates equal the oracle's
+     fp32 device model (2D) / the reference's fp64 arithmetic (1D) bit-for-bit;
+  3. Hogwild runs: sampled path stress of full default runs within tolerance of the reference CPU implementation.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import odgi_b200
+from odgi_b200 import capi
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+INT_FIELDS = ("step_index", "path", "rank_a", "rank_b", "node_a", "node_b", "pos_a", "pos_b", "end_a", "end_b")
+
+
+@pytest.fixture(scope="module")
+def graphs(golden_graphs):
+    return {k: (odgi_b200.graph_from_arrays(a), orc.Graph.from_arrays(a)) for k, a in golden_graphs.items()}
+
+
+def _cfgs(gd, go, dims, **kw):
+    if dims == 2:
+        return capi.layout_defaults(gd, **kw), orc.default_layout_config(go, **kw)
+    return capi.sort_defaults(gd, **kw), orc.default_sort_config(go, **kw)
+
+
+@pytest.mark.parametrize("name,dims,cooling,theta_zipf", [
+    ("DRB1-3123", 2, False, None), ("DRB1-3123", 2, True, None), ("chr6.C4", 2, False, None), ("chr6.C4", 2, True, None),
+    ("LPA", 1, False, None), ("LPA", 1, True, 0.001), ("DRB1-3123", 1, True, 0.001), ("note5", 2, False, None), ("t", 2, True, None)])
+def test_sampler_bit_exact(graphs, name, dims, cooling, theta_zipf):
+    gd, go = graphs[name]
+    cd, co = _cfgs(gd, go, dims)
+    n = 20000
+    with odgi_b200.Engine(gd) as e:
+        for stream in (0, 1, 77777):
+            dev = e.sample_terms(cd, dims, cooling, n, stream=stream, theta_zipf=theta_zipf)
+            ref, valid = orc.sample_terms(go, co, dims, cooling, n, stream=stream, theta_zipf=theta_zipf)
+            assert np.array_equal(dev["valid"], valid)
+            ok = valid.astype(bool)
+            for f in INT_FIELDS:
+                if dims == 1 and f in ("end_a", "end_b"):
+                    continue
+                assert np.array_equal(dev[f][ok], ref[f][ok].astype(dev[f].dtype)), (name, stream, f)
+            # the integer path distance itself
+            assert np.array_equal(np.abs(dev["pos_a"][ok].astype(np.int64) - dev["pos_b"][ok].astype(np.int64)),
+                                  np.abs(ref["pos_a"][ok].astype(np.int64) - ref["pos_b"][ok].astype(np.int64)))
+
+
+def test_sampler_one_step_paths():
+    """Paths of a single step are drawn but not counted (path_sgd_layout.cpp:190-192); sort.cpp:129-255 is the
+    reference's own test of that corner."""
+    node_len = np.array([3, 1, 2, 5, 4], dtype=np.uint32)
+    first = np.array([0, 1, 4, 5, 5, 7], dtype=np.uint64)  # a 1-step, a 3-step, a 1-step, an EMPTY and a 2-step path
+    step_node = np.array([0, 1, 2, 3, 4, 0, 4], dtype=np.uint32)
+    step_rev = np.array([0, 1, 0, 0, 1, 0, 0], dtype=np.uint8)
+    gd = odgi_b200.FlatGraph(node_len, first, step_node, step_rev)
+    go = orc.Graph(node_len, first, step_node, step_rev)
+    cd, co = _cfgs(gd, go, 2)
+    with odgi_b200.Engine(gd) as e:
+        dev = e.sample_terms(cd, 2, False, 5000)
+    ref, valid = orc.sample_terms(go, co, 2, False, 5000)
+    assert np.array_equal(dev["valid"], valid) and 0 < valid.sum() < 5000
+    ok = valid.astype(bool)
+    for f in INT_FIELDS:
+        assert np.array_equal(dev[f][ok], ref[f][ok].astype(dev[f].dtype)), f
+
+
+@pytest.mark.parametrize("name", ["DRB1-3123", "chr6.C4"])
+def test_2d_single_stream_bit_exact(graphs, name):
+    gd, go = graphs[name]
+    kw = dict(iter_max=4, min_term_updates=6000, eta_max=2000.0)
+    cd, co = _cfgs(gd, go, 2, **kw)
+    cd.n_streams, cd.batch = 1, 1
+    X0, Y0 = orc.layout_init(go, seed=3)
+    xy0 = orc.XY_to_xy(X0, Y0)
+    n_ref, xy_ref = orc.layout_2d_f32(go, co, xy0.copy(), n_streams=1)
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_2d_f32(xy0)
+        st = e.run_2d(cd)
+        xy_dev = e.get_coords_2d_f32()
+    assert st["term_updates"] == n_ref == 4 * 6000
+    assert np.array_equal(xy_dev, xy_ref)
+
+
+@pytest.mark.parametrize("name", ["LPA", "DRB1-3123"])
+def test_1d_single_stream_bit_exact(graphs, name):
+    gd, go = graphs[name]
+    kw = dict(iter_max=3, min_term_updates=5000, eta_max=2000.0, cooling_start=0.3)
+    cd, co = _cfgs(gd, go, 1, **kw)
+    cd.n_streams, cd.batch = 1, 1
+    n_ref, x_ref = orc.sort_1d(go, co, orc.sort_init(go), n_streams=1)
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_1d(None)
+        st = e.run_1d(cd)
+        x_dev = e.get_coords_1d()
+    assert st["term_updates"] == n_ref == 4 * 5000  # iter_max + 1 iterations
+    assert np.array_equal(x_dev, x_ref)
+
+
+def test_1d_frozen_nodes_stay_put(graphs):
+    gd, go = graphs["DRB1-3123"]
+    cd, co = _cfgs(gd, go, 1, iter_max=5)
+    frozen = (np.arange(gd.N) % 3 == 0).astype(np.uint8)
+    x0 = orc.sort_init(go)
+    x, st = odgi_b200.sort_1d(gd, cd, x0, frozen=frozen)
+    assert np.array_equal(x[frozen == 1], x0[frozen == 1])
+    assert np.any(x[frozen == 0] != x0[frozen == 0])
+    assert st["term_updates"] == 6 * cd.min_term_updates
+    # single stream: identical to the oracle with the same frozen set
+    cd.n_streams, cd.batch = 1, 1
+    cd.min_term_updates = co.min_term_updates = 4000
+    n_ref, x_ref = orc.sort_1d(go, co, x0.copy(), n_streams=1, frozen=frozen)
+    x1, _ = odgi_b200.sort_1d(gd, cd, x0, frozen=frozen)
+    assert np.array_equal(x1, x_ref)
+
+
+def _stress_band(golden_dir, key):
+    with open(os.path.join(golden_dir, "stress_reference.json")) as f:
+        return json.load(f)[key]
+
+
+@pytest.mark.parametrize("name", ["DRB1-3123", "chr6.C4"])
+def test_2d_default_run_stress_within_reference_band(graphs, golden_dir, name):
+    """Full `odgi layout` default run (30 x 10*S updates, Hogwild, batch 4) vs the reference CPU implementation:
+    sampled path stress within max(1 %, 2 sigma) of the mean over the reference's own runs (tests/golden/
+    stress_reference.json, written by scripts/make_stress_golden.py from oracle/_ref runs with the same init)."""
+    gd, go = graphs[name]
+    band = _stress_band(golden_dir, f"{name}.layout2d")
+    X0, Y0 = orc.layout_init(go, seed=42)
+    cd = capi.layout_defaults(gd)
+    X, Y, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
+    assert st["term_updates"] == 30 * 10 * gd.S
+    assert np.all(np.isfinite(X)) and np.all(np.isfinite(Y))
+    s = orc.path_stress_2d(go, X, Y, n_pairs=band["n_pairs"], seed=band["seed"])
+    mean, sd = band["mean"], band["sd"]
+    tol = max(0.01 * mean, 2 * sd)
+    assert abs(s - mean) <= tol, (s, mean, sd)
+
+
+@pytest.mark.parametrize("name", ["LPA", "DRB1-3123"])
+def test_1d_default_run_stress_within_reference_band(graphs, golden_dir, name):
+    gd, go = graphs[name]
+    band = _stress_band(golden_dir, f"{name}.sort1d")
+    cd = capi.sort_defaults(gd)
+    x, st = odgi_b200.sort_1d(gd, cd)
+    assert st["term_updates"] == 101 * gd.S
+    s = orc.path_stress_1d(go, x, n_pairs=band["n_pairs"], seed=band["seed"])
+    mean, sd = band["mean"], band["sd"]
+    tol = max(0.01 * mean, 2 * sd)
+    assert abs(s - mean) <= tol, (s, mean, sd)
+    # the node order derived from X is a permutation, identical to the reference's sort on the same X
+    order = orc.order_from_x(x)
+    assert np.array_equal(np.sort(order), np.arange(gd.N, dtype=np.uint64))
+
+
+def test_engine_equals_one_shot(graphs):
+    gd, go = graphs["DRB1-3123"]
+    cd = capi.layout_defaults(gd, iter_max=3, n_streams=1, batch=1, min_term_updates=3000)
+    X0, Y0 = orc.layout_init(go, seed=9)
+    X1, Y1, _ = odgi_b200.layout_2d(gd, cd, X0, Y0)
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_2d(X0, Y0)
+        e.run_2d(cd)
+        X2, Y2 = e.get_coords_2d()
+    assert np.array_equal(X1, X2) and np.array_equal(Y1, Y2)
+
+
+def test_delta_early_stop(graphs):
+    gd, go = graphs["DRB1-3123"]
+    cd = capi.layout_defaults(gd, delta=1e30)  # every iteration's max |Delta| is below this: stop after the first
+    X0, Y0 = orc.layout_init(go, seed=1)
+    _, _, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
+    assert st["iterations_run"] == 1 and st["last_delta_max"] > 0
+
+
+def test_atomic_add_variant_runs(graphs):
+    gd, go = graphs["DRB1-3123"]
+    cd = capi.layout_defaults(gd, flags=capi.PGSGD_FLAG_ATOMIC_ADD)
+    X0, Y0 = orc.layout_init(go, seed=42)
+    X, Y, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
+    s0 = orc.path_stress_2d(go, X0, Y0, 200000, 5)
+    s1 = orc.path_stress_2d(go, X, Y, 200000, 5)
+    assert np.all(np.isfinite(X)) and s1 < s0
