@@ -69,14 +69,20 @@ typedef struct pgsgd_config {
     uint64_t space_quantization_step;
     double   cooling_start;                /* first cooling iteration = floor(cooling_start * iter_max) */
     uint64_t seed;                         /* worker stream t is seeded seed + t; reference: 9399220 (path_sgd_layout.cpp:168) */
-    uint32_t n_streams;                    /* device worker streams (one per GPU thread); 0 = fill the GPU */
-    uint32_t batch;                        /* terms a stream keeps in flight (1, 2 or 4); 0 = default.
+    uint32_t n_streams;                    /* device worker streams (one per GPU thread); 0 = automatic: fill the GPU, but keep
+                                              the terms in flight (n_streams * batch) below node_count / 4 — beyond that
+                                              Hogwild staleness measurably worsens the layout of small graphs */
+    uint32_t batch;                        /* terms a stream keeps in flight (1, 2 or 4); 0 = default (1).
                                               batch 1 applies a stream's terms strictly in order */
     uint32_t flags;                        /* PGSGD_FLAG_* */
     uint32_t reserved;
 } pgsgd_config;
 
-#define PGSGD_FLAG_ATOMIC_ADD   1u  /* accumulate updates with red.global.add instead of Hogwild stores */
+/* Coordinate write flavour.  Default (no flag): red.global.add of the displacement — no update is ever lost; a single
+ * worker stream gives bit-identical results to the load/compute/store of the reference (tests/test_gpu_parity.py).
+ * The other two reproduce the reference's racy last-writer-wins write (path_sgd_layout.cpp:360-363, layout.cu:184-187). */
+#define PGSGD_FLAG_EXCH_WRITE   1u  /* 64-bit atom.exch of the new (x,y) — the reference CUDA kernel's atomicExch semantics */
+#define PGSGD_FLAG_PLAIN_STORE  4u  /* st.global of the new (x,y) (slower on B200: 14 vs 21 G updates/s, profiles/) */
 #define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
 
 typedef struct pgsgd_stats {

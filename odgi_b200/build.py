@@ -45,4 +45,4 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_native(force=True, verbose=True))
+    print(build_native(force=True, verbose="-v" in __import__("sys").argv))

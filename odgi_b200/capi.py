@@ -15,8 +15,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpgsgd_b200.so")
 
-PGSGD_FLAG_ATOMIC_ADD = 1
+PGSGD_FLAG_EXCH_WRITE = 1
 PGSGD_FLAG_SUM_DELTAS = 2
+PGSGD_FLAG_PLAIN_STORE = 4
 
 
 class PgsgdError(RuntimeError):

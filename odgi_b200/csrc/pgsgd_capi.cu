@@ -226,7 +226,7 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     const uint64_t U_rank = U / e->n_ranks + ((uint64_t) e->rank < U % e->n_ranks ? 1 : 0);
 
     // launch shape: a whole number of resident waves of the persistent grid
-    const int batch = cfg->batch ? (int) cfg->batch : 4;
+    const int batch = cfg->batch ? (int) cfg->batch : 1;
     const int block = 256;
     const size_t smem_need = (e->P + 1) * sizeof(uint64_t);
     const bool smem_paths = smem_need <= 200 * 1024;
@@ -237,10 +237,17 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     uint64_t n_streams = cfg->n_streams;
     if (n_streams == 0) {
         n_streams = (uint64_t) e->sm_count * blocks_per_sm * block;
-        // tiny graphs: keep at least ~64 terms per stream so the launch is not all prologue
+        // Hogwild staleness: with more than ~N/4 terms in flight the final stress of small graphs drifts away from the
+        // reference's (measured: profiles/r01_stream_sweep.md); large graphs are not affected by this cap
+        uint64_t cap = (e->N / 4) / batch;
+        if (cap < 32) cap = 32;
+        if (n_streams > cap) n_streams = cap;
+        // keep at least ~64 terms per stream so the launch is not all prologue
         const uint64_t want = (U_rank + 63) / 64;
-        if (want < n_streams) n_streams = ((want + block - 1) / block) * block;
-        if (n_streams == 0) n_streams = block;
+        if (want < n_streams) n_streams = want;
+        if (n_streams >= (uint64_t) block) n_streams = (n_streams / block) * block;
+        else n_streams = ((n_streams + 31) / 32) * 32;
+        if (n_streams == 0) n_streams = 32;
     }
     LaunchShape shape;
     shape.block = n_streams < (uint64_t) block ? (int) ((n_streams + 31) / 32 * 32) : block;
@@ -402,6 +409,15 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
     if (ndev == 0) return fail(PGSGD_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(PGSGD_ERR_ARG, "device %d out of range (have %d)", device, ndev);
     CU(cudaSetDevice(device));
+    // The path gathers single 16/32-byte records at random addresses: ask L2 not to widen its DRAM fetches beyond one
+    // 32-byte sector (the default granularity over-fetches ~3.4x on this access pattern, profiles/).  PGSGD_L2_FETCH
+    // overrides (bytes: 32, 64 or 128) for experiments.
+    {
+        size_t gran = 32;
+        if (const char* s = getenv("PGSGD_L2_FETCH")) gran = (size_t) atoi(s);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
 
     const double t0 = now_s();
     pgsgd_engine* e = new pgsgd_engine();

@@ -190,8 +190,48 @@ __device__ __forceinline__ void draw_term(const SamplerParams& sp, FirstPtr firs
     }
 }
 
+// ---- L2 residency control ---------------------------------------------------------------------------
+// The step records are a multi-GB stream with no reuse; the coordinates (16 B per node) are re-read and re-written
+// millions of times per iteration and fit (or nearly fit) the 126 MB L2.  Step-record loads therefore carry an
+// L2::evict_first policy and every coordinate access an L2::evict_last policy, so the stream cannot push the
+// coordinates out (ncu before/after: profiles/).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+__device__ __forceinline__ uint4 load_step(const StepRec* steps, uint64_t i, uint64_t policy) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(reinterpret_cast<const uint4*>(steps) + i), "l"(policy));
+    return r;
+}
 __device__ __forceinline__ uint4 load_step(const StepRec* steps, uint64_t i) {
     return __ldg(reinterpret_cast<const uint4*>(steps) + i);
+}
+
+__device__ __forceinline__ float2 ld_coord2(const float2* p, uint64_t policy) {
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void red_coord2(float2* p, float dx, float dy, uint64_t policy) {
+    asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" :: "l"(p), "f"(dx), "f"(dy), "l"(policy) : "memory");
+}
+__device__ __forceinline__ double ld_coord1(const double* p, uint64_t policy) {
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void red_coord1(double* p, double d, uint64_t policy) {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(d), "l"(policy) : "memory");
 }
 
 __device__ __forceinline__ uint64_t step_pos(const uint4& r) { return ((uint64_t) r.w << 32) | r.z; }

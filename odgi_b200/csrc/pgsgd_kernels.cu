@@ -19,8 +19,22 @@ namespace pgsgd {
 
 namespace {
 
-__device__ __forceinline__ float2 ld_coord(const float2* p) { return __ldcg(p); }
-__device__ __forceinline__ void st_coord(float2* p, float2 v) { __stcg(p, v); }
+// Racy (last-writer-wins) coordinate writes, selected by PGSGD_FLAG_EXCH_WRITE / PGSGD_FLAG_PLAIN_STORE: one 64-bit
+// atom.exch per node end = the reference kernel's four atomicExch(float*) (layout.cu:184-187) with x and y of an end
+// written together, or a plain st.global.  Measured on B200 (profiles/): L2-side atomics sustain 21 G updates/s where
+// plain st.global (any cache operator) plateaus at 14 G updates/s.  The default write is red.global.add (see the kernel).
+__device__ __forceinline__ void st_coord(float2* p, float2 v, bool plain_store) {
+    if (plain_store) {
+        __stcg(p, v);
+    } else {
+        unsigned long long bits = ((unsigned long long) __float_as_uint(v.y) << 32) | __float_as_uint(v.x);
+        atomicExch(reinterpret_cast<unsigned long long*>(p), bits);
+    }
+}
+__device__ __forceinline__ void st_coord(double* p, double v, bool plain_store) {
+    if (plain_store) __stcg(p, v);
+    else atomicExch(reinterpret_cast<unsigned long long*>(p), (unsigned long long) __double_as_longlong(v));
+}
 
 template <int BATCH>
 struct MinBlocks {
@@ -56,8 +70,11 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
         g.s3 = p.rng[3 * p.rng_stride + tid];
         const uint64_t quota = p.quota_base + (tid < p.quota_rem ? 1 : 0);
         const float eta_f = __double2float_rn(p.eta);
-        const bool atomic_add = (p.flags & 1u) != 0;
+        const bool atomic_add = (p.flags & 5u) == 0;  // default; PGSGD_FLAG_EXCH_WRITE / PGSGD_FLAG_PLAIN_STORE select a racy write
+        const bool st_mode = (p.flags & 4u) != 0;     // PGSGD_FLAG_PLAIN_STORE
         float2* const xy2 = reinterpret_cast<float2*>(p.xy);
+        const uint64_t pol_stream = l2_policy_evict_first();  // step records: read once, never reused
+        const uint64_t pol_keep = l2_policy_evict_last();     // coordinates: keep resident in L2
 
         while (done < quota) {
             const uint64_t remaining = quota - done;
@@ -73,8 +90,8 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
 #pragma unroll
             for (int b = 0; b < BATCH; ++b) {
                 if (t[b].valid) {
-                    ra[b] = load_step(p.steps, t[b].ia);
-                    rb[b] = load_step(p.steps, t[b].ib);
+                    ra[b] = load_step(p.steps, t[b].ia, pol_stream);
+                    rb[b] = load_step(p.steps, t[b].ib, pol_stream);
                 }
             }
             if (DIMS == 2) {
@@ -96,8 +113,8 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
                         dij[b] = dpos ? __ull2float_rn(dpos) : 1e-9f;  // term_dist == 0 -> 1e-9 (:283-285)
                         pa[b] = xy2 + ((uint64_t) (ra[b].x >> 1) * 2 + end_a);
                         pb[b] = xy2 + ((uint64_t) (rb[b].x >> 1) * 2 + end_b);
-                        ca[b] = ld_coord(pa[b]);
-                        cb[b] = ld_coord(pb[b]);
+                        ca[b] = ld_coord2(pa[b], pol_keep);
+                        cb[b] = ld_coord2(pb[b], pol_keep);
                     }
                 }
                 // phase 4: the update (path_sgd_layout.cpp:294-363) in fp32, applied in draw order
@@ -116,14 +133,14 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
                         const float r_x = __fmul_rn(r, dx);
                         const float r_y = __fmul_rn(r, dy);
                         if (atomic_add) {
-                            atomicAdd(pa[b], make_float2(-r_x, -r_y));
-                            atomicAdd(pb[b], make_float2(r_x, r_y));
+                            red_coord2(pa[b], -r_x, -r_y, pol_keep);
+                            red_coord2(pb[b], r_x, r_y, pol_keep);
                         } else {
                             const float2 na = make_float2(__fsub_rn(ca[b].x, r_x), __fsub_rn(ca[b].y, r_y));
-                            st_coord(pa[b], na);
+                            st_coord(pa[b], na, st_mode);
                             // the reference re-reads X[j] after storing X[i]: matters only when both ends alias
                             const float2 base = (pa[b] == pb[b]) ? na : cb[b];
-                            st_coord(pb[b], make_float2(__fadd_rn(base.x, r_x), __fadd_rn(base.y, r_y)));
+                            st_coord(pb[b], make_float2(__fadd_rn(base.x, r_x), __fadd_rn(base.y, r_y)), st_mode);
                         }
                         ++done;
                     }
@@ -153,8 +170,8 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
                             upd[b] = u | 4u;
                             qa[b] = p.x1d + na;
                             qb[b] = p.x1d + nb;
-                            xa[b] = __ldcg(qa[b]);
-                            xb[b] = __ldcg(qb[b]);
+                            xa[b] = ld_coord1(qa[b], pol_keep);
+                            xb[b] = ld_coord1(qb[b], pol_keep);
                         }
                     }
                 }
@@ -171,13 +188,13 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
                             delta_max = fmaxf(delta_max, (float) fabs(Delta));
                             const double r_x = __dmul_rn(__ddiv_rn(Delta, mag), dx);
                             if (atomic_add) {
-                                if (upd[b] & 1u) atomicAdd(qa[b], -r_x);
-                                if (upd[b] & 2u) atomicAdd(qb[b], r_x);
+                                if (upd[b] & 1u) red_coord1(qa[b], -r_x, pol_keep);
+                                if (upd[b] & 2u) red_coord1(qb[b], r_x, pol_keep);
                             } else {
                                 const double na = __dsub_rn(xa[b], r_x);
-                                if (upd[b] & 1u) __stcg(qa[b], na);
+                                if (upd[b] & 1u) st_coord(qa[b], na, st_mode);
                                 const double base = (qa[b] == qb[b] && (upd[b] & 1u)) ? na : xb[b];
-                                if (upd[b] & 2u) __stcg(qb[b], __dadd_rn(base, r_x));
+                                if (upd[b] & 2u) st_coord(qb[b], __dadd_rn(base, r_x), st_mode);
                             }
                         }
                         ++done;

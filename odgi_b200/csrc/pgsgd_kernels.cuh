@@ -22,7 +22,7 @@ struct IterParams {
     double eta;                 // learning rate of this iteration
     unsigned int* delta_max_bits;  // max |Delta| as ordered float bits, or nullptr when not tracked
     unsigned long long* counted;   // total counted updates (atomicAdd once per block)
-    uint32_t flags;             // PGSGD_FLAG_ATOMIC_ADD
+    uint32_t flags;             // PGSGD_FLAG_* write flavour bits
     uint32_t smem_paths;        // 1: path_first table staged in shared memory
 };
 

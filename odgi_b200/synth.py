@@ -106,23 +106,23 @@ def preset(name: str, seed: int = 42, with_pos: bool = False) -> FlatGraph:
 def write_gfa(g: FlatGraph, path: str) -> None:
     """GFA1 with placeholder sequences (only lengths matter to PG-SGD): lets the unmodified reference load a
     synthetic graph.  Edges are the adjacencies the paths use."""
+    first = g.path_first_step.astype(np.int64)
+    rev = g.step_rev if g.step_rev is not None else np.zeros(g.S, dtype=np.uint8)
     with open(path, "w") as f:
         f.write("H\tVN:Z:1.0\n")
-        for i, ln in enumerate(g.node_len):
-            f.write(f"S\t{i + 1}\t{'A' * int(ln)}\n")
-        edges = set()
-        first = g.path_first_step.astype(np.int64)
-        rev = g.step_rev if g.step_rev is not None else np.zeros(g.S, dtype=np.uint8)
+        f.write("".join(f"S\t{i + 1}\t{'A' * int(ln)}\n" for i, ln in enumerate(g.node_len)))
+        # unique (from handle, to handle) pairs over all consecutive steps
+        h = (g.step_node.astype(np.uint64) << np.uint64(1)) | rev.astype(np.uint64)
+        keep = np.ones(g.S, dtype=bool)
+        keep[first[1:] - 1] = False  # the last step of a path has no successor
+        keep = keep[:-1] if g.S else keep
+        pairs = np.unique((h[:-1][keep[: g.S - 1]] << np.uint64(32)) | h[1:][keep[: g.S - 1]])
+        u, v = pairs >> np.uint64(32), pairs & np.uint64(0xFFFFFFFF)
+        sign = np.array(["+", "-"])
+        f.write("".join(f"L\t{int(a >> 1) + 1}\t{sign[int(a & 1)]}\t{int(b >> 1) + 1}\t{sign[int(b & 1)]}\t0M\n" for a, b in zip(u, v)))
         for p in range(g.P):
             a, b = int(first[p]), int(first[p + 1])
-            n, r = g.step_node[a:b].astype(np.int64) + 1, rev[a:b]
-            for j in range(b - a - 1):
-                edges.add((int(n[j]), int(r[j]), int(n[j + 1]), int(r[j + 1])))
-        for (u, ur, v, vr) in sorted(edges):
-            f.write(f"L\t{u}\t{'-' if ur else '+'}\t{v}\t{'-' if vr else '+'}\t0M\n")
-        for p in range(g.P):
-            a, b = int(first[p]), int(first[p + 1])
-            n, r = g.step_node[a:b].astype(np.int64) + 1, rev[a:b]
-            steps = ",".join(f"{int(x)}{'-' if y else '+'}" for x, y in zip(n, r))
+            ids = (g.step_node[a:b].astype(np.int64) + 1).astype(str)
+            steps = ",".join(np.char.add(ids, sign[rev[a:b]]))
             name = g.path_names[p] if p < len(g.path_names) else f"path{p}"
             f.write(f"P\t{name}\t{steps}\t*\n")

@@ -74,12 +74,13 @@ def test_sampler_one_step_paths():
         assert np.array_equal(dev[f][ok], ref[f][ok].astype(dev[f].dtype)), f
 
 
+@pytest.mark.parametrize("flags", [0, capi.PGSGD_FLAG_EXCH_WRITE, capi.PGSGD_FLAG_PLAIN_STORE])
 @pytest.mark.parametrize("name", ["DRB1-3123", "chr6.C4"])
-def test_2d_single_stream_bit_exact(graphs, name):
+def test_2d_single_stream_bit_exact(graphs, name, flags):
     gd, go = graphs[name]
     kw = dict(iter_max=4, min_term_updates=6000, eta_max=2000.0)
     cd, co = _cfgs(gd, go, 2, **kw)
-    cd.n_streams, cd.batch = 1, 1
+    cd.n_streams, cd.batch, cd.flags = 1, 1, flags
     X0, Y0 = orc.layout_init(go, seed=3)
     xy0 = orc.XY_to_xy(X0, Y0)
     n_ref, xy_ref = orc.layout_2d_f32(go, co, xy0.copy(), n_streams=1)
@@ -91,12 +92,13 @@ def test_2d_single_stream_bit_exact(graphs, name):
     assert np.array_equal(xy_dev, xy_ref)
 
 
+@pytest.mark.parametrize("flags", [0, capi.PGSGD_FLAG_EXCH_WRITE])
 @pytest.mark.parametrize("name", ["LPA", "DRB1-3123"])
-def test_1d_single_stream_bit_exact(graphs, name):
+def test_1d_single_stream_bit_exact(graphs, name, flags):
     gd, go = graphs[name]
     kw = dict(iter_max=3, min_term_updates=5000, eta_max=2000.0, cooling_start=0.3)
     cd, co = _cfgs(gd, go, 1, **kw)
-    cd.n_streams, cd.batch = 1, 1
+    cd.n_streams, cd.batch, cd.flags = 1, 1, flags
     n_ref, x_ref = orc.sort_1d(go, co, orc.sort_init(go), n_streams=1)
     with odgi_b200.Engine(gd) as e:
         e.set_coords_1d(None)
@@ -128,38 +130,46 @@ def _stress_band(golden_dir, key):
         return json.load(f)[key]
 
 
+def _assert_in_band(values, band):
+    """mean over seeds within max(1 %, 2 sigma_ref) of the reference mean; every single run within 2.5 %"""
+    mean, sd = band["mean"], band["sd"]
+    tol = max(0.01 * mean, 2 * sd)
+    assert abs(np.mean(values) - mean) <= tol, (values, mean, sd)
+    assert all(abs(v - mean) <= 0.025 * mean + 2 * sd for v in values), (values, mean, sd)
+
+
 @pytest.mark.parametrize("name", ["DRB1-3123", "chr6.C4"])
 def test_2d_default_run_stress_within_reference_band(graphs, golden_dir, name):
-    """Full `odgi layout` default run (30 x 10*S updates, Hogwild, batch 4) vs the reference CPU implementation:
-    sampled path stress within max(1 %, 2 sigma) of the mean over the reference's own runs (tests/golden/
-    stress_reference.json, written by scripts/make_stress_golden.py from oracle/_ref runs with the same init)."""
+    """Full `odgi layout` default runs (30 x 10*S updates, Hogwild, automatic launch shape) vs the reference CPU
+    implementation: sampled path stress within max(1 %, 2 sigma) of the mean over the reference's own runs
+    (tests/golden/stress_reference.json, written by scripts/make_stress_golden.py from oracle/_ref runs, same init)."""
     gd, go = graphs[name]
     band = _stress_band(golden_dir, f"{name}.layout2d")
     X0, Y0 = orc.layout_init(go, seed=42)
-    cd = capi.layout_defaults(gd)
-    X, Y, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
-    assert st["term_updates"] == 30 * 10 * gd.S
-    assert np.all(np.isfinite(X)) and np.all(np.isfinite(Y))
-    s = orc.path_stress_2d(go, X, Y, n_pairs=band["n_pairs"], seed=band["seed"])
-    mean, sd = band["mean"], band["sd"]
-    tol = max(0.01 * mean, 2 * sd)
-    assert abs(s - mean) <= tol, (s, mean, sd)
+    vals = []
+    for seed in (9399220, 1234567, 42):
+        cd = capi.layout_defaults(gd, seed=seed)
+        X, Y, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
+        assert st["term_updates"] == 30 * 10 * gd.S
+        assert np.all(np.isfinite(X)) and np.all(np.isfinite(Y))
+        vals.append(orc.path_stress_2d(go, X, Y, n_pairs=band["n_pairs"], seed=band["seed"]))
+    _assert_in_band(vals, band)
 
 
 @pytest.mark.parametrize("name", ["LPA", "DRB1-3123"])
 def test_1d_default_run_stress_within_reference_band(graphs, golden_dir, name):
     gd, go = graphs[name]
     band = _stress_band(golden_dir, f"{name}.sort1d")
-    cd = capi.sort_defaults(gd)
-    x, st = odgi_b200.sort_1d(gd, cd)
-    assert st["term_updates"] == 101 * gd.S
-    s = orc.path_stress_1d(go, x, n_pairs=band["n_pairs"], seed=band["seed"])
-    mean, sd = band["mean"], band["sd"]
-    tol = max(0.01 * mean, 2 * sd)
-    assert abs(s - mean) <= tol, (s, mean, sd)
-    # the node order derived from X is a permutation, identical to the reference's sort on the same X
-    order = orc.order_from_x(x)
-    assert np.array_equal(np.sort(order), np.arange(gd.N, dtype=np.uint64))
+    vals = []
+    for seed in (9399220, 1234567, 42):
+        cd = capi.sort_defaults(gd, seed=seed)
+        x, st = odgi_b200.sort_1d(gd, cd)
+        assert st["term_updates"] == 101 * gd.S
+        vals.append(orc.path_stress_1d(go, x, n_pairs=band["n_pairs"], seed=band["seed"]))
+        # the node order derived from X is a permutation
+        order = orc.order_from_x(x)
+        assert np.array_equal(np.sort(order), np.arange(gd.N, dtype=np.uint64))
+    _assert_in_band(vals, band)
 
 
 def test_engine_equals_one_shot(graphs):
@@ -182,9 +192,10 @@ def test_delta_early_stop(graphs):
     assert st["iterations_run"] == 1 and st["last_delta_max"] > 0
 
 
-def test_atomic_add_variant_runs(graphs):
+@pytest.mark.parametrize("flags", [capi.PGSGD_FLAG_EXCH_WRITE, capi.PGSGD_FLAG_PLAIN_STORE])
+def test_write_variants_run(graphs, flags):
     gd, go = graphs["DRB1-3123"]
-    cd = capi.layout_defaults(gd, flags=capi.PGSGD_FLAG_ATOMIC_ADD)
+    cd = capi.layout_defaults(gd, flags=flags)
     X0, Y0 = orc.layout_init(go, seed=42)
     X, Y, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
     s0 = orc.path_stress_2d(go, X0, Y0, 200000, 5)
