@@ -75,8 +75,22 @@ typedef struct pgsgd_config {
     uint32_t batch;                        /* terms a stream keeps in flight (1, 2 or 4); 0 = default (1).
                                               batch 1 applies a stream's terms strictly in order */
     uint32_t flags;                        /* PGSGD_FLAG_* */
-    uint32_t reserved;
+    uint32_t sampling;                     /* PGSGD_SAMPLING_*: how the first step of a term is chosen */
 } pgsgd_config;
+
+/* First-step sampling.  The partner of a term is always drawn by the reference's rule.
+ *  STREAM: every worker stream draws its first step i.i.d. uniform over all steps, exactly like a reference worker
+ *          thread (path_sgd_layout.cpp:175-182) — the device streams are bit-identical to CPU worker threads with the
+ *          same seeds.  Two random 16-byte HBM reads per term.
+ *  TILE  : the step array is cut into tiles of 2048 consecutive steps; a CTA stages a tile in shared memory with
+ *          coalesced 128-bit loads and uses each of its steps once as a first step; tile visits follow per-pass
+ *          bijections, so over an iteration every step is a first step exactly floor(U/S) (+1) times — the same
+ *          uniform marginal with the first pick's sampling noise removed.  ~1 random HBM read per term or fewer.
+ *  AUTO  : TILE for graphs whose step records exceed the L2 (>= 2^22 steps) and that are large enough for the
+ *          in-flight cap, else STREAM. */
+#define PGSGD_SAMPLING_AUTO   0u
+#define PGSGD_SAMPLING_STREAM 1u
+#define PGSGD_SAMPLING_TILE   2u
 
 /* Coordinate write flavour.  Default (no flag): red.global.add of the displacement — no update is ever lost; a single
  * worker stream gives bit-identical results to the load/compute/store of the reference (tests/test_gpu_parity.py).

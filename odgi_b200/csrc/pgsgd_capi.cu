@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -93,6 +94,7 @@ int check_config(const pgsgd_config* c) {
     if (!(c->theta > 0.0 && c->theta < 1.0)) return fail(PGSGD_ERR_ARG, "theta must be in (0,1)");
     if (!(c->eta_max > 0.0)) return fail(PGSGD_ERR_ARG, "eta_max must be > 0");
     if (c->batch != 0 && c->batch != 1 && c->batch != 2 && c->batch != 4) return fail(PGSGD_ERR_ARG, "batch must be 0, 1, 2 or 4");
+    if (c->sampling > PGSGD_SAMPLING_TILE) return fail(PGSGD_ERR_ARG, "sampling must be PGSGD_SAMPLING_AUTO, _STREAM or _TILE");
     return PGSGD_OK;
 }
 
@@ -225,37 +227,64 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     const uint64_t U = cfg->min_term_updates;
     const uint64_t U_rank = U / e->n_ranks + ((uint64_t) e->rank < U % e->n_ranks ? 1 : 0);
 
-    // launch shape: a whole number of resident waves of the persistent grid
-    const int batch = cfg->batch ? (int) cfg->batch : 1;
+    // ---- sampling mode and launch shape ----
     const int block = 256;
-    const size_t smem_need = (e->P + 1) * sizeof(uint64_t);
-    const bool smem_paths = smem_need <= 200 * 1024;
-    const size_t smem = smem_paths ? smem_need : 0;
+    const size_t smem_first = (e->P + 1) * sizeof(uint64_t);
+    bool tile_mode = cfg->sampling == PGSGD_SAMPLING_TILE || (cfg->sampling == PGSGD_SAMPLING_AUTO && e->S >= (1ull << 22));
+    int batch = cfg->batch ? (int) cfg->batch : (tile_mode ? 4 : 1);
+    if (tile_mode && batch == 1) batch = 2;
+    bool smem_paths = false;
+    size_t smem = 0;
     int blocks_per_sm = 0;
-    CU(iteration_occupancy(dims, batch, block, smem, smem_paths, &blocks_per_sm));
-    if (blocks_per_sm < 1) return fail(PGSGD_ERR_CUDA, "iteration kernel does not fit on an SM (smem %zu)", smem);
-    uint64_t n_streams = cfg->n_streams;
-    if (n_streams == 0) {
-        n_streams = (uint64_t) e->sm_count * blocks_per_sm * block;
-        // Hogwild staleness: with more than ~N/4 terms in flight the final stress of small graphs drifts away from the
-        // reference's (measured: profiles/r01_stream_sweep.md); large graphs are not affected by this cap
-        uint64_t cap = (e->N / 4) / batch;
-        if (cap < 32) cap = 32;
-        if (n_streams > cap) n_streams = cap;
-        // keep at least ~64 terms per stream so the launch is not all prologue
-        const uint64_t want = (U_rank + 63) / 64;
-        if (want < n_streams) n_streams = want;
-        if (n_streams >= (uint64_t) block) n_streams = (n_streams / block) * block;
-        else n_streams = ((n_streams + 31) / 32) * 32;
-        if (n_streams == 0) n_streams = 32;
-    }
+    uint64_t n_streams = 0;
     LaunchShape shape;
-    shape.block = n_streams < (uint64_t) block ? (int) ((n_streams + 31) / 32 * 32) : block;
-    shape.grid = (int) ((n_streams + shape.block - 1) / shape.block);
-    shape.smem = smem;
+    if (tile_mode) {
+        const size_t tile_bytes = (size_t) TILE_STEPS * sizeof(StepRec);
+        smem_paths = tile_bytes + smem_first <= 200 * 1024;
+        smem = tile_bytes + (smem_paths ? smem_first : 0);
+        CU(tile_occupancy(dims, batch, smem, smem_paths, &blocks_per_sm));
+        if (blocks_per_sm < 1) return fail(PGSGD_ERR_CUDA, "tile kernel does not fit on an SM (smem %zu)", smem);
+        uint64_t grid = (uint64_t) e->sm_count * blocks_per_sm;
+        if (cfg->n_streams) grid = (cfg->n_streams + block - 1) / block;
+        // Hogwild staleness cap (see below): terms in flight = grid * block * batch
+        const uint64_t cap_grid = (e->N / 4) / ((uint64_t) block * batch);
+        if (!cfg->n_streams && grid > cap_grid) grid = cap_grid;
+        if (grid == 0) {
+            if (cfg->sampling == PGSGD_SAMPLING_TILE) grid = 1; else tile_mode = false;
+        }
+        if (tile_mode) {
+            n_streams = grid * block;
+            shape.block = block; shape.grid = (int) grid; shape.smem = smem;
+        }
+    }
+    if (!tile_mode) {
+        batch = cfg->batch ? (int) cfg->batch : 1;
+        smem_paths = smem_first <= 200 * 1024;
+        smem = smem_paths ? smem_first : 0;
+        CU(iteration_occupancy(dims, batch, block, smem, smem_paths, &blocks_per_sm));
+        if (blocks_per_sm < 1) return fail(PGSGD_ERR_CUDA, "iteration kernel does not fit on an SM (smem %zu)", smem);
+        n_streams = cfg->n_streams;
+        if (n_streams == 0) {
+            n_streams = (uint64_t) e->sm_count * blocks_per_sm * block;
+            // Hogwild staleness: with more than ~N/4 terms in flight the final stress of small graphs drifts away from the
+            // reference's (measured: profiles/r01_stream_sweep.md); large graphs are not affected by this cap
+            uint64_t cap = (e->N / 4) / batch;
+            if (cap < 32) cap = 32;
+            if (n_streams > cap) n_streams = cap;
+            // keep at least ~64 terms per stream so the launch is not all prologue
+            const uint64_t want = (U_rank + 63) / 64;
+            if (want < n_streams) n_streams = want;
+            if (n_streams >= (uint64_t) block) n_streams = (n_streams / block) * block;
+            else n_streams = ((n_streams + 31) / 32) * 32;
+            if (n_streams == 0) n_streams = 32;
+        }
+        shape.block = n_streams < (uint64_t) block ? (int) ((n_streams + 31) / 32 * 32) : block;
+        shape.grid = (int) ((n_streams + shape.block - 1) / shape.block);
+        shape.smem = smem;
+    }
 
     if (iter_begin == 0 || e->rng_streams != n_streams) {
-        if (iter_begin != 0) return fail(PGSGD_ERR_STATE, "continuing a schedule needs the same n_streams as the call that started it");
+        if (iter_begin != 0) return fail(PGSGD_ERR_STATE, "continuing a schedule needs the same launch shape as the call that started it");
         rc = ensure_rng(e, n_streams);
         if (rc) return rc;
         // worker stream t of rank r is the reference's worker thread (r * n_streams + t): seed + tid (path_sgd_layout.cpp:168)
@@ -293,6 +322,17 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     p.counted = e->d_counted;
     p.flags = cfg->flags;
     p.smem_paths = smem_paths ? 1u : 0u;
+    if (tile_mode) {
+        // tile visits of the WHOLE job (all ranks); rank r takes visits v = r (mod n_ranks)
+        const uint64_t W = TILE_STEPS;
+        p.n_tiles = (e->S + W - 1) / W;
+        const uint64_t q = U / e->S, rU = U % e->S;
+        const uint64_t extra = (rU + W - 1) / W;
+        p.n_visits = q * p.n_tiles + extra;
+        p.last_visit_terms = rU ? rU - (extra - 1) * W : W;
+        p.visit_rank = (uint32_t) e->rank;
+        p.visit_nranks = (uint32_t) e->n_ranks;
+    }
 
     CU(cudaEventRecord(e->ev0, e->stream));
     uint64_t iter = iter_begin;
@@ -306,12 +346,24 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
             p.sp.cooling = iter >= first_cooling_iteration;  // path_sgd_layout.cpp:153 (adj_theta is unused in 2D, :213)
         }
         p.sp.zipf = make_zipf_const(theta_zipf);
+        if (tile_mode) {
+            // one bijection of the tile index per pass: i -> (i * mul + add) mod n_tiles with gcd(mul, n_tiles) = 1
+            uint64_t sm = cfg->seed ^ (0x9e3779b97f4a7c15ULL * (iter + 1));
+            for (int k = 0; k < 16; ++k) {
+                uint64_t mul;
+                do { mul = splitmix64_next(sm) % p.n_tiles; } while (p.n_tiles > 1 && (mul == 0 || std::gcd(mul, p.n_tiles) != 1));
+                if (p.n_tiles == 1) mul = 1;
+                p.perm_mul[k] = mul;
+                p.perm_add[k] = splitmix64_next(sm) % p.n_tiles;
+            }
+        }
         if (track_delta) CU(cudaMemsetAsync(e->d_delta, 0, sizeof(unsigned int), e->stream));
         if (sum_deltas) {
             if (dims == 2) CU(cudaMemcpyAsync(e->d_xy_prev, e->d_xy, 4 * e->N * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
             else CU(cudaMemcpyAsync(e->d_x1d_prev, e->d_x1d, e->N * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
         }
-        CU(launch_iteration(dims, batch, p, shape, e->stream));
+        if (tile_mode) CU(launch_tile_iteration(dims, batch, p, shape, e->stream));
+        else CU(launch_iteration(dims, batch, p, shape, e->stream));
         ++st.kernel_launches;
         if (e->comm) {
             // one collective per cooling-schedule step: coordinates are replicated, term updates are sharded

@@ -153,24 +153,11 @@ __device__ __forceinline__ uint32_t find_path(FirstPtr first, uint32_t P, uint64
     return lo;
 }
 
-// One worker draw — the order of RNG consumption is the reference's (2D: path_sgd_layout.cpp:182-262,
-// 1D: path_sgd.cpp:222-279): step, [coin], [direction coin], Zipf | uniform partner, [end a, end b]
-template <int DIMS, typename FirstPtr>
-__device__ __forceinline__ void draw_term(const SamplerParams& sp, FirstPtr first, Xoshiro& g, Term& t) {
-    const uint64_t step_index = draw_uniform(g, sp.step_count);
-    const uint32_t p = find_path(first, sp.path_count, step_index);
-    const uint64_t f = first[p];
-    const uint64_t count = first[p + 1] - f;
-    t.step_index = step_index;
-    t.path = p;
-    t.flip_a = t.flip_b = 0;
-    t.ia = t.ib = step_index;
-    if (count == 1) {  // `continue` without counting (path_sgd_layout.cpp:190-192)
-        t.valid = 0;
-        return;
-    }
-    t.valid = 1;
-    const uint64_t s_rank = step_index - f;
+// The partner draw given the first step (path start f, step count, rank s_rank): [coin], [direction coin],
+// Zipf | uniform partner, [end a, end b] — the reference's order of RNG consumption (2D: path_sgd_layout.cpp:205-262,
+// 1D: path_sgd.cpp:245-279).  Shared by the stream kernel, the tile kernel and the verification hook.
+template <int DIMS>
+__device__ __forceinline__ void draw_partner(const SamplerParams& sp, Xoshiro& g, uint64_t f, uint64_t count, uint64_t s_rank, Term& t) {
     uint64_t rank_b;
     if (sp.cooling || draw_flip(g)) {
         const bool backward = (s_rank > 0 && draw_flip(g)) || s_rank == count - 1;
@@ -188,6 +175,32 @@ __device__ __forceinline__ void draw_term(const SamplerParams& sp, FirstPtr firs
         t.flip_a = draw_flip(g);
         t.flip_b = draw_flip(g);
     }
+}
+
+// Resolve a global step index to its path and draw the partner.  valid = 0 for a step of a 1-step path
+// (`continue` without counting, path_sgd_layout.cpp:190-192).
+template <int DIMS, typename FirstPtr>
+__device__ __forceinline__ void draw_term_at(const SamplerParams& sp, FirstPtr first, Xoshiro& g, uint64_t step_index, Term& t) {
+    const uint32_t p = find_path(first, sp.path_count, step_index);
+    const uint64_t f = first[p];
+    const uint64_t count = first[p + 1] - f;
+    t.step_index = step_index;
+    t.path = p;
+    t.flip_a = t.flip_b = 0;
+    t.ia = t.ib = step_index;
+    if (count == 1) {
+        t.valid = 0;
+        return;
+    }
+    t.valid = 1;
+    draw_partner<DIMS>(sp, g, f, count, step_index - f, t);
+}
+
+// One worker draw exactly as a reference worker thread makes it: uniform first step over all steps
+// (path_sgd_layout.cpp:182), then the partner.
+template <int DIMS, typename FirstPtr>
+__device__ __forceinline__ void draw_term(const SamplerParams& sp, FirstPtr first, Xoshiro& g, Term& t) {
+    draw_term_at<DIMS>(sp, first, g, draw_uniform(g, sp.step_count), t);
 }
 
 // ---- L2 residency control ---------------------------------------------------------------------------

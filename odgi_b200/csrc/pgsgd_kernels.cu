@@ -222,6 +222,189 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
     if (threadIdx.x == 0 && block_counted) atomicAdd(p.counted, block_counted);
 }
 
+
+// --------------------------------------------------------------------------------------------------
+// tile-sampling iteration kernel
+//
+// The stream kernel above is bound by the RANDOM-ACCESS rate of HBM (~40 G 32-byte sectors/s measured, profiles/):
+// two random step-record reads per term.  Here a CTA stages TILE_STEPS consecutive step records in shared memory with
+// fully coalesced 128-bit loads (a DRAM-page-friendly stream) and uses every staged step exactly once as the first
+// step of a term; the partner is drawn with the reference's rule (coin, direction, dirty Zipf | uniform in path) and
+// is served from the tile when it falls inside it (~45 % of Zipf partners), else by one random 16-byte load.
+// Over a launch the tile visits follow per-pass bijections of the tile index, so every step is the first step of
+// exactly floor(U/S) terms (+1 for a prefix): the reference's "uniform over all steps" (path_sgd_layout.cpp:175-182)
+// with the sampling noise of the first pick removed; the conditional law of the partner is unchanged.
+// Consecutive lanes hold consecutive steps, so their coordinate reads/reds of the first node coalesce as well.
+// --------------------------------------------------------------------------------------------------
+template <int DIMS, int BATCH, bool SMEM_PATHS>
+__global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(const __grid_constant__ IterParams p) {
+    constexpr int ROUNDS = TILE_STEPS / 256;
+    static_assert(ROUNDS % BATCH == 0, "tile rounds must be a multiple of the batch");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long block_counted;
+    uint4* const tile = reinterpret_cast<uint4*>(smem_raw);
+    const uint64_t* first;
+    if (SMEM_PATHS) {
+        uint64_t* sfirst = reinterpret_cast<uint64_t*>(smem_raw + (size_t) TILE_STEPS * sizeof(uint4));
+        for (uint32_t i = threadIdx.x; i <= p.sp.path_count; i += blockDim.x) sfirst[i] = p.sp.path_first[i];
+        first = sfirst;
+    } else {
+        first = p.sp.path_first;
+    }
+    if (threadIdx.x == 0) block_counted = 0;
+
+    const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    Xoshiro g;
+    g.s0 = p.rng[tid];
+    g.s1 = p.rng[p.rng_stride + tid];
+    g.s2 = p.rng[2 * p.rng_stride + tid];
+    g.s3 = p.rng[3 * p.rng_stride + tid];
+    const float eta_f = __double2float_rn(p.eta);
+    const bool atomic_add = (p.flags & 5u) == 0;
+    const bool st_mode = (p.flags & 4u) != 0;
+    float2* const xy2 = reinterpret_cast<float2*>(p.xy);
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_last();
+    uint64_t done = 0;
+    float delta_max = 0.0f;
+
+    // visits of this rank: v = visit_rank + k * visit_nranks; CTA c takes k = c, c + gridDim.x, ...
+    for (uint64_t k = blockIdx.x;; k += gridDim.x) {
+        const uint64_t v = (uint64_t) p.visit_rank + k * p.visit_nranks;
+        if (v >= p.n_visits) break;
+        const uint64_t pass = v / p.n_tiles, i = v - pass * p.n_tiles;
+        const uint64_t t_idx = (i * p.perm_mul[pass & 15] + p.perm_add[pass & 15]) % p.n_tiles;
+        const uint64_t base = t_idx * (uint64_t) TILE_STEPS;
+        const uint32_t terms = v + 1 == p.n_visits ? (uint32_t) p.last_visit_terms : (uint32_t) TILE_STEPS;
+        __syncthreads();  // the previous visit's readers are done with the tile
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const uint32_t j = r * 256 + threadIdx.x;
+            if (base + j < p.sp.step_count) tile[j] = load_step(p.steps, base + j, pol_stream);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int r0 = 0; r0 < ROUNDS; r0 += BATCH) {
+            Term t[BATCH];
+            uint4 ra[BATCH], rb[BATCH];
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                const uint32_t j = (r0 + b) * 256 + threadIdx.x;
+                t[b].valid = 0;
+                if (j < terms && base + j < p.sp.step_count) draw_term_at<DIMS>(p.sp, first, g, base + j, t[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < BATCH; ++b) {
+                if (t[b].valid) {
+                    ra[b] = tile[t[b].ia - base];
+                    const uint64_t off = t[b].ib - base;  // wraps to a huge value when ib < base
+                    if (off < (uint64_t) TILE_STEPS) rb[b] = tile[off];
+                    else rb[b] = load_step(p.steps, t[b].ib, pol_stream);
+                }
+            }
+            if (DIMS == 2) {
+                float2 ca[BATCH], cb[BATCH];
+                float2* pa[BATCH];
+                float2* pb[BATCH];
+                float dij[BATCH];
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    if (t[b].valid) {
+                        uint64_t pos_a = step_pos(ra[b]), pos_b = step_pos(rb[b]);
+                        uint32_t end_a = ra[b].x & 1u, end_b = rb[b].x & 1u;
+                        if (t[b].flip_a) { pos_a += ra[b].y; end_a ^= 1u; }
+                        if (t[b].flip_b) { pos_b += rb[b].y; end_b ^= 1u; }
+                        const uint64_t dpos = pos_a > pos_b ? pos_a - pos_b : pos_b - pos_a;
+                        dij[b] = dpos ? __ull2float_rn(dpos) : 1e-9f;
+                        pa[b] = xy2 + ((uint64_t) (ra[b].x >> 1) * 2 + end_a);
+                        pb[b] = xy2 + ((uint64_t) (rb[b].x >> 1) * 2 + end_b);
+                        ca[b] = ld_coord2(pa[b], pol_keep);
+                        cb[b] = ld_coord2(pb[b], pol_keep);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    if (t[b].valid) {
+                        float mu = __fdiv_rn(eta_f, dij[b]);
+                        if (mu > 1.0f) mu = 1.0f;
+                        float dx = __fsub_rn(ca[b].x, cb[b].x);
+                        const float dy = __fsub_rn(ca[b].y, cb[b].y);
+                        if (dx == 0.0f) dx = 1e-9f;
+                        const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+                        const float Delta = __fmul_rn(__fmul_rn(mu, __fsub_rn(mag, dij[b])), 0.5f);
+                        delta_max = fmaxf(delta_max, fabsf(Delta));
+                        const float r = __fdiv_rn(Delta, mag);
+                        const float r_x = __fmul_rn(r, dx);
+                        const float r_y = __fmul_rn(r, dy);
+                        if (atomic_add) {
+                            red_coord2(pa[b], -r_x, -r_y, pol_keep);
+                            red_coord2(pb[b], r_x, r_y, pol_keep);
+                        } else {
+                            const float2 na = make_float2(__fsub_rn(ca[b].x, r_x), __fsub_rn(ca[b].y, r_y));
+                            st_coord(pa[b], na, st_mode);
+                            const float2 bs = (pa[b] == pb[b]) ? na : cb[b];
+                            st_coord(pb[b], make_float2(__fadd_rn(bs.x, r_x), __fadd_rn(bs.y, r_y)), st_mode);
+                        }
+                        ++done;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < BATCH; ++b) {
+                    if (t[b].valid) {
+                        const uint32_t na = ra[b].x >> 1, nb = rb[b].x >> 1;
+                        uint32_t u = 3u;
+                        if (p.frozen) {
+                            if (p.frozen[na]) u &= ~1u;
+                            if (p.frozen[nb]) u &= ~2u;
+                        }
+                        const double d = fabs(__dsub_rn(__ull2double_rn(step_pos(ra[b])), __ull2double_rn(step_pos(rb[b]))));
+                        if (u == 0) { ++done; continue; }
+                        if (d == 0.0) continue;
+                        double* qa = p.x1d + na;
+                        double* qb = p.x1d + nb;
+                        const double xa = ld_coord1(qa, pol_keep), xb = ld_coord1(qb, pol_keep);
+                        double mu = __dmul_rn(p.eta, __ddiv_rn(1.0, d));
+                        if (mu > 1.0) mu = 1.0;
+                        double dx = __dsub_rn(xa, xb);
+                        if (dx == 0.0) dx = 1e-9;
+                        const double mag = fabs(dx);
+                        const double Delta = __dmul_rn(__dmul_rn(mu, __dsub_rn(mag, d)), 0.5);
+                        delta_max = fmaxf(delta_max, (float) fabs(Delta));
+                        const double r_x = __dmul_rn(__ddiv_rn(Delta, mag), dx);
+                        if (atomic_add) {
+                            if (u & 1u) red_coord1(qa, -r_x, pol_keep);
+                            if (u & 2u) red_coord1(qb, r_x, pol_keep);
+                        } else {
+                            const double nav = __dsub_rn(xa, r_x);
+                            if (u & 1u) st_coord(qa, nav, st_mode);
+                            const double bs = (qa == qb && (u & 1u)) ? nav : xb;
+                            if (u & 2u) st_coord(qb, __dadd_rn(bs, r_x), st_mode);
+                        }
+                        ++done;
+                    }
+                }
+            }
+        }
+    }
+    p.rng[tid] = g.s0;
+    p.rng[p.rng_stride + tid] = g.s1;
+    p.rng[2 * p.rng_stride + tid] = g.s2;
+    p.rng[3 * p.rng_stride + tid] = g.s3;
+
+    unsigned long long wsum = done;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&block_counted, wsum);
+    if (p.delta_max_bits) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) delta_max = fmaxf(delta_max, __shfl_xor_sync(0xffffffffu, delta_max, o));
+        if ((threadIdx.x & 31) == 0) atomicMax(p.delta_max_bits, __float_as_uint(delta_max));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && block_counted) atomicAdd(p.counted, block_counted);
+}
+
 __global__ void seed_streams_kernel(uint64_t* rng, uint64_t stride, uint64_t n, uint64_t seed_base) {
     const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -340,6 +523,40 @@ cudaError_t occupancy_t(int block, size_t smem, bool smem_paths, int* out) {
 inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n + block - 1) / block); }
 
 }  // namespace
+
+template <int DIMS, int BATCH, bool SP>
+cudaError_t tile_launch_one(const IterParams& p, const LaunchShape& s, cudaStream_t stream) {
+    auto k = pgsgd_tile_kernel<DIMS, BATCH, SP>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
+    if (e != cudaSuccess) return e;
+    k<<<s.grid, s.block, s.smem, stream>>>(p);
+    return cudaGetLastError();
+}
+template <int DIMS, int BATCH, bool SP>
+cudaError_t tile_occ_one(size_t smem, int* out) {
+    auto k = pgsgd_tile_kernel<DIMS, BATCH, SP>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, 256, smem);
+}
+
+cudaError_t launch_tile_iteration(int dims, int batch, const IterParams& p, const LaunchShape& shape, cudaStream_t stream) {
+    if (shape.block != 256) return cudaErrorInvalidValue;
+    const bool sp = p.smem_paths != 0;
+    if (dims == 2 && batch == 4) return sp ? tile_launch_one<2, 4, true>(p, shape, stream) : tile_launch_one<2, 4, false>(p, shape, stream);
+    if (dims == 2 && batch == 2) return sp ? tile_launch_one<2, 2, true>(p, shape, stream) : tile_launch_one<2, 2, false>(p, shape, stream);
+    if (dims == 1 && batch == 4) return sp ? tile_launch_one<1, 4, true>(p, shape, stream) : tile_launch_one<1, 4, false>(p, shape, stream);
+    if (dims == 1 && batch == 2) return sp ? tile_launch_one<1, 2, true>(p, shape, stream) : tile_launch_one<1, 2, false>(p, shape, stream);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t tile_occupancy(int dims, int batch, size_t smem, bool sp, int* out) {
+    if (dims == 2 && batch == 4) return sp ? tile_occ_one<2, 4, true>(smem, out) : tile_occ_one<2, 4, false>(smem, out);
+    if (dims == 2 && batch == 2) return sp ? tile_occ_one<2, 2, true>(smem, out) : tile_occ_one<2, 2, false>(smem, out);
+    if (dims == 1 && batch == 4) return sp ? tile_occ_one<1, 4, true>(smem, out) : tile_occ_one<1, 4, false>(smem, out);
+    if (dims == 1 && batch == 2) return sp ? tile_occ_one<1, 2, true>(smem, out) : tile_occ_one<1, 2, false>(smem, out);
+    return cudaErrorInvalidValue;
+}
 
 cudaError_t launch_seed_streams(uint64_t* rng, uint64_t rng_stride, uint64_t n, uint64_t seed_base, cudaStream_t stream) {
     if (!n) return cudaSuccess;

@@ -24,7 +24,16 @@ struct IterParams {
     unsigned long long* counted;   // total counted updates (atomicAdd once per block)
     uint32_t flags;             // PGSGD_FLAG_* write flavour bits
     uint32_t smem_paths;        // 1: path_first table staged in shared memory
+    // ---- tile sampling (pgsgd_tile_kernel) ----
+    uint64_t n_visits;          // tile visits of this launch (all ranks); visit v is handled by CTA v % gridDim of rank v % n_ranks
+    uint64_t n_tiles;           // ceil(S / TILE_STEPS)
+    uint64_t last_visit_terms;  // terms of the final visit (<= TILE_STEPS)
+    uint64_t perm_mul[16];      // per pass: tile = (i * perm_mul[pass] + perm_add[pass]) % n_tiles, a bijection on [0, n_tiles)
+    uint64_t perm_add[16];
+    uint32_t visit_rank, visit_nranks;  // this rank handles visits v with v % visit_nranks == visit_rank
 };
+
+constexpr int TILE_STEPS = 2048;   // steps staged in shared memory per tile visit (32 KB of 16-byte records)
 
 struct LaunchShape {
     int block;           // threads per block
@@ -37,6 +46,9 @@ cudaError_t launch_seed_streams(uint64_t* rng, uint64_t rng_stride, uint64_t n, 
 
 // one iteration of 2D / 1D PG-SGD
 cudaError_t launch_iteration(int dims, int batch, const IterParams& p, const LaunchShape& shape, cudaStream_t stream);
+// the same with tile sampling (TILE_STEPS consecutive steps staged in shared memory per visit)
+cudaError_t launch_tile_iteration(int dims, int batch, const IterParams& p, const LaunchShape& shape, cudaStream_t stream);
+cudaError_t tile_occupancy(int dims, int batch, size_t smem, bool smem_paths, int* blocks_per_sm);
 // occupancy query for the kernel variant (resident blocks per SM for the given block size / smem)
 cudaError_t iteration_occupancy(int dims, int batch, int block, size_t smem, bool smem_paths, int* blocks_per_sm);
 

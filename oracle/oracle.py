@@ -84,6 +84,9 @@ def lib():
         L.orc_layout_2d_f32.restype = C.c_uint64
         L.orc_sort_1d.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_void_p, C.c_void_p]
         L.orc_sort_1d.restype = C.c_uint64
+        L.orc_run_range.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_run_range.restype = C.c_uint64
         L.orc_replay_single.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_int, C.c_uint64, C.c_uint64, C.c_double,
                                         C.c_double, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_replay_single.restype = C.c_uint64
@@ -271,6 +274,45 @@ def sort_1d(g: Graph, cfg: Config, X, n_streams: int = 1, frozen=None):
     gc, cc = g.c(), cfg.c()
     n = lib().orc_sort_1d(C.byref(gc), C.byref(cc), n_streams, _ptr(fz), _ptr(X))
     return int(n), X
+
+
+def run_range(g: Graph, cfg: Config, n_streams: int, seed_base: int, updates: int, iter_begin: int, iter_end: int, mode: int,
+              X=None, Y=None, xy=None, frozen=None, rng_state=None) -> int:
+    """iterations [iter_begin, iter_end) in place on the given (contiguous, correctly typed) coordinate arrays"""
+    gc, cc = g.c(), cfg.c()
+    return int(lib().orc_run_range(C.byref(gc), C.byref(cc), n_streams, seed_base, updates, iter_begin, iter_end, mode,
+                                   _ptr(X), _ptr(Y), _ptr(xy), _ptr(frozen), _ptr(rng_state)))
+
+
+def emulate_multirank_2d_f32(g: Graph, cfg: Config, xy0, n_ranks: int, n_streams: int, sum_deltas: bool = False,
+                             syncs_per_iter: int = 1):
+    """Single-process emulation of the multi-GPU schedule of pgsgd_engine_run_2d with a communicator attached:
+    every iteration is cut into syncs_per_iter slices; in each slice every rank performs its share of the slice's
+    updates with its own worker streams (seed + rank*n_streams + t) on its replica, then the replicas are averaged in
+    fp32 (all-reduce AVG) or the displacements are summed.  Returns the common coordinates after the last iteration."""
+    reps = [np.ascontiguousarray(xy0, dtype=np.float32).copy() for _ in range(n_ranks)]
+    states = [np.zeros(4 * n_streams, dtype=np.uint64) for _ in range(n_ranks)]
+    U = cfg.min_term_updates
+    for it in range(cfg.iter_max):
+        for k in range(syncs_per_iter):
+            u_slice = U // syncs_per_iter + (1 if k < U % syncs_per_iter else 0)
+            prev = reps[0].copy()
+            for r in range(n_ranks):
+                share = u_slice // n_ranks + (1 if r < u_slice % n_ranks else 0)
+                run_range(g, cfg, n_streams, cfg.seed + r * n_streams, share, it, it + 1, 1, xy=reps[r], rng_state=states[r])
+            if sum_deltas:
+                acc = np.zeros_like(prev)
+                for r in range(n_ranks):
+                    acc = acc + (reps[r] - prev)
+                merged = prev + acc
+            else:
+                acc = reps[0].copy()
+                for r in range(1, n_ranks):
+                    acc = acc + reps[r]
+                merged = (acc / np.float32(n_ranks)).astype(np.float32)
+            for r in range(n_ranks):
+                reps[r][...] = merged
+    return reps[0]
 
 
 def replay_single(g: Graph, cfg: Config, dims: int, n_terms: int, switch_at: int, eta0: float, eta1: float,

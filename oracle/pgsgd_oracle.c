@@ -338,19 +338,29 @@ static void tables_init(run_tables* rt, const orc_config* c) {
 }
 static void tables_free(run_tables* rt) { free(rt->etas); free(rt->zetas); }
 
-/* mode: 0 = 2D fp64, 1 = 2D fp32 model, 2 = 1D */
-static uint64_t run_streams(const orc_graph* g, const orc_config* c, uint64_t n_streams, int mode, double* X, double* Y,
-                            float* xy, const uint8_t* frozen) {
+/* mode: 0 = 2D fp64, 1 = 2D fp32 model, 2 = 1D.
+ * Runs iterations [iter_begin, iter_end) of the schedule with `updates` counted updates per iteration.  rng_state
+ * (nullable, 4*n_streams words) carries the worker streams across calls; streams are seeded seed_base + t when no
+ * state is supplied or the supplied state is still all-zero. */
+static uint64_t run_streams_range(const orc_graph* g, const orc_config* c, uint64_t n_streams, uint64_t seed_base, uint64_t updates,
+                                  uint64_t iter_begin, uint64_t iter_end, int mode, double* X, double* Y, float* xy,
+                                  const uint8_t* frozen, uint64_t* rng_state) {
     if (!any_path_with_more_than_one_step(g)) return 0; /* path_sgd_layout.cpp:64-74 */
     run_tables rt;
     tables_init(&rt, c);
     orc_rng* rngs = (orc_rng*) malloc(sizeof(orc_rng) * n_streams);
     uint64_t* remaining = (uint64_t*) malloc(sizeof(uint64_t) * n_streams);
-    for (uint64_t t = 0; t < n_streams; ++t) orc_rng_seed(&rngs[t], c->seed + t);
+    /* an all-zero state is not a valid xoshiro state: it marks "not seeded yet" */
+    if (!rng_state || (rng_state[0] | rng_state[1] | rng_state[2] | rng_state[3]) == 0) {
+        for (uint64_t t = 0; t < n_streams; ++t) orc_rng_seed(&rngs[t], seed_base + t);
+    } else {
+        memcpy(rngs, rng_state, sizeof(orc_rng) * n_streams);
+    }
     const int dims = mode == 2 ? 1 : 2;
-    const uint64_t n_iters = mode == 2 ? c->iter_max + 1 : c->iter_max;
+    uint64_t n_iters = mode == 2 ? c->iter_max + 1 : c->iter_max;
+    if (iter_end < n_iters) n_iters = iter_end;
     uint64_t counted = 0;
-    for (uint64_t iter = 0; iter < n_iters; ++iter) {
+    for (uint64_t iter = iter_begin; iter < n_iters; ++iter) {
         const double eta = rt.etas[iter];
         int cooling;
         double theta_zipf = c->theta;
@@ -360,7 +370,7 @@ static uint64_t run_streams(const orc_graph* g, const orc_config* c, uint64_t n_
         } else {
             cooling = iter >= rt.first_cooling_iteration; /* path_sgd_layout.cpp:153; adj_theta unused in 2D (:213) */
         }
-        uint64_t base = c->min_term_updates / n_streams, rem = c->min_term_updates % n_streams;
+        uint64_t base = updates / n_streams, rem = updates % n_streams;
         uint64_t live = 0;
         for (uint64_t t = 0; t < n_streams; ++t) { remaining[t] = base + (t < rem ? 1 : 0); live += remaining[t] != 0; }
         double delta_max = 0;
@@ -382,10 +392,22 @@ static uint64_t run_streams(const orc_graph* g, const orc_config* c, uint64_t n_
          * in practice; Delta_max is re-armed to delta at every boundary :152) */
         if (c->delta > 0 && iter + 1 < n_iters && delta_max <= c->delta) break;
     }
+    if (rng_state) memcpy(rng_state, rngs, sizeof(orc_rng) * n_streams);
     free(rngs);
     free(remaining);
     tables_free(&rt);
     return counted;
+}
+
+static uint64_t run_streams(const orc_graph* g, const orc_config* c, uint64_t n_streams, int mode, double* X, double* Y,
+                            float* xy, const uint8_t* frozen) {
+    return run_streams_range(g, c, n_streams, c->seed, c->min_term_updates, 0, UINT64_MAX, mode, X, Y, xy, frozen, NULL);
+}
+
+uint64_t orc_run_range(const orc_graph* g, const orc_config* c, uint64_t n_streams, uint64_t seed_base, uint64_t updates,
+                       uint64_t iter_begin, uint64_t iter_end, int mode, double* X, double* Y, float* xy,
+                       const uint8_t* frozen, uint64_t* rng_state) {
+    return run_streams_range(g, c, n_streams, seed_base, updates, iter_begin, iter_end, mode, X, Y, xy, frozen, rng_state);
 }
 
 uint64_t orc_layout_2d(const orc_graph* g, const orc_config* c, uint64_t n_streams, double* X, double* Y) {

@@ -107,6 +107,14 @@ uint64_t orc_layout_2d(const orc_graph* g, const orc_config* c, uint64_t n_strea
 uint64_t orc_layout_2d_f32(const orc_graph* g, const orc_config* c, uint64_t n_streams, float* xy);
 uint64_t orc_sort_1d(const orc_graph* g, const orc_config* c, uint64_t n_streams, const uint8_t* frozen, double* X);
 
+/* Iterations [iter_begin, iter_end) with an explicit per-iteration update count and stream seed base: the building
+ * block used by the tests to emulate the multi-GPU schedule (each rank: its share of the updates with its own streams,
+ * then the coordinates are averaged across ranks).  mode: 0 = 2D fp64, 1 = 2D fp32 model, 2 = 1D.  rng_state
+ * (4*n_streams words, nullable) carries the streams across calls. */
+uint64_t orc_run_range(const orc_graph* g, const orc_config* c, uint64_t n_streams, uint64_t seed_base, uint64_t updates,
+                       uint64_t iter_begin, uint64_t iter_end, int mode, double* X, double* Y, float* xy,
+                       const uint8_t* frozen, uint64_t* rng_state);
+
 /* Replay helper for pinning: runs ONE stream (seed+0) for n_terms emitted terms with the cooling flag /
  * eta switching at emitted-term index switch_at (use n_terms for "never"), applying fp64 updates;
  * optionally records the terms.  This is what scripts/pin_oracle.py aligns with the reference trace. */

@@ -201,3 +201,46 @@ def test_write_variants_run(graphs, flags):
     s0 = orc.path_stress_2d(go, X0, Y0, 200000, 5)
     s1 = orc.path_stress_2d(go, X, Y, 200000, 5)
     assert np.all(np.isfinite(X)) and s1 < s0
+
+
+# ---- tile sampling (PGSGD_SAMPLING_TILE): same partner law, stratified first step -------------------------------
+
+@pytest.mark.parametrize("name", ["DRB1-3123", "chr6.C4"])
+def test_2d_tile_sampling_stress_within_reference_band(graphs, golden_dir, name):
+    gd, go = graphs[name]
+    band = _stress_band(golden_dir, f"{name}.layout2d")
+    X0, Y0 = orc.layout_init(go, seed=42)
+    vals = []
+    for seed in (9399220, 1234567, 42):
+        cd = capi.layout_defaults(gd, seed=seed, sampling=capi.SAMPLING_TILE)
+        X, Y, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
+        # every step is a first step exactly 10 times per iteration
+        assert st["term_updates"] == 30 * 10 * gd.S
+        assert np.all(np.isfinite(X)) and np.all(np.isfinite(Y))
+        vals.append(orc.path_stress_2d(go, X, Y, n_pairs=band["n_pairs"], seed=band["seed"]))
+    _assert_in_band(vals, band)
+
+
+@pytest.mark.parametrize("name", ["LPA", "DRB1-3123"])
+def test_1d_tile_sampling_stress_within_reference_band(graphs, golden_dir, name):
+    gd, go = graphs[name]
+    band = _stress_band(golden_dir, f"{name}.sort1d")
+    vals = []
+    for seed in (9399220, 1234567, 42):
+        cd = capi.sort_defaults(gd, seed=seed, sampling=capi.SAMPLING_TILE)
+        x, st = odgi_b200.sort_1d(gd, cd)
+        # 1D skips terms of zero path distance without counting them (path_sgd.cpp:320-323)
+        assert 0.97 * 101 * gd.S <= st["term_updates"] <= 101 * gd.S
+        vals.append(orc.path_stress_1d(go, x, n_pairs=band["n_pairs"], seed=band["seed"]))
+    _assert_in_band(vals, band)
+
+
+def test_tile_sampling_partial_pass_counts(graphs):
+    """U not a multiple of S: full passes + a truncated one; the counted updates are exact when the truncated pass
+    does not reach the short last tile"""
+    gd, go = graphs["chr6.C4"]
+    U = 3 * gd.S + 5000
+    cd = capi.layout_defaults(gd, iter_max=2, min_term_updates=U, sampling=capi.SAMPLING_TILE)
+    X0, Y0 = orc.layout_init(go, seed=1)
+    _, _, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
+    assert abs(int(st["term_updates"]) - 2 * U) <= 2 * 2048
