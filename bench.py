@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--sampling", type=int, default=0, help="0 auto, 1 stream (reference-exact worker streams), 2 tile")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -203,7 +204,8 @@ def main():
     g, desc = make_workload(args.workload)
     W, K = args.warmup, args.steps
     iter_max = max(30, W + K)
-    cfg = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags)
+    cfg = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags, sampling=args.sampling)
+    sampling_name = {1: "stream", 2: "tile"}.get(args.sampling, "tile" if g.S >= (1 << 22) else "stream")
     X0, Y0 = odgi_b200.layout_init(g, seed=42)
     U = cfg.min_term_updates
 
@@ -243,7 +245,13 @@ def main():
     clocks = sampler.stop()
     dev_s = max_over_ranks(st["seconds_iterations"])
     assert st["iterations_run"] == K and st["kernel_launches"] == K
-    total_updates = K * U
+    # counted term updates of the whole job (every rank reports its own share)
+    total_updates = st["term_updates"]
+    if dist is not None:
+        tt = torch.tensor([total_updates], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        total_updates = float(tt.item())
+    assert abs(total_updates - K * U) <= 1e-3 * K * U, (total_updates, K * U)
     value = total_updates / dev_s / 1e6
     Xf, Yf = e.get_coords_2d()
     finite = bool(np.all(np.isfinite(Xf)) and np.all(np.isfinite(Yf)))
@@ -261,7 +269,7 @@ def main():
         gp = capi.FlatGraph(pin(g.node_len), pin(g.path_first_step), pin(g.step_node), None if g.step_rev is None else pin(g.step_rev),
                             None if g.step_pos is None else pin(g.step_pos))
         Xp, Yp = pin(X0), pin(Y0)
-        cfg_e = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags)
+        cfg_e = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags, sampling=args.sampling)
         barrier()
         t0 = time.time()
         e2 = odgi_b200.Engine(gp, device=local_rank)        # flatten-to-device upload
@@ -275,7 +283,7 @@ def main():
         t_e2e = max_over_ranks(time.time() - t0)
         h2d = st2["h2d_bytes"]
         e2.close()
-        e2e = {"value": K * U / t_e2e / 1e6, "unit": "M updates/s", "h2d_bytes_per_step": h2d / K,
+        e2e = {"value": st2["term_updates"] * world / t_e2e / 1e6, "unit": "M updates/s", "h2d_bytes_per_step": h2d / K,
                "d2h_bytes_per_step": 4 * g.N * 8 / K, "seconds": t_e2e, "steps_in_call": K,
                "note": "one engine lifetime: graph flatten+upload from pinned host memory, coords up, K steps, coords down; host wall clock"}
 
@@ -286,7 +294,7 @@ def main():
 
     peak, peak_src = load_peaks()
     step_s = dev_s / K
-    achieved = (U / world) * BYTES_PER_UPDATE_2D / step_s / 1e9   # per-GPU kernel: its share of the step's updates
+    achieved = (total_updates / K / world) * BYTES_PER_UPDATE_2D / step_s / 1e9   # per-GPU kernel: its share of the step's updates
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
     if os.path.exists(tp):
@@ -303,14 +311,15 @@ def main():
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic" if args.workload in ("c4", "mid", "small", "tiny") else "reference test graph (flattened fixture)",
         "config": {"workload": args.workload, "description": desc, "nodes": g.N, "paths": g.P, "steps_in_graph": g.S,
-                   "updates_per_step": U, "iter_max": iter_max, "timed_iterations": [W, W + K], "batch": args.batch or 4,
+                   "updates_per_step": U, "iter_max": iter_max, "timed_iterations": [W, W + K], "sampling": sampling_name, "batch": args.batch or "auto",
                    "l2_policy": "inputs larger than L2" if g.S * 16 > 126e6 else "L2-resident graph (plumbing config)",
                    "parallelism": f"replicated coords, term updates split over {world} GPU(s), 1 NCCL all-reduce/step" if world > 1 else "1 GPU",
                    "device_bytes": dev_bytes, "coords_finite": finite},
         "gpu_launches": K * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_update": BYTES_PER_UPDATE_2D,
-                     "kernel": "pgsgd_iter_kernel<2,BATCH,smem_paths>", "kernel_ms": step_s * 1e3},
+                     "kernel": "pgsgd_tile_kernel<2,BATCH,smem_paths>" if sampling_name == "tile" else "pgsgd_iter_kernel<2,BATCH,smem_paths>",
+                     "kernel_ms": step_s * 1e3},
         "clocks": clocks, "wall_s_timed_region": wall,
     }
     if e2e:

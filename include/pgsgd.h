@@ -166,6 +166,11 @@ int pgsgd_engine_sample_terms(pgsgd_engine* e, const pgsgd_config* cfg, int dims
                               uint64_t* rank_b, uint32_t* node_a, uint32_t* node_b, uint64_t* pos_a, uint64_t* pos_b,
                               uint8_t* end_a, uint8_t* end_b, uint8_t* valid);
 
+/* Tile-sampling verification: with a trace buffer set, every term the tile kernel draws is recorded (first step,
+ * partner step as global step indices, flips = flip_a | flip_b << 1) until the buffer is full. */
+int pgsgd_engine_set_trace(pgsgd_engine* e, uint64_t capacity);   /* 0 = off */
+int pgsgd_engine_get_trace(pgsgd_engine* e, uint64_t* ia_out, uint64_t* ib_out, uint8_t* flips_out, uint64_t* n_out);
+
 /* ---- host-side helpers that mirror reference host code (pure CPU, no device needed) ---- */
 /* learning-rate schedule: path_linear_sgd_layout_schedule (path_sgd_layout.cpp:433-468); writes iter_max+1 */
 int pgsgd_schedule(const pgsgd_config* cfg, double* etas_out);

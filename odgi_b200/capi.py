@@ -57,7 +57,7 @@ EXPORTED_SYMBOLS = [
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
     "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
-    "pgsgd_engine_attach_comm", "pgsgd_engine_sample_terms", "pgsgd_schedule", "pgsgd_zetas",
+    "pgsgd_engine_attach_comm", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
 ]
 
 _lib = None
@@ -92,6 +92,8 @@ def lib():
         L.pgsgd_comm_unique_id.argtypes = [vp]
         L.pgsgd_engine_attach_comm.argtypes = [vp, vp, i32, i32]
         L.pgsgd_engine_sample_terms.argtypes = [vp, C.POINTER(ConfigC), i32, i32, dbl, u64, u64] + [vp] * 11
+        L.pgsgd_engine_set_trace.argtypes = [vp, u64]
+        L.pgsgd_engine_get_trace.argtypes = [vp, vp, vp, vp, vp]
         L.pgsgd_schedule.argtypes = [C.POINTER(ConfigC), vp]
         L.pgsgd_zetas.argtypes = [C.POINTER(ConfigC), vp, u64]
         L.pgsgd_zetas.restype = u64
@@ -313,6 +315,16 @@ class Engine:
     def attach_comm(self, unique_id: bytes, n_ranks: int, rank: int):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         _check(lib().pgsgd_engine_attach_comm(self._h, buf, n_ranks, rank))
+
+    def set_trace(self, capacity: int):
+        _check(lib().pgsgd_engine_set_trace(self._h, capacity))
+
+    def get_trace(self, capacity: int):
+        ia = np.zeros(capacity, np.uint64); ib = np.zeros(capacity, np.uint64); fl = np.zeros(capacity, np.uint8)
+        n = C.c_uint64(0)
+        _check(lib().pgsgd_engine_get_trace(self._h, _ptr(ia), _ptr(ib), _ptr(fl), C.byref(n)))
+        k = int(n.value)
+        return ia[:k], ib[:k], fl[:k]
 
     def sample_terms(self, cfg: Config, dims: int, cooling: bool, n_terms: int, stream: int = 0, theta_zipf=None):
         out = {"step_index": np.zeros(n_terms, np.uint64), "path": np.zeros(n_terms, np.uint32),

@@ -87,6 +87,16 @@ ZipfConst make_zipf_const(double theta) {
     return z;
 }
 
+ZipfConstF make_zipf_const_f(const ZipfConst& z) {
+    ZipfConstF f;
+    f.one_minus_theta = (float) z.one_minus_theta;
+    f.alpha_int = (int) z.alpha;
+    f.alpha_frac = (float) (z.alpha - (double) f.alpha_int);
+    f.zeta2 = (float) z.zeta2;
+    f.thresh2 = (float) z.thresh2;
+    return f;
+}
+
 int check_config(const pgsgd_config* c) {
     if (!c) return fail(PGSGD_ERR_ARG, "config is NULL");
     if (c->iter_max == 0) return fail(PGSGD_ERR_ARG, "iter_max must be > 0");
@@ -120,6 +130,9 @@ struct pgsgd_engine {
     uint64_t rng_streams = 0;     // streams seeded by the run in progress
     unsigned int* d_delta = nullptr;
     unsigned long long* d_counted = nullptr;
+    unsigned long long* d_trace = nullptr;        // verification trace of the tile kernel (pgsgd_engine_set_trace)
+    unsigned long long* d_trace_count = nullptr;
+    uint64_t trace_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<double> h_x1d_default;  // cumulative bp of the node order (path_sgd.cpp:63-69)
@@ -231,7 +244,7 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     const int block = 256;
     const size_t smem_first = (e->P + 1) * sizeof(uint64_t);
     bool tile_mode = cfg->sampling == PGSGD_SAMPLING_TILE || (cfg->sampling == PGSGD_SAMPLING_AUTO && e->S >= (1ull << 22));
-    int batch = cfg->batch ? (int) cfg->batch : (tile_mode ? 4 : 1);
+    int batch = cfg->batch ? (int) cfg->batch : (tile_mode ? 2 : 1);
     if (tile_mode && batch == 1) batch = 2;
     bool smem_paths = false;
     size_t smem = 0;
@@ -322,6 +335,9 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     p.counted = e->d_counted;
     p.flags = cfg->flags;
     p.smem_paths = smem_paths ? 1u : 0u;
+    p.trace = e->d_trace;
+    p.trace_count = e->d_trace_count;
+    p.trace_cap = e->trace_cap;
     if (tile_mode) {
         // tile visits of the WHOLE job (all ranks); rank r takes visits v = r (mod n_ranks)
         const uint64_t W = TILE_STEPS;
@@ -346,6 +362,7 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
             p.sp.cooling = iter >= first_cooling_iteration;  // path_sgd_layout.cpp:153 (adj_theta is unused in 2D, :213)
         }
         p.sp.zipf = make_zipf_const(theta_zipf);
+        p.sp.zipf_f = make_zipf_const_f(p.sp.zipf);
         if (tile_mode) {
             // one bijection of the tile index per pass: i -> (i * mul + add) mod n_tiles with gcd(mul, n_tiles) = 1
             uint64_t sm = cfg->seed ^ (0x9e3779b97f4a7c15ULL * (iter + 1));
@@ -552,6 +569,7 @@ void pgsgd_engine_destroy(pgsgd_engine* e) {
     cudaSetDevice(e->device);
     if (e->comm) ncclCommDestroy(e->comm);
     cudaFree(e->d_steps); cudaFree(e->d_path_first); cudaFree(e->d_xy); cudaFree(e->d_xy_prev); cudaFree(e->d_x1d);
+    cudaFree(e->d_trace); cudaFree(e->d_trace_count);
     cudaFree(e->d_x1d_prev); cudaFree(e->d_frozen); cudaFree(e->d_zetas); cudaFree(e->d_rng); cudaFree(e->d_delta); cudaFree(e->d_counted);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -666,6 +684,36 @@ int pgsgd_engine_run_range(pgsgd_engine* e, const pgsgd_config* cfg, int dims, u
     return run_engine(e, cfg, dims, iter_begin, iter_end, stats);
 }
 
+int pgsgd_engine_set_trace(pgsgd_engine* e, uint64_t capacity) {
+    if (!e) return fail(PGSGD_ERR_ARG, "set_trace: NULL engine");
+    CU(cudaSetDevice(e->device));
+    if (e->d_trace) { cudaFree(e->d_trace); e->d_trace = nullptr; }
+    if (!e->d_trace_count) CU(cudaMalloc(&e->d_trace_count, sizeof(unsigned long long)));
+    CU(cudaMemset(e->d_trace_count, 0, sizeof(unsigned long long)));
+    e->trace_cap = capacity;
+    if (capacity) CU(cudaMalloc(&e->d_trace, capacity * 2 * sizeof(unsigned long long)));
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_get_trace(pgsgd_engine* e, uint64_t* ia_out, uint64_t* ib_out, uint8_t* flips_out, uint64_t* n_out) {
+    if (!e || !n_out) return fail(PGSGD_ERR_ARG, "get_trace: NULL argument");
+    if (!e->d_trace) return fail(PGSGD_ERR_STATE, "no trace buffer (pgsgd_engine_set_trace)");
+    CU(cudaSetDevice(e->device));
+    unsigned long long n = 0;
+    CU(cudaMemcpy(&n, e->d_trace_count, sizeof(n), cudaMemcpyDeviceToHost));
+    if (n > e->trace_cap) n = e->trace_cap;
+    std::vector<unsigned long long> h(2 * n);
+    if (n) CU(cudaMemcpy(h.data(), e->d_trace, 2 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (uint64_t k = 0; k < n; ++k) {
+        if (ia_out) ia_out[k] = h[2 * k];
+        if (ib_out) ib_out[k] = h[2 * k + 1] & 0x3FFFFFFFFFFFFFFFull;
+        if (flips_out) flips_out[k] = (uint8_t) (h[2 * k + 1] >> 62);
+    }
+    *n_out = n;
+    CU(cudaMemset(e->d_trace_count, 0, sizeof(unsigned long long)));
+    return PGSGD_OK;
+}
+
 int pgsgd_comm_unique_id(uint8_t id_out[128]) {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
     ncclUniqueId id;
@@ -707,6 +755,7 @@ int pgsgd_engine_sample_terms(pgsgd_engine* e, const pgsgd_config* cfg, int dims
     sp.cooling = cooling ? 1u : 0u;
     sp.space = cfg->space; sp.space_max = cfg->space_max; sp.space_q = cfg->space_quantization_step;
     sp.zipf = make_zipf_const(theta_zipf);
+    sp.zipf_f = make_zipf_const_f(sp.zipf);
     const uint64_t n = n_terms ? n_terms : 1;
     uint8_t* d_buf = nullptr;
     const uint64_t per = 8 * 5 + 4 * 3 + 3;  // bytes per term over all outputs

@@ -123,6 +123,15 @@ __device__ __forceinline__ uint64_t draw_zipf(Xoshiro& g, uint64_t n, const Zipf
     return __double2ull_rz(__dadd_rn(1.0, __dmul_rn((double) n, fast_precise_pow(base, zc.alpha))));
 }
 
+// fp32 constants of the same Zipf configuration for the economical sampler of the tile kernel
+struct ZipfConstF {
+    float one_minus_theta;
+    float alpha_frac;      // alpha - floor(alpha)
+    int   alpha_int;       // floor(alpha)
+    float zeta2;
+    float thresh2;
+};
+
 // ---- everything the sampler needs, passed by value to the kernels ---------------------------------
 struct SamplerParams {
     const uint64_t* path_first;   // [P+1] global copy (used when the table does not fit in shared memory)
@@ -132,6 +141,7 @@ struct SamplerParams {
     uint32_t cooling;             // 1: always take the Zipf branch (path_sgd_layout.cpp:205)
     uint64_t space, space_max, space_q;
     ZipfConst zipf;
+    ZipfConstF zipf_f;
 };
 
 struct Term {
@@ -174,6 +184,65 @@ __device__ __forceinline__ void draw_partner(const SamplerParams& sp, Xoshiro& g
     if (DIMS == 2) {
         t.flip_a = draw_flip(g);
         t.flip_b = draw_flip(g);
+    }
+}
+
+// ---- economical partner draw (tile kernel) ---------------------------------------------------------------------
+// Same law as draw_partner, restated for throughput: ONE Xoshiro256+ output feeds a whole term (4 coin bits, a
+// 24-bit uniform for the Zipf draw or a 32-bit uniform partner), and the dirty Zipf — including the reference's
+// exponent-bit-hack pow — is evaluated in fp32.  The fp32 evaluation can move a partner by one step in rare boundary
+// cases; the distribution is checked against the oracle's in tests/test_gpu_parity.py (chi-square on the jump lengths).
+
+// dirtyzipf::fast_precise_pow with the exponent split as (e + frac) by the caller, on floats: the hack only reads the
+// top 20 mantissa bits of the double's high word, which a float carries exactly
+__device__ __forceinline__ float fast_precise_pow_f32(float a, int e, float frac) {
+    const int hi = (__float_as_int(a) >> 3) + 0x38000000;                  // high word of (double) a
+    const int t = 1072632447 + __float2int_rd(frac * (float) (hi - 1072632447));
+    const float f = __int_as_float((t - 0x38000000) << 3);
+    float r = 1.0f;
+    while (e) {
+        if (e & 1) r *= a;
+        a *= a;
+        e >>= 1;
+    }
+    return r * f;
+}
+
+__device__ __forceinline__ uint64_t draw_zipf_f32(uint32_t u24, uint64_t n, const ZipfConstF& zc, float zeta_n) {
+    const float nf = (float) n;
+    const float eta = __fdividef(1.0f - fast_precise_pow_f32(__fdividef(2.0f, nf), 0, zc.one_minus_theta),
+                                 1.0f - __fdividef(zc.zeta2, zeta_n));
+    const float u = (float) u24 * 5.9604644775390625e-8f;  // 2^-24
+    const float uz = u * zeta_n;
+    if (uz < 1.0f) return 1;
+    if (uz < zc.thresh2) return 2;
+    const float base = fmaf(eta, u, 1.0f - eta);
+    uint64_t z = 1 + (uint64_t) (nf * fast_precise_pow_f32(base, zc.alpha_int, zc.alpha_frac));
+    return z > n ? n : z;
+}
+
+template <int DIMS>
+__device__ __forceinline__ void draw_partner_fast(const SamplerParams& sp, Xoshiro& g, uint64_t f, uint64_t count, uint64_t s_rank, Term& t) {
+    const uint64_t x = xoshiro_next(g);
+    const uint32_t top = (uint32_t) (x >> 32);
+    uint64_t rank_b;
+    if (sp.cooling || (top >> 31)) {
+        const bool backward = (s_rank > 0 && ((top >> 30) & 1u)) || s_rank == count - 1;
+        const uint64_t room = backward ? s_rank : count - s_rank - 1;
+        const uint64_t jump_space = sp.space < room ? sp.space : room;
+        uint64_t zi = jump_space;
+        if (jump_space > sp.space_max) zi = sp.space_max + (jump_space - sp.space_max) / sp.space_q + 1;
+        const uint64_t z = draw_zipf_f32((top >> 4) & 0xFFFFFFu, jump_space, sp.zipf_f, (float) __ldg(sp.zetas + zi));
+        rank_b = backward ? s_rank - z : s_rank + z;
+    } else if (count <= 0xFFFFFFFFull) {
+        rank_b = __umulhi((uint32_t) (x >> 4), (uint32_t) count);  // bits [35:4]
+    } else {
+        rank_b = draw_uniform(g, count);
+    }
+    t.ib = f + rank_b;
+    if (DIMS == 2) {
+        t.flip_a = (top >> 29) & 1u;
+        t.flip_b = (top >> 28) & 1u;
     }
 }
 

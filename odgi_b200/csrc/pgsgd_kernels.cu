@@ -276,6 +276,11 @@ __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(con
         const uint64_t t_idx = (i * p.perm_mul[pass & 15] + p.perm_add[pass & 15]) % p.n_tiles;
         const uint64_t base = t_idx * (uint64_t) TILE_STEPS;
         const uint32_t terms = v + 1 == p.n_visits ? (uint32_t) p.last_visit_terms : (uint32_t) TILE_STEPS;
+        // path of the tile's first and last step (one search each per visit instead of one per term)
+        const uint64_t last_step = (base + TILE_STEPS <= p.sp.step_count ? base + TILE_STEPS : p.sp.step_count) - 1;
+        const uint32_t p_lo = find_path(first, p.sp.path_count, base);
+        const bool tile_one_path = first[p_lo + 1] > last_step;
+        const uint64_t tile_f = first[p_lo], tile_count = first[p_lo + 1] - tile_f;
         __syncthreads();  // the previous visit's readers are done with the tile
 #pragma unroll
         for (int r = 0; r < ROUNDS; ++r) {
@@ -290,8 +295,30 @@ __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(con
 #pragma unroll
             for (int b = 0; b < BATCH; ++b) {
                 const uint32_t j = (r0 + b) * 256 + threadIdx.x;
+                const uint64_t ia = base + j;
                 t[b].valid = 0;
-                if (j < terms && base + j < p.sp.step_count) draw_term_at<DIMS>(p.sp, first, g, base + j, t[b]);
+                if (j < terms && ia < p.sp.step_count) {
+                    // the tile almost always lies inside one path: its (start, count) were resolved once per visit
+                    uint64_t f = tile_f, count = tile_count;
+                    if (!tile_one_path) {
+                        const uint32_t pp = find_path(first, p.sp.path_count, ia);
+                        f = first[pp];
+                        count = first[pp + 1] - f;
+                    }
+                    t[b].ia = ia;
+                    if (count > 1) {  // steps of 1-step paths are skipped, not counted (path_sgd_layout.cpp:190-192)
+                        t[b].valid = 1;
+                        t[b].flip_a = t[b].flip_b = 0;
+                        draw_partner_fast<DIMS>(p.sp, g, f, count, ia - f, t[b]);
+                        if (p.trace) {
+                            const unsigned long long k = atomicAdd(p.trace_count, 1ull);
+                            if (k < p.trace_cap) {
+                                p.trace[2 * k] = ia;
+                                p.trace[2 * k + 1] = t[b].ib | ((unsigned long long) t[b].flip_a << 62) | ((unsigned long long) t[b].flip_b << 63);
+                            }
+                        }
+                    }
+                }
             }
 #pragma unroll
             for (int b = 0; b < BATCH; ++b) {

@@ -31,6 +31,10 @@ struct IterParams {
     uint64_t perm_mul[16];      // per pass: tile = (i * perm_mul[pass] + perm_add[pass]) % n_tiles, a bijection on [0, n_tiles)
     uint64_t perm_add[16];
     uint32_t visit_rank, visit_nranks;  // this rank handles visits v with v % visit_nranks == visit_rank
+    // ---- verification: when trace != nullptr every drawn term is appended as {ia, ib | flip_a << 62 | flip_b << 63} ----
+    unsigned long long* trace;
+    unsigned long long* trace_count;
+    uint64_t trace_cap;
 };
 
 constexpr int TILE_STEPS = 2048;   // steps staged in shared memory per tile visit (32 KB of 16-byte records)

@@ -244,3 +244,60 @@ def test_tile_sampling_partial_pass_counts(graphs):
     X0, Y0 = orc.layout_init(go, seed=1)
     _, _, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
     assert abs(int(st["term_updates"]) - 2 * U) <= 2 * 2048
+
+
+def _jump_hist(rank_a, rank_b, edges):
+    d = rank_b.astype(np.int64) - rank_a.astype(np.int64)
+    return np.histogram(np.abs(d), bins=edges)[0].astype(np.float64), float(np.mean(d < 0))
+
+
+@pytest.mark.parametrize("name,dims,cooling", [("chr6.C4", 2, False), ("chr6.C4", 2, True), ("LPA", 1, True), ("DRB1-3123", 2, True)])
+def test_tile_sampler_law_matches_reference_law(graphs, name, dims, cooling):
+    """The tile kernel's economical partner draw (one RNG word per term, fp32 dirty Zipf) against the oracle's exact
+    reference sampler: every step is a first step exactly once per pass, and the jump-length histogram, direction,
+    Zipf-vs-uniform and end-flip frequencies agree (two-sample chi-square on log-spaced jump bins)."""
+    gd, go = graphs[name]
+    iter_max = 4
+    kw = dict(iter_max=iter_max, min_term_updates=gd.S, sampling=capi.SAMPLING_TILE, cooling_start=0.5)
+    cd = capi.layout_defaults(gd, **kw) if dims == 2 else capi.sort_defaults(gd, **kw)
+    it = 3 if cooling else 0   # 2D cools from iteration 2, 1D from iteration 3
+    with odgi_b200.Engine(gd) as e:
+        if dims == 2:
+            e.set_coords_2d(*orc.layout_init(go, 1))
+        else:
+            e.set_coords_1d(None)
+        if it:
+            e.run_range(cd, dims, 0, it)
+        e.set_trace(gd.S + 16)
+        e.run_range(cd, dims, it, it + 1)
+        ia, ib, fl = e.get_trace(gd.S + 16)
+    first = gd.path_first_step.astype(np.int64)
+    counts = np.diff(first)
+    multi = np.repeat(counts > 1, counts)
+    # every step of a multi-step path is a first step exactly once
+    assert ia.size == int(multi.sum())
+    assert np.array_equal(np.sort(ia), np.nonzero(multi)[0].astype(np.uint64))
+    pa = np.searchsorted(first, ia.astype(np.int64), side="right") - 1
+    pb = np.searchsorted(first, ib.astype(np.int64), side="right") - 1
+    assert np.array_equal(pa, pb)  # partners never leave the path
+    ra, rb = ia.astype(np.int64) - first[pa], ib.astype(np.int64) - first[pb]
+    # reference law from the oracle (same graph, same config), ~the same number of terms
+    co = (orc.default_layout_config(go, iter_max=iter_max, min_term_updates=gd.S) if dims == 2
+          else orc.default_sort_config(go, iter_max=iter_max, min_term_updates=gd.S))
+    theta_z = 0.001 if (dims == 1 and cooling) else None
+    n_ref = min(int(ia.size), 200_000)
+    ref, valid = orc.sample_terms(go, co, dims, cooling, n_ref, stream=5, theta_zipf=theta_z)
+    ok = valid.astype(bool)
+    edges = np.unique(np.concatenate([[0, 1, 2, 3, 4, 6, 8, 12, 16], np.round(np.geomspace(24, max(int(counts.max()), 32), 24)).astype(np.int64)]))
+    edges = np.append(edges, edges[-1] + 1)
+    h_dev, back_dev = _jump_hist(ra, rb, edges)
+    h_ref, back_ref = _jump_hist(ref["rank_a"][ok], ref["rank_b"][ok], edges)
+    keep = (h_dev + h_ref) >= 20
+    a, b = h_dev[keep], h_ref[keep]
+    k1, k2 = np.sqrt(b.sum() / a.sum()), np.sqrt(a.sum() / b.sum())
+    chi2 = float((((k1 * a - k2 * b) ** 2) / (a + b)).sum())
+    dof = int(keep.sum()) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof), (chi2, dof, h_dev, h_ref)
+    assert abs(back_dev - back_ref) < 0.01
+    if dims == 2:
+        assert abs(np.mean(fl & 1) - 0.5) < 0.01 and abs(np.mean(fl >> 1) - 0.5) < 0.01
