@@ -153,8 +153,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    g, desc = make_workload(args.workload) if args.workload not in ("c4", "mid") else (None, None)
-    # each step = one iteration over a bounded sample; (steps + warmup) iterations in one reference invocation
+    # each step = one iteration over a bounded sample of the workload (same generator, same haplotype count)
     t0 = time.time()
     cb = cpu_baseline(args.workload, threads)
     line = {"impl": "reference", "metric": "M node-pair SGD updates/sec", "value": cb["value"], "unit": "M updates/s", "n_gpus": args.gpus,

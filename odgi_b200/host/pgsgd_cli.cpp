@@ -1,0 +1,303 @@
+// pgsgd_cli.cpp — `pgsgd layout|sort ... --gpu`: the `odgi layout` / `odgi sort -Y` command-line surface for the PG-SGD
+// path (same short/long flags and defaults: src/subcommand/layout_main.cpp:28-107,198-266; sort_main.cpp:313-414),
+// standalone: GFA in -> flattened graph -> C-ABI (include/pgsgd.h) -> TSV layout / node order out.
+// Everything that is not the PG-SGD path (the .og container, other sort pipelines, drawing) stays in odgi.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <random>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "gfa_lite.hpp"
+#include "pgsgd_arrays.hpp"
+
+namespace {
+
+struct Args {
+    std::map<std::string, std::string> kv;
+    bool has(const std::string& k) const { return kv.count(k) != 0; }
+    std::string str(const std::string& k, const std::string& d = "") const { auto it = kv.find(k); return it == kv.end() ? d : it->second; }
+    double num(const std::string& k, double d) const { auto it = kv.find(k); return it == kv.end() ? d : std::stod(it->second); }
+    uint64_t u64(const std::string& k, uint64_t d) const { auto it = kv.find(k); return it == kv.end() ? d : std::stoull(it->second); }
+};
+
+// flag table: short, long, takes value
+struct Flag { const char* s; const char* l; bool val; };
+const Flag LAYOUT_FLAGS[] = {
+    {"i", "idx", true}, {"o", "out", true}, {"T", "tsv", true}, {"N", "layout-initialization", true},
+    {"G", "path-sgd-min-term-updates-paths", true}, {"U", "path-sgd-min-term-updates-nodes", true}, {"j", "path-sgd-delta", true},
+    {"g", "path-sgd-eps", true}, {"v", "path-sgd-eta-max", true}, {"a", "path-sgd-zipf-theta", true}, {"x", "path-sgd-iter-max", true},
+    {"K", "path-sgd-cooling", true}, {"F", "path-sgd-iteration-max-learning-rate", true}, {"k", "path-sgd-zipf-space", true},
+    {"I", "path-sgd-zipf-space-max", true}, {"l", "path-sgd-zipf-space-quantization-step", true}, {"t", "threads", true},
+    {"", "gpu", false}, {"P", "progress", false}, {"h", "help", false}, {"", "seed", true}, {"", "init-seed", true}, {"", "sampling", true}};
+const Flag SORT_FLAGS[] = {
+    {"i", "idx", true}, {"o", "out", true}, {"Y", "path-sgd", false}, {"G", "path-sgd-min-term-updates-paths", true},
+    {"U", "path-sgd-min-term-updates-nodes", true}, {"j", "path-sgd-delta", true}, {"g", "path-sgd-eps", true},
+    {"v", "path-sgd-eta-max", true}, {"a", "path-sgd-zipf-theta", true}, {"x", "path-sgd-iter-max", true}, {"K", "path-sgd-cooling", true},
+    {"F", "path-sgd-iteration-max-learning-rate", true}, {"k", "path-sgd-zipf-space", true}, {"I", "path-sgd-zipf-space-max", true},
+    {"l", "path-sgd-zipf-space-quantization-step", true}, {"t", "threads", true}, {"", "gpu", false}, {"P", "progress", false},
+    {"h", "help", false}, {"", "seed", true}, {"", "sampling", true}, {"", "layout-out", true}};
+
+template <size_t NF>
+bool parse(int argc, char** argv, const Flag (&flags)[NF], Args& a, const char* sub) {
+    for (int i = 2; i < argc; ++i) {
+        std::string tok = argv[i], name, value;
+        bool have_value = false;
+        if (tok.rfind("--", 0) == 0) {
+            name = tok.substr(2);
+            auto eq = name.find('=');
+            if (eq != std::string::npos) { value = name.substr(eq + 1); name = name.substr(0, eq); have_value = true; }
+        } else if (tok.size() >= 2 && tok[0] == '-') {
+            name = tok.substr(1, 1);
+            if (tok.size() > 2) { value = tok.substr(tok[2] == '=' ? 3 : 2); have_value = true; }
+        } else {
+            std::cerr << "[odgi::" << sub << "] error: unexpected argument " << tok << std::endl;
+            return false;
+        }
+        const Flag* f = nullptr;
+        for (const Flag& c : flags) if (name == c.l || (c.s[0] && name == c.s)) { f = &c; break; }
+        if (!f) { std::cerr << "[odgi::" << sub << "] error: unknown flag " << tok << std::endl; return false; }
+        if (f->val && !have_value) {
+            if (i + 1 >= argc) { std::cerr << "[odgi::" << sub << "] error: flag " << tok << " needs a value" << std::endl; return false; }
+            value = argv[++i];
+        }
+        a.kv[f->l] = f->val ? value : "1";
+    }
+    return true;
+}
+
+// weakly connected components over path adjacencies and L lines (union-find); component ids in order of first node
+struct Components {
+    std::vector<uint32_t> parent;
+    explicit Components(size_t n) : parent(n) { std::iota(parent.begin(), parent.end(), 0u); }
+    uint32_t find(uint32_t x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; }
+    void unite(uint32_t a, uint32_t b) { a = find(a); b = find(b); if (a != b) parent[std::max(a, b)] = std::min(a, b); }
+};
+
+std::vector<uint32_t> components_of(const pgsgd::FlatGraph& fg, const std::string& gfa) {
+    Components uf(fg.node_len.size());
+    for (size_t p = 0; p + 1 < fg.path_first_step.size(); ++p)
+        for (uint64_t s = fg.path_first_step[p]; s + 1 < fg.path_first_step[p + 1]; ++s) uf.unite(fg.step_node[s], fg.step_node[s + 1]);
+    std::ifstream in(gfa);
+    std::string line;
+    while (std::getline(in, line)) {
+        if (line.size() < 2 || line[0] != 'L') continue;
+        std::istringstream ss(line);
+        std::string tag, a, ao, b;
+        ss >> tag >> a >> ao >> b;
+        const uint64_t ia = std::strtoull(a.c_str(), nullptr, 10), ib = std::strtoull(b.c_str(), nullptr, 10);
+        if (ia >= 1 && ib >= 1 && ia <= fg.node_len.size() && ib <= fg.node_len.size()) uf.unite((uint32_t) ia - 1, (uint32_t) ib - 1);
+    }
+    std::vector<uint32_t> comp(fg.node_len.size());
+    std::map<uint32_t, uint32_t> ids;
+    for (uint32_t i = 0; i < comp.size(); ++i) {
+        const uint32_t r = uf.find(i);
+        auto it = ids.find(r);
+        if (it == ids.end()) it = ids.emplace(r, (uint32_t) ids.size()).first;
+        comp[i] = it->second;
+    }
+    return comp;
+}
+
+void common_config(const Args& a, const pgsgd::FlatGraph& fg, bool is_sort, pgsgd_config& c) {
+    std::memset(&c, 0, sizeof(c));
+    const uint64_t S = fg.steps(), N = fg.node_len.size();
+    c.iter_max = a.u64("path-sgd-iter-max", is_sort ? 100 : 30);
+    c.iter_with_max_learning_rate = a.u64("path-sgd-iteration-max-learning-rate", 0);
+    c.theta = a.num("path-sgd-zipf-theta", 0.99);
+    c.eps = a.num("path-sgd-eps", 0.01);
+    c.delta = a.num("path-sgd-delta", 0);
+    c.cooling_start = a.num("path-sgd-cooling", 0.5);
+    if (a.has("path-sgd-min-term-updates-paths")) c.min_term_updates = (uint64_t) (a.num("path-sgd-min-term-updates-paths", 0) * (double) S);
+    else if (a.has("path-sgd-min-term-updates-nodes")) c.min_term_updates = (uint64_t) (a.num("path-sgd-min-term-updates-nodes", 0) * (double) N);
+    else c.min_term_updates = (uint64_t) ((is_sort ? 1.0 : 10.0) * (double) S);
+    c.eta_max = a.has("path-sgd-eta-max") ? a.num("path-sgd-eta-max", 0) : (double) fg.max_path_steps * (double) fg.max_path_steps;
+    if (is_sort) {  // sort_main.cpp:387-412
+        const uint64_t max_len = fg.max_path_bp;
+        c.space = a.has("path-sgd-zipf-space") ? std::min(a.u64("path-sgd-zipf-space", 0), max_len) : max_len;
+        c.space_max = a.has("path-sgd-zipf-space-max") ? std::min(c.space, a.u64("path-sgd-zipf-space-max", 0)) : 100;
+        if (a.has("path-sgd-zipf-space-quantization-step")) {
+            c.space_quantization_step = std::max<uint64_t>(2, a.u64("path-sgd-zipf-space-quantization-step", 0));
+        } else {
+            const uint64_t max_dists = std::max<uint64_t>(c.space_max + 1, 100);
+            c.space_quantization_step = std::max<uint64_t>(2, (uint64_t) std::ceil((double) (c.space - c.space_max) / (double) (max_dists - c.space_max)));
+        }
+    } else {  // layout_main.cpp:261-266
+        c.space = a.has("path-sgd-zipf-space") ? std::min(a.u64("path-sgd-zipf-space", 0), fg.max_path_steps) : fg.max_path_steps;
+        c.space_max = a.has("path-sgd-zipf-space-max") ? std::min(c.space, a.u64("path-sgd-zipf-space-max", 0)) : 1000;
+        c.space_quantization_step = a.has("path-sgd-zipf-space-quantization-step") ? std::max<uint64_t>(2, a.u64("path-sgd-zipf-space-quantization-step", 0)) : 100;
+    }
+    c.seed = a.u64("seed", 9399220);
+    c.sampling = (uint32_t) a.u64("sampling", 0);
+}
+
+int need_gpu(const Args& a, const char* sub) {
+    if (!a.has("gpu")) {
+        std::cerr << "[odgi::" << sub << "] error: this build provides only the GPU path of the path-guided SGD; pass --gpu "
+                     "(the CPU path is odgi's own: src/algorithms/path_sgd" << (std::string(sub) == "layout" ? "_layout" : "") << ".cpp)." << std::endl;
+        return 1;
+    }
+    if (pgsgd_device_count() < 1) {
+        std::cerr << "[odgi::" << sub << "] error: --gpu given but no usable CUDA device was found." << std::endl;
+        return 1;
+    }
+    return 0;
+}
+
+int main_layout(int argc, char** argv) {
+    Args a;
+    if (!parse(argc, argv, LAYOUT_FLAGS, a, "layout") || a.has("help") || argc == 2) {
+        std::cout << "pgsgd layout -i g.gfa (-T out.tsv) --gpu [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-N d|r|u|g|h] [-t N] [-P]\n"
+                     "  the `odgi layout` PG-SGD flags with the same defaults; --seed N (worker streams), --init-seed N (layout initialisation)\n";
+        return a.has("help") ? 0 : 1;
+    }
+    if (!a.has("idx")) { std::cerr << "[odgi::layout] error: Please specify an input file from where to load the graph via -i=[FILE], --idx=[FILE]." << std::endl; return 1; }
+    if (!a.has("tsv")) { std::cerr << "[odgi::layout] error: Please specify an output file to where to store the layout via -T/--tsv=[FILE] (the binary .lay container is written by odgi itself)." << std::endl; return 1; }
+    if (int rc = need_gpu(a, "layout")) return rc;
+    pgsgd::FlatGraph fg;
+    try { fg = pgsgd::read_gfa_flat(a.str("idx")); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
+    pgsgd_config c;
+    common_config(a, fg, false, c);
+    const uint64_t N = fg.node_len.size();
+    std::vector<double> X(2 * N), Y(2 * N);
+    // layout_main.cpp:268-330 — the reference seeds from std::random_device; --init-seed makes runs reproducible
+    std::mt19937 rng(a.has("init-seed") ? (uint32_t) a.u64("init-seed", 0) : std::random_device{}());
+    std::uniform_real_distribution<double> uniform_noise(0, std::sqrt((double) N * 2));
+    std::normal_distribution<double> gaussian_noise(0, std::sqrt((double) N * 2));
+    uint64_t total_length = 0;
+    for (uint32_t l : fg.node_len) total_length += l;
+    std::uniform_real_distribution<double> uniform_noise_in_length(0, (double) total_length);
+    const char init = a.str("layout-initialization", "d")[0];
+    uint64_t len = 0;
+    for (uint64_t r = 0; r < N; ++r) {
+        const uint64_t pos = 2 * r;
+        switch (init) {
+            case 'g': X[pos] = gaussian_noise(rng); Y[pos] = gaussian_noise(rng); X[pos + 1] = gaussian_noise(rng); Y[pos + 1] = gaussian_noise(rng); break;
+            case 'u': X[pos] = (double) len; Y[pos] = uniform_noise(rng); len += fg.node_len[r]; X[pos + 1] = (double) len; Y[pos + 1] = uniform_noise(rng); break;
+            case 'r': X[pos] = uniform_noise_in_length(rng); Y[pos] = uniform_noise_in_length(rng); X[pos + 1] = uniform_noise_in_length(rng); Y[pos + 1] = uniform_noise_in_length(rng); break;
+            case 'h': std::cerr << "[odgi::layout] error: the Hilbert initialisation is not available in this build." << std::endl; return 1;
+            default: X[pos] = (double) len; Y[pos] = gaussian_noise(rng); len += fg.node_len[r]; X[pos + 1] = (double) len; Y[pos + 1] = gaussian_noise(rng);
+        }
+    }
+    pgsgd_stats st;
+    const pgsgd_graph_view v = fg.view();
+    if (pgsgd_layout_2d(&v, &c, X.data(), Y.data(), &st) != PGSGD_OK) { std::cerr << "[odgi::layout] error: " << pgsgd_last_error() << std::endl; return 1; }
+    if (a.has("progress"))
+        std::cerr << "[odgi::path_linear_sgd_layout] 2D path-guided SGD: " << st.term_updates << " term updates in " << st.seconds_iterations
+                  << " s on the GPU (" << st.term_updates / st.seconds_iterations / 1e6 << " M updates/s), upload " << st.seconds_upload << " s" << std::endl;
+    // stack the weakly connected components vertically with a 1000-unit border (layout_main.cpp:402-435)
+    const std::vector<uint32_t> comp = components_of(fg, a.str("idx"));
+    const uint32_t n_comp = comp.empty() ? 0 : *std::max_element(comp.begin(), comp.end()) + 1;
+    const double border = 1000.0, inf = std::numeric_limits<double>::max();
+    std::vector<double> min_x(n_comp, inf), min_y(n_comp, inf), max_y(n_comp, std::numeric_limits<double>::lowest());
+    for (uint64_t r = 0; r < N; ++r)
+        for (uint64_t j = 2 * r; j <= 2 * r + 1; ++j) {
+            min_x[comp[r]] = std::min(min_x[comp[r]], X[j]); min_y[comp[r]] = std::min(min_y[comp[r]], Y[j]); max_y[comp[r]] = std::max(max_y[comp[r]], Y[j]);
+        }
+    std::vector<double> x_off(n_comp), y_off(n_comp);
+    double curr_y_offset = border;
+    for (uint32_t k = 0; k < n_comp; ++k) {
+        x_off[k] = min_x[k] - border;
+        y_off[k] = curr_y_offset - min_y[k];
+        curr_y_offset += (max_y[k] - min_y[k]) + border;
+    }
+    for (uint64_t r = 0; r < N; ++r)
+        for (uint64_t j = 2 * r; j <= 2 * r + 1; ++j) { X[j] -= x_off[comp[r]]; Y[j] += y_off[comp[r]]; }
+    // layout::to_tsv (src/algorithms/layout.cpp:10-34): idx X Y component, two rows per node, grouped by component
+    std::ofstream fout;
+    std::ostream* out = &std::cout;
+    if (a.str("tsv") != "-") { fout.open(a.str("tsv")); out = &fout; }
+    *out << std::setprecision(std::numeric_limits<double>::digits10 + 1);
+    *out << "idx\tX\tY\tcomponent" << std::endl;
+    for (uint32_t k = 0; k < n_comp; ++k)
+        for (uint64_t r = 0; r < N; ++r) {
+            if (comp[r] != k) continue;
+            *out << 2 * r << "\t" << X[2 * r] << "\t" << Y[2 * r] << "\t" << k << '\n';
+            *out << 2 * r + 1 << "\t" << X[2 * r + 1] << "\t" << Y[2 * r + 1] << "\t" << k << '\n';
+        }
+    return 0;
+}
+
+int main_sort(int argc, char** argv) {
+    Args a;
+    if (!parse(argc, argv, SORT_FLAGS, a, "sort") || a.has("help") || argc == 2) {
+        std::cout << "pgsgd sort -i g.gfa -o order.txt -Y --gpu [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-t N] [-P]\n"
+                     "  the `odgi sort -Y` PG-SGD flags with the same defaults; writes the node order (one node id per line) that\n"
+                     "  path_linear_sgd_order derives (sorted by position, then handle); odgi applies it with apply_ordering.\n";
+        return a.has("help") ? 0 : 1;
+    }
+    if (!a.has("idx")) { std::cerr << "[odgi::sort] error: please specify an input file from where to load the graph via -i=[FILE], --idx=[FILE]." << std::endl; return 1; }
+    if (!a.has("out")) { std::cerr << "[odgi::sort] error: please specify an output file to where to store the node order via -o=[FILE], --out=[FILE]." << std::endl; return 1; }
+    if (!a.has("path-sgd")) { std::cerr << "[odgi::sort] error: only the path-guided SGD sort (-Y, --path-sgd) is provided by this build." << std::endl; return 1; }
+    if (int rc = need_gpu(a, "sort")) return rc;
+    pgsgd::FlatGraph fg;
+    try { fg = pgsgd::read_gfa_flat(a.str("idx")); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
+    pgsgd_config c;
+    common_config(a, fg, true, c);
+    const uint64_t N = fg.node_len.size();
+    std::vector<double> X(N);
+    pgsgd_stats st;
+    const pgsgd_graph_view v = fg.view();
+    if (pgsgd_sort_1d(&v, &c, nullptr, 0, X.data(), &st) != PGSGD_OK) { std::cerr << "[odgi::sort] error: " << pgsgd_last_error() << std::endl; return 1; }
+    if (a.has("progress"))
+        std::cerr << "[odgi::path_linear_sgd] 1D path-guided SGD: " << st.term_updates << " term updates in " << st.seconds_iterations << " s on the GPU" << std::endl;
+    // path_linear_sgd_order (path_sgd.cpp:638-683): sort by (weak component, pos, handle).  The reference clears its
+    // component map before reading it (path_sgd.cpp:588), so the component key is constant there; mirrored here.
+    std::vector<uint64_t> order(N);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](uint64_t i, uint64_t j) { return X[i] < X[j] || (X[i] == X[j] && i < j); });
+    std::ofstream f(a.str("out"));
+    for (uint64_t r : order) f << r + 1 << '\n';
+    if (a.has("layout-out")) {  // -L in odgi sort: the 1D layout (start, start + node length) per sorted node
+        std::ofstream l(a.str("layout-out"));
+        l << std::setprecision(std::numeric_limits<double>::digits10 + 1) << "node\tstart\tend\n";
+        for (uint64_t r : order) l << r + 1 << "\t" << X[r] << "\t" << X[r] + (double) fg.node_len[r] << '\n';
+    }
+    return 0;
+}
+
+// pgsgd flatten -i g.gfa -o g.arr : the flattened graph as a PGSGDARR container (what bench.py / the tests load)
+int main_flatten(int argc, char** argv) {
+    std::string in, out;
+    for (int i = 2; i + 1 < argc; i += 2) {
+        if (!std::strcmp(argv[i], "-i")) in = argv[i + 1];
+        else if (!std::strcmp(argv[i], "-o")) out = argv[i + 1];
+    }
+    if (in.empty() || out.empty()) { std::cerr << "usage: pgsgd flatten -i g.gfa -o g.arr" << std::endl; return 1; }
+    pgsgd::FlatGraph fg;
+    try { fg = pgsgd::read_gfa_flat(in); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
+    std::vector<uint8_t> names;
+    for (auto& n : fg.path_names) { names.insert(names.end(), n.begin(), n.end()); names.push_back((uint8_t) '\n'); }
+    pgsgd::ArrayWriter w(out);
+    w.add("node_len", fg.node_len);
+    w.add("path_first_step", fg.path_first_step);
+    w.add("step_node", fg.step_node);
+    w.add("step_rev", fg.step_rev);
+    w.add("step_pos", fg.step_pos);
+    w.add("path_names", names);
+    w.close();
+    std::cout << "{\"nodes\": " << fg.node_len.size() << ", \"paths\": " << fg.path_names.size() << ", \"steps\": " << fg.steps() << "}" << std::endl;
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    if (argc < 2) { std::cerr << "usage: pgsgd layout|sort [flags] --gpu   (the PG-SGD subset of `odgi layout` / `odgi sort -Y`)" << std::endl; return 1; }
+    const std::string sub = argv[1];
+    if (sub == "layout") return main_layout(argc, argv);
+    if (sub == "sort") return main_sort(argc, argv);
+    if (sub == "flatten") return main_flatten(argc, argv);
+    std::cerr << "unknown subcommand " << sub << " (layout, sort)" << std::endl;
+    return 1;
+}
