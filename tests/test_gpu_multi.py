@@ -1,0 +1,84 @@
+"""N > 1: the NCCL path (replicated coordinates, term updates split over ranks, one all-reduce per iteration),
+two processes / two GPUs.  Skipped when fewer than 2 devices are visible."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import odgi_b200
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.environ["PGSGD_ROOT"])
+import torch, torch.distributed as dist
+import odgi_b200
+from odgi_b200 import capi
+from odgi_b200.arrays import read_arrays
+from oracle import oracle as orc
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo")
+a = read_arrays(os.path.join(os.environ["PGSGD_ROOT"], "tests/golden/DRB1-3123.graph.arr.gz"))
+gd, go = odgi_b200.graph_from_arrays(a), orc.Graph.from_arrays(a)
+def fresh_id():
+    # every communicator needs its own ncclUniqueId
+    obj = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    return obj[0]
+X0, Y0 = orc.layout_init(go, 42)
+out = {}
+for tag, flags in (("avg", 0), ("sum", capi.PGSGD_FLAG_SUM_DELTAS)):
+    # one worker stream per rank, strict order: the run must equal the oracle's emulation of the 2-rank schedule bit for bit
+    kw = dict(iter_max=4, min_term_updates=6000, eta_max=2000.0)
+    cd = capi.layout_defaults(gd, n_streams=1, batch=1, sampling=capi.SAMPLING_STREAM, flags=flags, **kw)
+    co = orc.default_layout_config(go, **kw)
+    with odgi_b200.Engine(gd, device=rank) as e:
+        e.attach_comm(fresh_id(), world, rank)
+        e.set_coords_2d_f32(orc.XY_to_xy(X0, Y0))
+        st = e.run_2d(cd)
+        xy = e.get_coords_2d_f32()
+    ref = orc.emulate_multirank_2d_f32(go, co, orc.XY_to_xy(X0, Y0), world, 1, sum_deltas=bool(flags))
+    out[tag] = {"equal": bool(np.array_equal(xy, ref)), "updates": int(st["term_updates"]), "maxdiff": float(np.max(np.abs(xy - ref)))}
+    # all ranks hold the same coordinates
+    t = torch.from_numpy(xy.copy())
+    lst = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(lst, t)
+    out[tag]["replicas_identical"] = bool(all(torch.equal(lst[0], x) for x in lst))
+# a default-shaped run on 2 GPUs: stress stays close to the single-GPU band (averaging costs a few percent, DESIGN.md §6)
+cd = capi.layout_defaults(gd)
+with odgi_b200.Engine(gd, device=rank) as e:
+    e.attach_comm(fresh_id(), world, rank)
+    e.set_coords_2d(X0, Y0)
+    st = e.run_2d(cd)
+    X, Y = e.get_coords_2d()
+out["default_stress"] = orc.path_stress_2d(go, X, Y, 1000000, 12345)
+out["default_updates"] = int(st["term_updates"])
+if rank == 0:
+    print("RESULT " + json.dumps(out))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(odgi_b200.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_nccl_run_matches_emulation(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, PGSGD_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    import json
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    res = json.loads(line[7:])
+    for tag in ("avg", "sum"):
+        assert res[tag]["replicas_identical"], res
+        assert res[tag]["updates"] == 4 * 3000, res
+        assert res[tag]["equal"], res
+    assert res["default_updates"] == 30 * 10 * 35059 // 2
+    assert 0.06 < res["default_stress"] < 0.09, res
