@@ -157,6 +157,17 @@ int pgsgd_engine_run_range(pgsgd_engine* e, const pgsgd_config* cfg, int dims, u
 int pgsgd_comm_unique_id(uint8_t id_out[128]);
 int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int n_ranks, int rank);
 
+/* How the ranks of a communicator combine their work (select after attach_comm, before uploading coordinates):
+ *  ALLREDUCE: coordinates replicated on every GPU; each rank applies its share of an iteration's updates to its replica;
+ *             one ncclAllReduce (mean, or sum of displacements with PGSGD_FLAG_SUM_DELTAS) per iteration.
+ *  PEER     : coordinates PARTITIONED by node range over the GPUs of one NVLink domain (<= 8); every update reads and
+ *             red.adds the owner's slice directly through NVLink peer memory (CUDA IPC), so all GPUs run one shared
+ *             Hogwild exactly like the threads of the reference — no replica drift, no all-reduce of coordinates.  Tiles
+ *             are assigned to the rank owning their nodes, which keeps ~80 % of the traffic on the local GPU. */
+#define PGSGD_MULTI_ALLREDUCE 0
+#define PGSGD_MULTI_PEER      1
+int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode);
+
 /* ---- verification hooks (used by tests; they exercise exactly the device code the runs use) ---- */
 /* The first n_terms draws of worker stream `stream`, produced by the device sampler.  dims = 2 or 1;
  * cooling / theta_zipf as the iteration would set them.  Outputs are [n_terms] each (any may be NULL);

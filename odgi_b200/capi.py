@@ -19,6 +19,7 @@ PGSGD_FLAG_EXCH_WRITE = 1
 PGSGD_FLAG_SUM_DELTAS = 2
 PGSGD_FLAG_PLAIN_STORE = 4
 SAMPLING_AUTO, SAMPLING_STREAM, SAMPLING_TILE = 0, 1, 2
+MULTI_ALLREDUCE, MULTI_PEER = 0, 1
 
 
 class PgsgdError(RuntimeError):
@@ -57,7 +58,7 @@ EXPORTED_SYMBOLS = [
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
     "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
-    "pgsgd_engine_attach_comm", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
+    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
 ]
 
 _lib = None
@@ -91,6 +92,7 @@ def lib():
         L.pgsgd_engine_run_range.argtypes = [vp, C.POINTER(ConfigC), i32, u64, u64, C.POINTER(StatsC)]
         L.pgsgd_comm_unique_id.argtypes = [vp]
         L.pgsgd_engine_attach_comm.argtypes = [vp, vp, i32, i32]
+        L.pgsgd_engine_set_multi_mode.argtypes = [vp, i32]
         L.pgsgd_engine_sample_terms.argtypes = [vp, C.POINTER(ConfigC), i32, i32, dbl, u64, u64] + [vp] * 11
         L.pgsgd_engine_set_trace.argtypes = [vp, u64]
         L.pgsgd_engine_get_trace.argtypes = [vp, vp, vp, vp, vp]
@@ -325,6 +327,10 @@ class Engine:
         _check(lib().pgsgd_engine_get_trace(self._h, _ptr(ia), _ptr(ib), _ptr(fl), C.byref(n)))
         k = int(n.value)
         return ia[:k], ib[:k], fl[:k]
+
+    def set_multi_mode(self, mode: int):
+        """0 = all-reduce of replicated coordinates, 1 = NVLink peer memory (partitioned coordinates)"""
+        _check(lib().pgsgd_engine_set_multi_mode(self._h, mode))
 
     def sample_terms(self, cfg: Config, dims: int, cooling: bool, n_terms: int, stream: int = 0, theta_zipf=None):
         out = {"step_index": np.zeros(n_terms, np.uint64), "path": np.zeros(n_terms, np.uint32),

@@ -142,6 +142,19 @@ struct pgsgd_engine {
     uint64_t h2d_bytes = 0;
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
+    // ---- peer mode (PGSGD_MULTI_PEER): coordinates partitioned by node range, accessed through NVLink peer memory ----
+    int multi_mode = 0;
+    bool peer_ready_2d = false, peer_ready_1d = false;
+    uint64_t part_chunk = 0;                 // nodes per partition (last one may be shorter)
+    uint32_t part_lo[9] = {0};
+    float* d_xy_part = nullptr;              // this rank's slice, part_chunk * 4 floats
+    double* d_x1d_part = nullptr;
+    float* peer_xy[8] = {nullptr};           // pre-offset base pointers (see IterParams::part_xy)
+    double* peer_x1d[8] = {nullptr};
+    std::vector<void*> ipc_opened;
+    std::vector<uint32_t> tile_mid_node;     // node of the middle step of every tile (tile -> owner rank)
+    uint32_t* d_tile_list = nullptr;
+    uint64_t my_tiles = 0, my_tile_steps = 0;
 };
 
 namespace {
@@ -208,6 +221,118 @@ std::vector<double> build_schedule(const pgsgd_config& c) {
 }
 
 // the iteration loop shared by 2D and 1D
+int comm_barrier(pgsgd_engine* e) {
+    if (!e->comm) return PGSGD_OK;
+    NC(ncclAllReduce(e->d_delta, e->d_delta, 1, ncclUint32, ncclMax, e->comm, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return PGSGD_OK;
+}
+
+// Peer mode set-up: partition the node range, allocate this rank's slice, exchange CUDA IPC handles through the NCCL
+// communicator and map every peer's slice (NVLink peer memory).  Also assigns every tile to the rank that owns the node
+// of its middle step, so that in tile mode both first-node accesses and most partner accesses stay on the local GPU.
+int setup_peer(pgsgd_engine* e, int dims) {
+    if (!e->comm || e->n_ranks < 2) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator with at least 2 ranks");
+    if (e->n_ranks > 8) return fail(PGSGD_ERR_ARG, "peer mode supports up to 8 ranks (one NVSwitch domain)");
+    const int n = e->n_ranks;
+    e->part_chunk = (e->N + n - 1) / n;
+    for (int q = 0; q <= n; ++q) {
+        const uint64_t lo = (uint64_t) q * e->part_chunk;
+        e->part_lo[q] = (uint32_t) (lo < e->N ? lo : e->N);
+    }
+    for (int q = n + 1; q < 9; ++q) e->part_lo[q] = (uint32_t) e->N;
+    void* mine = nullptr;
+    const size_t bytes = e->part_chunk * (dims == 2 ? 4 * sizeof(float) : sizeof(double));
+    if (dims == 2) {
+        if (!e->d_xy_part) { int rc = dev_alloc(e, &e->d_xy_part, e->part_chunk * 4); if (rc) return rc; }
+        mine = e->d_xy_part;
+    } else {
+        if (!e->d_x1d_part) { int rc = dev_alloc(e, &e->d_x1d_part, e->part_chunk); if (rc) return rc; }
+        mine = e->d_x1d_part;
+    }
+    CU(cudaMemsetAsync(mine, 0, bytes, e->stream));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, mine));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    uint8_t* d_h = nullptr;
+    CU(cudaMalloc(&d_h, 64 * (size_t) (n + 1)));
+    CU(cudaMemcpyAsync(d_h, &h, 64, cudaMemcpyHostToDevice, e->stream));
+    NC(ncclAllGather(d_h, d_h + 64, 64, ncclUint8, e->comm, e->stream));
+    std::vector<cudaIpcMemHandle_t> all(n);
+    CU(cudaMemcpyAsync(all.data(), d_h + 64, 64 * (size_t) n, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(d_h);
+    for (int q = 0; q < n; ++q) {
+        void* ptr = mine;
+        if (q != e->rank) {
+            CU(cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess));
+            e->ipc_opened.push_back(ptr);
+        }
+        if (dims == 2) e->peer_xy[q] = reinterpret_cast<float*>(ptr) - 4 * (ptrdiff_t) e->part_lo[q];
+        else e->peer_x1d[q] = reinterpret_cast<double*>(ptr) - (ptrdiff_t) e->part_lo[q];
+    }
+    if (!e->d_tile_list) {
+        std::vector<uint32_t> mine_tiles;
+        uint64_t steps = 0;
+        const uint64_t W = TILE_STEPS;
+        for (uint64_t t = 0; t < e->tile_mid_node.size(); ++t) {
+            uint64_t owner = e->tile_mid_node[t] / e->part_chunk;
+            if (owner >= (uint64_t) n) owner = n - 1;
+            if ((int) owner == e->rank) {
+                mine_tiles.push_back((uint32_t) t);
+                const uint64_t lo = t * W, hi = lo + W < e->S ? lo + W : e->S;
+                steps += hi - lo;
+            }
+        }
+        e->my_tiles = mine_tiles.size();
+        e->my_tile_steps = steps;
+        int rc = dev_alloc(e, &e->d_tile_list, mine_tiles.size());
+        if (rc) return rc;
+        if (!mine_tiles.empty()) CU(cudaMemcpyAsync(e->d_tile_list, mine_tiles.data(), mine_tiles.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    if (dims == 2) e->peer_ready_2d = true; else e->peer_ready_1d = true;
+    return comm_barrier(e);
+}
+
+// full replica (d_xy / d_x1d) -> this rank's slice; called after every coordinate upload in peer mode
+int peer_scatter(pgsgd_engine* e, int dims) {
+    if (!(dims == 2 ? e->peer_ready_2d : e->peer_ready_1d)) { int rc = setup_peer(e, dims); if (rc) return rc; }
+    const uint64_t lo = e->part_lo[e->rank], hi = e->part_lo[e->rank + 1];
+    if (dims == 2) CU(cudaMemcpyAsync(e->d_xy_part, e->d_xy + 4 * lo, (hi - lo) * 4 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+    else CU(cudaMemcpyAsync(e->d_x1d_part, e->d_x1d + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    return comm_barrier(e);
+}
+
+// every rank's slice -> full replica on every rank (one ncclAllGather of equally sized, padded slices)
+int peer_gather(pgsgd_engine* e, int dims) {
+    const int n = e->n_ranks;
+    int rc = comm_barrier(e);
+    if (rc) return rc;
+    if (dims == 2) {
+        float* tmp = nullptr;
+        CU(cudaMalloc(&tmp, (size_t) n * e->part_chunk * 4 * sizeof(float)));
+        ncclResult_t r = ncclAllGather(e->d_xy_part, tmp, e->part_chunk * 4, ncclFloat, e->comm, e->stream);
+        cudaError_t ce = cudaSuccess;
+        if (r == ncclSuccess) ce = cudaMemcpyAsync(e->d_xy, tmp, 4 * e->N * sizeof(float), cudaMemcpyDeviceToDevice, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        cudaFree(tmp);
+        if (r != ncclSuccess) return fail(PGSGD_ERR_NCCL, "peer_gather: %s", ncclGetErrorString(r));
+        if (ce != cudaSuccess) return fail(PGSGD_ERR_CUDA, "peer_gather: %s", cudaGetErrorString(ce));
+    } else {
+        double* tmp = nullptr;
+        CU(cudaMalloc(&tmp, (size_t) n * e->part_chunk * sizeof(double)));
+        ncclResult_t r = ncclAllGather(e->d_x1d_part, tmp, e->part_chunk, ncclDouble, e->comm, e->stream);
+        cudaError_t ce = cudaSuccess;
+        if (r == ncclSuccess) ce = cudaMemcpyAsync(e->d_x1d, tmp, e->N * sizeof(double), cudaMemcpyDeviceToDevice, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        cudaFree(tmp);
+        if (r != ncclSuccess) return fail(PGSGD_ERR_NCCL, "peer_gather: %s", ncclGetErrorString(r));
+        if (ce != cudaSuccess) return fail(PGSGD_ERR_CUDA, "peer_gather: %s", cudaGetErrorString(ce));
+    }
+    return PGSGD_OK;
+}
+
 // iterations [iter_begin, iter_end) of the schedule cfg defines; iter_end == UINT64_MAX means "to the end"
 int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end, pgsgd_stats* stats) {
     int rc = check_config(cfg);
@@ -239,6 +364,10 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     // this rank's share of every iteration's term updates
     const uint64_t U = cfg->min_term_updates;
     const uint64_t U_rank = U / e->n_ranks + ((uint64_t) e->rank < U % e->n_ranks ? 1 : 0);
+    const bool peer = e->multi_mode == PGSGD_MULTI_PEER && e->comm;
+    if (peer && !(dims == 2 ? e->peer_ready_2d : e->peer_ready_1d)) return fail(PGSGD_ERR_STATE, "peer mode: coordinates were not set after the mode was selected");
+    // in peer mode all ranks update ONE coordinate array: the Hogwild in-flight cap is shared by the ranks
+    const uint64_t cap_div = peer ? (uint64_t) e->n_ranks : 1;
 
     // ---- sampling mode and launch shape ----
     const int block = 256;
@@ -260,7 +389,7 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
         uint64_t grid = (uint64_t) e->sm_count * blocks_per_sm;
         if (cfg->n_streams) grid = (cfg->n_streams + block - 1) / block;
         // Hogwild staleness cap (see below): terms in flight = grid * block * batch
-        const uint64_t cap_grid = (e->N / 4) / ((uint64_t) block * batch);
+        const uint64_t cap_grid = (e->N / 4) / ((uint64_t) block * batch * cap_div);
         if (!cfg->n_streams && grid > cap_grid) grid = cap_grid;
         if (grid == 0) {
             if (cfg->sampling == PGSGD_SAMPLING_TILE) grid = 1; else tile_mode = false;
@@ -281,7 +410,7 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
             n_streams = (uint64_t) e->sm_count * blocks_per_sm * block;
             // Hogwild staleness: with more than ~N/4 terms in flight the final stress of small graphs drifts away from the
             // reference's (measured: profiles/r01_stream_sweep.md); large graphs are not affected by this cap
-            uint64_t cap = (e->N / 4) / batch;
+            uint64_t cap = (e->N / 4) / (batch * cap_div);
             if (cap < 32) cap = 32;
             if (n_streams > cap) n_streams = cap;
             // keep at least ~64 terms per stream so the launch is not all prologue
@@ -307,7 +436,7 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     CU(cudaMemsetAsync(e->d_counted, 0, sizeof(unsigned long long), e->stream));
 
     const bool track_delta = cfg->delta > 0;
-    const bool sum_deltas = e->comm && (cfg->flags & PGSGD_FLAG_SUM_DELTAS);
+    const bool sum_deltas = e->comm && e->multi_mode != PGSGD_MULTI_PEER && (cfg->flags & PGSGD_FLAG_SUM_DELTAS);
     if (sum_deltas) {
         if (dims == 2 && !e->d_xy_prev) { rc = dev_alloc(e, &e->d_xy_prev, 4 * e->N); if (rc) return rc; }
         if (dims == 1 && !e->d_x1d_prev) { rc = dev_alloc(e, &e->d_x1d_prev, e->N); if (rc) return rc; }
@@ -348,6 +477,25 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
         p.last_visit_terms = rU ? rU - (extra - 1) * W : W;
         p.visit_rank = (uint32_t) e->rank;
         p.visit_nranks = (uint32_t) e->n_ranks;
+        if (peer) {
+            // this rank walks ITS OWN tiles (those whose middle node it owns): U * my_steps / S terms per iteration
+            p.tile_list = e->d_tile_list;
+            p.n_tiles = e->my_tiles;
+            p.visit_rank = 0;
+            p.visit_nranks = 1;
+            const uint64_t rUr = (uint64_t) ((double) rU * (double) e->my_tile_steps / (double) e->S);
+            const uint64_t extra_r = (rUr + W - 1) / W;
+            p.n_visits = e->my_tiles ? q * p.n_tiles + extra_r : 0;
+            p.last_visit_terms = rUr ? rUr - (extra_r - 1) * W : W;
+            if (p.n_tiles == 0) p.n_tiles = 1;
+        }
+    }
+    if (peer) {
+        p.n_parts = (uint32_t) e->n_ranks;
+        for (int q = 0; q < 9; ++q) p.part_lo[q] = e->part_lo[q];
+        for (int q = 0; q < 8; ++q) { p.part_xy[q] = e->peer_xy[q]; p.part_x1d[q] = e->peer_x1d[q]; }
+        rc = comm_barrier(e);  // nobody starts before every slice is in place
+        if (rc) return rc;
     }
 
     CU(cudaEventRecord(e->ev0, e->stream));
@@ -382,7 +530,11 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
         if (tile_mode) CU(launch_tile_iteration(dims, batch, p, shape, e->stream));
         else CU(launch_iteration(dims, batch, p, shape, e->stream));
         ++st.kernel_launches;
-        if (e->comm) {
+        if (peer) {
+            // no coordinate traffic here: every update already went to its owner through NVLink.  One 4-byte all-reduce per
+            // iteration keeps the ranks in the same cooling-schedule step (and carries the early-stop statistic).
+            NC(ncclAllReduce(e->d_delta, e->d_delta, 1, ncclUint32, ncclMax, e->comm, e->stream));
+        } else if (e->comm) {
             // one collective per cooling-schedule step: coordinates are replicated, term updates are sharded
             if (dims == 2) {
                 if (sum_deltas) {
@@ -519,6 +671,14 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
         }
         pos = pos_host.data();
     }
+    {
+        const uint64_t W = TILE_STEPS, nt = (g->step_count + W - 1) / W;
+        e->tile_mid_node.resize(nt);
+        for (uint64_t t = 0; t < nt; ++t) {
+            const uint64_t lo = t * W, hi = lo + W < g->step_count ? lo + W : g->step_count;
+            e->tile_mid_node[t] = g->step_node[lo + (hi - lo) / 2];
+        }
+    }
     // 1D default initialisation, kept on the host until asked for
     e->h_x1d_default.resize(e->N);
     {
@@ -567,6 +727,8 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
 void pgsgd_engine_destroy(pgsgd_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    for (void* q : e->ipc_opened) cudaIpcCloseMemHandle(q);
+    cudaFree(e->d_xy_part); cudaFree(e->d_x1d_part); cudaFree(e->d_tile_list);
     if (e->comm) ncclCommDestroy(e->comm);
     cudaFree(e->d_steps); cudaFree(e->d_path_first); cudaFree(e->d_xy); cudaFree(e->d_xy_prev); cudaFree(e->d_x1d);
     cudaFree(e->d_trace); cudaFree(e->d_trace_count);
@@ -594,6 +756,7 @@ int pgsgd_engine_set_coords_2d(pgsgd_engine* e, const double* X, const double* Y
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     cudaFree(dX); cudaFree(dY);
     if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "set_coords_2d: %s", cudaGetErrorString(err));
+    if (e->multi_mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, 2); if (rc) return rc; }
     e->have_2d = true;
     e->h2d_bytes += 4 * e->N * sizeof(double);
     e->seconds_upload += now_s() - t0;
@@ -604,6 +767,7 @@ int pgsgd_engine_get_coords_2d(pgsgd_engine* e, double* X, double* Y) {
     if (!e || !X || !Y) return fail(PGSGD_ERR_ARG, "get_coords_2d: NULL argument");
     if (!e->have_2d) return fail(PGSGD_ERR_STATE, "no 2D coordinates on the device");
     CU(cudaSetDevice(e->device));
+    if (e->multi_mode == PGSGD_MULTI_PEER && e->peer_ready_2d) { int rc = peer_gather(e, 2); if (rc) return rc; }
     double *dX = nullptr, *dY = nullptr;
     CU(cudaMalloc(&dX, 2 * e->N * sizeof(double)));
     if (cudaMalloc(&dY, 2 * e->N * sizeof(double)) != cudaSuccess) { cudaFree(dX); return fail(PGSGD_ERR_NOMEM, "cudaMalloc failed"); }
@@ -622,6 +786,7 @@ int pgsgd_engine_set_coords_2d_f32(pgsgd_engine* e, const float* xy) {
     if (!e->d_xy) { int rc = dev_alloc(e, &e->d_xy, 4 * e->N); if (rc) return rc; }
     CU(cudaMemcpyAsync(e->d_xy, xy, 4 * e->N * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    if (e->multi_mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, 2); if (rc) return rc; }
     e->have_2d = true;
     e->h2d_bytes += 4 * e->N * sizeof(float);
     return PGSGD_OK;
@@ -631,6 +796,7 @@ int pgsgd_engine_get_coords_2d_f32(pgsgd_engine* e, float* xy) {
     if (!e || !xy) return fail(PGSGD_ERR_ARG, "get_coords_2d_f32: NULL argument");
     if (!e->have_2d) return fail(PGSGD_ERR_STATE, "no 2D coordinates on the device");
     CU(cudaSetDevice(e->device));
+    if (e->multi_mode == PGSGD_MULTI_PEER && e->peer_ready_2d) { int rc = peer_gather(e, 2); if (rc) return rc; }
     CU(cudaMemcpyAsync(xy, e->d_xy, 4 * e->N * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return PGSGD_OK;
@@ -643,6 +809,7 @@ int pgsgd_engine_set_coords_1d(pgsgd_engine* e, const double* X) {
     const double* src = X ? X : e->h_x1d_default.data();
     CU(cudaMemcpyAsync(e->d_x1d, src, e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    if (e->multi_mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, 1); if (rc) return rc; }
     e->have_1d = true;
     e->h2d_bytes += e->N * sizeof(double);
     return PGSGD_OK;
@@ -652,6 +819,7 @@ int pgsgd_engine_get_coords_1d(pgsgd_engine* e, double* X) {
     if (!e || !X) return fail(PGSGD_ERR_ARG, "get_coords_1d: NULL argument");
     if (!e->have_1d) return fail(PGSGD_ERR_STATE, "no 1D coordinates on the device");
     CU(cudaSetDevice(e->device));
+    if (e->multi_mode == PGSGD_MULTI_PEER && e->peer_ready_1d) { int rc = peer_gather(e, 1); if (rc) return rc; }
     CU(cudaMemcpyAsync(X, e->d_x1d, e->N * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return PGSGD_OK;
@@ -732,6 +900,15 @@ int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int 
     ncclUniqueId id;
     memcpy(&id, unique_id, sizeof(id));
     NC(ncclCommInitRank(&e->comm, n_ranks, id, rank));
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode) {
+    if (!e) return fail(PGSGD_ERR_ARG, "set_multi_mode: NULL engine");
+    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_PEER) return fail(PGSGD_ERR_ARG, "unknown multi-GPU mode %d", mode);
+    if (mode == PGSGD_MULTI_PEER && (!e->comm || e->n_ranks < 2)) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator (pgsgd_engine_attach_comm) with >= 2 ranks");
+    if (e->have_2d || e->have_1d) return fail(PGSGD_ERR_STATE, "select the multi-GPU mode before uploading coordinates");
+    e->multi_mode = mode;
     return PGSGD_OK;
 }
 

@@ -36,6 +36,22 @@ __device__ __forceinline__ void st_coord(double* p, double v, bool plain_store) 
     else atomicExch(reinterpret_cast<unsigned long long*>(p), (unsigned long long) __double_as_longlong(v));
 }
 
+// coordinate addressing: one array, or the owner's slice in peer mode (n_parts <= 8: a branch-free range count)
+__device__ __forceinline__ float2* coord2_ptr(const IterParams& p, uint32_t node, uint32_t end) {
+    if (p.n_parts <= 1) return reinterpret_cast<float2*>(p.xy) + ((uint64_t) node * 2 + end);
+    uint32_t q = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) q += (k < (int) p.n_parts && node >= p.part_lo[k]) ? 1u : 0u;
+    return reinterpret_cast<float2*>(p.part_xy[q]) + ((uint64_t) node * 2 + end);
+}
+__device__ __forceinline__ double* coord1_ptr(const IterParams& p, uint32_t node) {
+    if (p.n_parts <= 1) return p.x1d + node;
+    uint32_t q = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) q += (k < (int) p.n_parts && node >= p.part_lo[k]) ? 1u : 0u;
+    return p.part_x1d[q] + node;
+}
+
 template <int BATCH>
 struct MinBlocks {
     static constexpr int value = BATCH >= 4 ? 2 : (BATCH == 2 ? 3 : 4);
@@ -72,7 +88,6 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
         const float eta_f = __double2float_rn(p.eta);
         const bool atomic_add = (p.flags & 5u) == 0;  // default; PGSGD_FLAG_EXCH_WRITE / PGSGD_FLAG_PLAIN_STORE select a racy write
         const bool st_mode = (p.flags & 4u) != 0;     // PGSGD_FLAG_PLAIN_STORE
-        float2* const xy2 = reinterpret_cast<float2*>(p.xy);
         const uint64_t pol_stream = l2_policy_evict_first();  // step records: read once, never reused
         const uint64_t pol_keep = l2_policy_evict_last();     // coordinates: keep resident in L2
 
@@ -111,8 +126,8 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
                         if (t[b].flip_b) { pos_b += rb[b].y; end_b ^= 1u; }
                         const uint64_t dpos = pos_a > pos_b ? pos_a - pos_b : pos_b - pos_a;
                         dij[b] = dpos ? __ull2float_rn(dpos) : 1e-9f;  // term_dist == 0 -> 1e-9 (:283-285)
-                        pa[b] = xy2 + ((uint64_t) (ra[b].x >> 1) * 2 + end_a);
-                        pb[b] = xy2 + ((uint64_t) (rb[b].x >> 1) * 2 + end_b);
+                        pa[b] = coord2_ptr(p, ra[b].x >> 1, end_a);
+                        pb[b] = coord2_ptr(p, rb[b].x >> 1, end_b);
                         ca[b] = ld_coord2(pa[b], pol_keep);
                         cb[b] = ld_coord2(pb[b], pol_keep);
                     }
@@ -168,8 +183,8 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
                             upd[b] = 4u;  // both frozen: counted, nothing moves (:298-302)
                         } else if (d != 0.0) {  // d == 0: `continue`, not counted (:320-323)
                             upd[b] = u | 4u;
-                            qa[b] = p.x1d + na;
-                            qb[b] = p.x1d + nb;
+                            qa[b] = coord1_ptr(p, na);
+                            qb[b] = coord1_ptr(p, nb);
                             xa[b] = ld_coord1(qa[b], pol_keep);
                             xb[b] = ld_coord1(qb[b], pol_keep);
                         }
@@ -262,7 +277,6 @@ __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(con
     const float eta_f = __double2float_rn(p.eta);
     const bool atomic_add = (p.flags & 5u) == 0;
     const bool st_mode = (p.flags & 4u) != 0;
-    float2* const xy2 = reinterpret_cast<float2*>(p.xy);
     const uint64_t pol_stream = l2_policy_evict_first();
     const uint64_t pol_keep = l2_policy_evict_last();
     uint64_t done = 0;
@@ -273,7 +287,8 @@ __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(con
         const uint64_t v = (uint64_t) p.visit_rank + k * p.visit_nranks;
         if (v >= p.n_visits) break;
         const uint64_t pass = v / p.n_tiles, i = v - pass * p.n_tiles;
-        const uint64_t t_idx = (i * p.perm_mul[pass & 15] + p.perm_add[pass & 15]) % p.n_tiles;
+        uint64_t t_idx = (i * p.perm_mul[pass & 15] + p.perm_add[pass & 15]) % p.n_tiles;
+        if (p.tile_list) t_idx = p.tile_list[t_idx];  // peer mode: the k-th tile this rank owns
         const uint64_t base = t_idx * (uint64_t) TILE_STEPS;
         const uint32_t terms = v + 1 == p.n_visits ? (uint32_t) p.last_visit_terms : (uint32_t) TILE_STEPS;
         // path of the tile's first and last step (one search each per visit instead of one per term)
@@ -343,8 +358,8 @@ __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(con
                         if (t[b].flip_b) { pos_b += rb[b].y; end_b ^= 1u; }
                         const uint64_t dpos = pos_a > pos_b ? pos_a - pos_b : pos_b - pos_a;
                         dij[b] = dpos ? __ull2float_rn(dpos) : 1e-9f;
-                        pa[b] = xy2 + ((uint64_t) (ra[b].x >> 1) * 2 + end_a);
-                        pb[b] = xy2 + ((uint64_t) (rb[b].x >> 1) * 2 + end_b);
+                        pa[b] = coord2_ptr(p, ra[b].x >> 1, end_a);
+                        pb[b] = coord2_ptr(p, rb[b].x >> 1, end_b);
                         ca[b] = ld_coord2(pa[b], pol_keep);
                         cb[b] = ld_coord2(pb[b], pol_keep);
                     }
@@ -388,8 +403,8 @@ __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(con
                         const double d = fabs(__dsub_rn(__ull2double_rn(step_pos(ra[b])), __ull2double_rn(step_pos(rb[b]))));
                         if (u == 0) { ++done; continue; }
                         if (d == 0.0) continue;
-                        double* qa = p.x1d + na;
-                        double* qb = p.x1d + nb;
+                        double* qa = coord1_ptr(p, na);
+                        double* qb = coord1_ptr(p, nb);
                         const double xa = ld_coord1(qa, pol_keep), xb = ld_coord1(qb, pol_keep);
                         double mu = __dmul_rn(p.eta, __ddiv_rn(1.0, d));
                         if (mu > 1.0) mu = 1.0;

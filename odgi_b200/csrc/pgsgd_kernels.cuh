@@ -31,6 +31,13 @@ struct IterParams {
     uint64_t perm_mul[16];      // per pass: tile = (i * perm_mul[pass] + perm_add[pass]) % n_tiles, a bijection on [0, n_tiles)
     uint64_t perm_add[16];
     uint32_t visit_rank, visit_nranks;  // this rank handles visits v with v % visit_nranks == visit_rank
+    // ---- multi-GPU peer mode: the coordinate array is PARTITIONED by node range over the GPUs of the box and every
+    //      GPU reads / reds the owner's slice directly through NVLink peer memory (no replica, no all-reduce) ----
+    uint32_t n_parts;               // 0/1: single array (p.xy / p.x1d); else number of partitions
+    uint32_t part_lo[9];            // partition q owns node ranks [part_lo[q], part_lo[q+1])
+    float*  part_xy[8];             // part_xy[q] + 4*node is node's {x0,y0,x1,y1} (pointers pre-offset by -4*part_lo[q])
+    double* part_x1d[8];
+    const uint32_t* tile_list;      // tile mode: the tiles this rank owns (nullptr = all tiles 0..n_tiles-1)
     // ---- verification: when trace != nullptr every drawn term is appended as {ia, ib | flip_a << 62 | flip_b << 63} ----
     unsigned long long* trace;
     unsigned long long* trace_count;

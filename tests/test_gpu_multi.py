@@ -59,6 +59,30 @@ with odgi_b200.Engine(gd, device=rank) as e:
     X, Y = e.get_coords_2d()
 out["default_stress"] = orc.path_stress_2d(go, X, Y, 1000000, 12345)
 out["default_updates"] = int(st["term_updates"])
+# peer mode: ONE coordinate array partitioned over the GPUs, updated through NVLink peer memory
+for tag, sampling in (("peer_stream", capi.SAMPLING_STREAM), ("peer_tile", capi.SAMPLING_TILE)):
+    cd = capi.layout_defaults(gd, sampling=sampling)
+    with odgi_b200.Engine(gd, device=rank) as e:
+        e.attach_comm(fresh_id(), world, rank)
+        e.set_multi_mode(capi.MULTI_PEER)
+        e.set_coords_2d(X0, Y0)
+        Xc, Yc = e.get_coords_2d()          # scatter -> gather round trip returns what was uploaded (as fp32)
+        rt = bool(np.array_equal(Xc, X0.astype(np.float32).astype(np.float64)) and np.array_equal(Yc, Y0.astype(np.float32).astype(np.float64)))
+        st = e.run_2d(cd)
+        X, Y = e.get_coords_2d()
+    cnt = torch.tensor([int(st["term_updates"])]); dist.all_reduce(cnt)
+    t = torch.from_numpy(X.copy()); lst = [torch.zeros_like(t) for _ in range(world)]; dist.all_gather(lst, t)
+    out[tag] = {"stress": orc.path_stress_2d(go, X, Y, 1000000, 12345), "updates": int(cnt.item()), "roundtrip": rt,
+                "identical": bool(all(torch.equal(lst[0], x) for x in lst)), "finite": bool(np.all(np.isfinite(X)) and np.all(np.isfinite(Y)))}
+a1 = read_arrays(os.path.join(os.environ["PGSGD_ROOT"], "tests/golden/LPA.graph.arr.gz"))
+g1, o1 = odgi_b200.graph_from_arrays(a1), orc.Graph.from_arrays(a1)
+with odgi_b200.Engine(g1, device=rank) as e:
+    e.attach_comm(fresh_id(), world, rank)
+    e.set_multi_mode(capi.MULTI_PEER)
+    e.set_coords_1d(None)
+    st = e.run_1d(capi.sort_defaults(g1))
+    x = e.get_coords_1d()
+out["peer_1d"] = {"stress": orc.path_stress_1d(o1, x, 1000000, 12345), "finite": bool(np.all(np.isfinite(x)))}
 if rank == 0:
     print("RESULT " + json.dumps(out))
 dist.destroy_process_group()
@@ -82,3 +106,14 @@ def test_two_rank_nccl_run_matches_emulation(tmp_path):
         assert res[tag]["equal"], res
     assert res["default_updates"] == 30 * 10 * 35059 // 2
     assert 0.06 < res["default_stress"] < 0.09, res
+    # peer mode is one shared Hogwild: its stress sits in the single-GPU / reference band (no replica averaging loss)
+    with open(os.path.join(ROOT, "tests", "golden", "stress_reference.json")) as f:
+        bands = json.load(f)
+    b2 = bands["DRB1-3123.layout2d"]
+    for tag in ("peer_stream", "peer_tile"):
+        r = res[tag]
+        assert r["roundtrip"] and r["identical"] and r["finite"], res
+        assert abs(r["updates"] - 30 * 10 * 35059) <= 30 * 2048, res
+        assert abs(r["stress"] - b2["mean"]) <= 0.03 * b2["mean"], (tag, r["stress"], b2["mean"])
+    b1 = bands["LPA.sort1d"]
+    assert res["peer_1d"]["finite"] and abs(res["peer_1d"]["stress"] - b1["mean"]) <= 0.03 * b1["mean"] + 2 * b1["sd"], res
