@@ -176,8 +176,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--flags", type=int, default=0)
-    ap.add_argument("--multi", default="peer", choices=["peer", "allreduce"],
-                    help="N>1: 'peer' = coordinates partitioned over the GPUs, updated through NVLink peer memory; 'allreduce' = replicated + 1 all-reduce/step")
+    ap.add_argument("--multi", default="hybrid", choices=["hybrid", "peer", "allreduce"],
+                    help="N>1: 'peer' = coordinates partitioned over the GPUs, updated through NVLink peer memory (one shared Hogwild); "
+                         "'allreduce' = replicated + 1 all-reduce/step (fastest, costs layout quality); 'hybrid' = allreduce for the first "
+                         "third of the schedule, peer afterwards (single-GPU layout quality)")
     ap.add_argument("--sampling", type=int, default=0, help="0 auto, 1 stream (reference-exact worker streams), 2 tile")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -232,8 +234,7 @@ def main():
     e = odgi_b200.Engine(g, device=local_rank)
     if uid is not None:
         e.attach_comm(uid, world, rank)
-        if args.multi == "peer":
-            e.set_multi_mode(capi.MULTI_PEER)
+        e.set_multi_mode({"peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE}[args.multi])
     e.set_coords_2d(X0, Y0)
     barrier()
     e.run_range(cfg, 2, 0, W)                      # W untimed warm-up steps (iterations 0..W-1 of the schedule)
@@ -280,8 +281,7 @@ def main():
             obj = [capi.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(obj, src=0)
             e2.attach_comm(obj[0], world, rank)
-            if args.multi == "peer":
-                e2.set_multi_mode(capi.MULTI_PEER)
+            e2.set_multi_mode({"peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE}[args.multi])
         e2.set_coords_2d(Xp, Yp)                            # coordinate upload
         st2 = e2.run_range(cfg_e, 2, 0, K)                  # the same number of steps
         Xo, Yo = e2.get_coords_2d()                         # result download
@@ -320,7 +320,9 @@ def main():
                    "l2_policy": "inputs larger than L2" if g.S * 16 > 126e6 else "L2-resident graph (plumbing config)",
                    "parallelism": ("1 GPU" if world == 1 else
                                    f"coords partitioned over {world} GPUs, updated through NVLink peer memory (one shared Hogwild), tiles owned by node range"
-                                   if args.multi == "peer" else f"replicated coords, term updates split over {world} GPU(s), 1 NCCL all-reduce/step"),
+                                   if args.multi == "peer" else
+                                   f"hybrid over {world} GPUs: iterations < {iter_max // 3} replicated + 1 NCCL all-reduce/step, then coords partitioned and updated through NVLink peer memory"
+                                   if args.multi == "hybrid" else f"replicated coords, term updates split over {world} GPU(s), 1 NCCL all-reduce/step"),
                    "device_bytes": dev_bytes, "coords_finite": finite},
         "gpu_launches": K * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

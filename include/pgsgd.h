@@ -76,6 +76,7 @@ typedef struct pgsgd_config {
                                               batch 1 applies a stream's terms strictly in order */
     uint32_t flags;                        /* PGSGD_FLAG_* */
     uint32_t sampling;                     /* PGSGD_SAMPLING_*: how the first step of a term is chosen */
+    uint64_t multi_switch_iteration;       /* PGSGD_MULTI_HYBRID: first iteration of the peer phase; 0 = iter_max / 3 */
 } pgsgd_config;
 
 /* First-step sampling.  The partner of a term is always drawn by the reference's rule.
@@ -163,9 +164,14 @@ int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int 
  *  PEER     : coordinates PARTITIONED by node range over the GPUs of one NVLink domain (<= 8); every update reads and
  *             red.adds the owner's slice directly through NVLink peer memory (CUDA IPC), so all GPUs run one shared
  *             Hogwild exactly like the threads of the reference — no replica drift, no all-reduce of coordinates.  Tiles
- *             are assigned to the rank owning their nodes, which keeps ~80 % of the traffic on the local GPU. */
+ *             are assigned to the rank owning their nodes, which keeps ~80 % of the traffic on the local GPU.
+ *  HYBRID   : ALLREDUCE for the first third of the schedule (cfg.multi_switch_iteration), PEER from then on.  The early
+ *             iterations saturate every update (mu = 1) and draw half of the partners uniformly over the path (mostly on
+ *             another GPU): replicas tolerate them and NVLink does not; the annealing two thirds decide the final stress
+ *             and run as one shared Hogwild.  Final stress within the single-GPU band at 4 and 8 ranks. */
 #define PGSGD_MULTI_ALLREDUCE 0
 #define PGSGD_MULTI_PEER      1
+#define PGSGD_MULTI_HYBRID    2
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode);
 
 /* ---- verification hooks (used by tests; they exercise exactly the device code the runs use) ---- */

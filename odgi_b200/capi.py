@@ -19,7 +19,7 @@ PGSGD_FLAG_EXCH_WRITE = 1
 PGSGD_FLAG_SUM_DELTAS = 2
 PGSGD_FLAG_PLAIN_STORE = 4
 SAMPLING_AUTO, SAMPLING_STREAM, SAMPLING_TILE = 0, 1, 2
-MULTI_ALLREDUCE, MULTI_PEER = 0, 1
+MULTI_ALLREDUCE, MULTI_PEER, MULTI_HYBRID = 0, 1, 2
 
 
 class PgsgdError(RuntimeError):
@@ -39,7 +39,7 @@ class ConfigC(C.Structure):
                 ("delta", C.c_double), ("eps", C.c_double), ("eta_max", C.c_double), ("theta", C.c_double),
                 ("space", C.c_uint64), ("space_max", C.c_uint64), ("space_quantization_step", C.c_uint64),
                 ("cooling_start", C.c_double), ("seed", C.c_uint64), ("n_streams", C.c_uint32), ("batch", C.c_uint32),
-                ("flags", C.c_uint32), ("sampling", C.c_uint32)]
+                ("flags", C.c_uint32), ("sampling", C.c_uint32), ("multi_switch_iteration", C.c_uint64)]
 
 
 class StatsC(C.Structure):
@@ -132,11 +132,12 @@ class Config:
     batch: int = 0
     flags: int = 0
     sampling: int = 0   # 0 auto, 1 stream (reference-exact worker streams), 2 tile
+    multi_switch_iteration: int = 0   # hybrid multi-GPU mode: first peer-phase iteration (0 = iter_max // 3)
 
     def c(self) -> ConfigC:
         return ConfigC(self.iter_max, self.iter_with_max_learning_rate, self.min_term_updates, self.delta, self.eps,
                        self.eta_max, self.theta, self.space, self.space_max, self.space_quantization_step,
-                       self.cooling_start, self.seed, self.n_streams, self.batch, self.flags, self.sampling)
+                       self.cooling_start, self.seed, self.n_streams, self.batch, self.flags, self.sampling, self.multi_switch_iteration)
 
 
 @dataclass

@@ -143,7 +143,9 @@ struct pgsgd_engine {
     ncclComm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
     // ---- peer mode (PGSGD_MULTI_PEER): coordinates partitioned by node range, accessed through NVLink peer memory ----
-    int multi_mode = 0;
+    int multi_mode = 0;                      // what the caller selected (PGSGD_MULTI_*)
+    int active_mode = 0;                     // what the run in progress uses: ALLREDUCE or PEER (HYBRID switches between them)
+    bool coords_in_slices = false;           // the authoritative coordinates are in the peer slices (peer phase), not the replica
     bool peer_ready_2d = false, peer_ready_1d = false;
     uint64_t part_chunk = 0;                 // nodes per partition (last one may be shorter)
     uint32_t part_lo[9] = {0};
@@ -301,6 +303,7 @@ int peer_scatter(pgsgd_engine* e, int dims) {
     const uint64_t lo = e->part_lo[e->rank], hi = e->part_lo[e->rank + 1];
     if (dims == 2) CU(cudaMemcpyAsync(e->d_xy_part, e->d_xy + 4 * lo, (hi - lo) * 4 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
     else CU(cudaMemcpyAsync(e->d_x1d_part, e->d_x1d + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    e->coords_in_slices = true;
     return comm_barrier(e);
 }
 
@@ -334,7 +337,7 @@ int peer_gather(pgsgd_engine* e, int dims) {
 }
 
 // iterations [iter_begin, iter_end) of the schedule cfg defines; iter_end == UINT64_MAX means "to the end"
-int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end, pgsgd_stats* stats) {
+int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end, pgsgd_stats* stats) {
     int rc = check_config(cfg);
     if (rc) return rc;
     if (dims == 2 && !e->have_2d) return fail(PGSGD_ERR_STATE, "2D coordinates were not set (pgsgd_engine_set_coords_2d)");
@@ -364,7 +367,7 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     // this rank's share of every iteration's term updates
     const uint64_t U = cfg->min_term_updates;
     const uint64_t U_rank = U / e->n_ranks + ((uint64_t) e->rank < U % e->n_ranks ? 1 : 0);
-    const bool peer = e->multi_mode == PGSGD_MULTI_PEER && e->comm;
+    const bool peer = e->active_mode == PGSGD_MULTI_PEER && e->comm;
     if (peer && !(dims == 2 ? e->peer_ready_2d : e->peer_ready_1d)) return fail(PGSGD_ERR_STATE, "peer mode: coordinates were not set after the mode was selected");
     // in peer mode all ranks update ONE coordinate array: the Hogwild in-flight cap is shared by the ranks
     const uint64_t cap_div = peer ? (uint64_t) e->n_ranks : 1;
@@ -426,17 +429,18 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     }
 
     if (iter_begin == 0 || e->rng_streams != n_streams) {
-        if (iter_begin != 0) return fail(PGSGD_ERR_STATE, "continuing a schedule needs the same launch shape as the call that started it");
         rc = ensure_rng(e, n_streams);
         if (rc) return rc;
-        // worker stream t of rank r is the reference's worker thread (r * n_streams + t): seed + tid (path_sgd_layout.cpp:168)
-        CU(launch_seed_streams(e->d_rng, e->rng_stride, n_streams, cfg->seed + (uint64_t) e->rank * n_streams, e->stream));
+        // worker stream t of rank r is the reference's worker thread (r * n_streams + t): seed + tid (path_sgd_layout.cpp:168).
+        // A continuation with a different launch shape (the hybrid multi-GPU schedule changes phase) starts fresh streams.
+        const uint64_t reseed = iter_begin == 0 ? 0 : 0x5851F42D4C957F2DULL * iter_begin;
+        CU(launch_seed_streams(e->d_rng, e->rng_stride, n_streams, cfg->seed + reseed + (uint64_t) e->rank * n_streams, e->stream));
         e->rng_streams = n_streams;
     }
     CU(cudaMemsetAsync(e->d_counted, 0, sizeof(unsigned long long), e->stream));
 
     const bool track_delta = cfg->delta > 0;
-    const bool sum_deltas = e->comm && e->multi_mode != PGSGD_MULTI_PEER && (cfg->flags & PGSGD_FLAG_SUM_DELTAS);
+    const bool sum_deltas = e->comm && e->active_mode != PGSGD_MULTI_PEER && (cfg->flags & PGSGD_FLAG_SUM_DELTAS);
     if (sum_deltas) {
         if (dims == 2 && !e->d_xy_prev) { rc = dev_alloc(e, &e->d_xy_prev, 4 * e->N); if (rc) return rc; }
         if (dims == 1 && !e->d_x1d_prev) { rc = dev_alloc(e, &e->d_x1d_prev, e->N); if (rc) return rc; }
@@ -576,6 +580,53 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     st.term_updates = counted;
     st.seconds_iterations = ms * 1e-3;
     if (stats) *stats = st;
+    return PGSGD_OK;
+}
+
+// Picks the multi-GPU phase(s).  HYBRID: the first third of the schedule — where every update saturates (mu = 1) and half
+// of the partners are uniform over the path, i.e. mostly on another GPU — runs replicated with one all-reduce per
+// iteration; from then on the replica is scattered into node-range slices and all GPUs run ONE shared Hogwild through
+// NVLink peer memory.  Final stress equals the single-GPU one (oracle emulation + tests/test_gpu_multi.py), at most
+// of the all-reduce mode's throughput in the early phase.
+int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end, pgsgd_stats* stats) {
+    if (!e->comm || e->multi_mode != PGSGD_MULTI_HYBRID) {
+        e->active_mode = e->comm ? e->multi_mode : PGSGD_MULTI_ALLREDUCE;
+        return run_phase(e, cfg, dims, iter_begin, iter_end, stats);
+    }
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    const uint64_t n_iters = dims == 1 ? cfg->iter_max + 1 : cfg->iter_max;
+    if (iter_end > n_iters) iter_end = n_iters;
+    const uint64_t sw = cfg->multi_switch_iteration ? cfg->multi_switch_iteration : cfg->iter_max / 3;
+    pgsgd_stats a, b;
+    memset(&a, 0, sizeof(a));
+    memset(&b, 0, sizeof(b));
+    bool ran_a = false, ran_b = false;
+    if (iter_begin < sw && !e->coords_in_slices) {
+        e->active_mode = PGSGD_MULTI_ALLREDUCE;
+        rc = run_phase(e, cfg, dims, iter_begin, iter_end < sw ? iter_end : sw, &a);
+        if (rc) return rc;
+        ran_a = true;
+        if (a.iterations_run < (iter_end < sw ? iter_end : sw) - iter_begin) { if (stats) *stats = a; return PGSGD_OK; }  // early stop
+    }
+    if (iter_end > sw || e->coords_in_slices) {
+        if (!e->coords_in_slices) { rc = peer_scatter(e, dims); if (rc) return rc; }
+        e->active_mode = PGSGD_MULTI_PEER;
+        rc = run_phase(e, cfg, dims, iter_begin > sw ? iter_begin : (ran_a ? sw : iter_begin), iter_end, &b);
+        if (rc) return rc;
+        ran_b = true;
+    }
+    if (stats) {
+        pgsgd_stats st = ran_a ? a : b;
+        if (ran_a && ran_b) {
+            st.iterations_run += b.iterations_run;
+            st.term_updates += b.term_updates;
+            st.seconds_iterations += b.seconds_iterations;
+            st.kernel_launches += b.kernel_launches;
+            st.last_delta_max = b.last_delta_max;
+        }
+        *stats = st;
+    }
     return PGSGD_OK;
 }
 
@@ -756,6 +807,7 @@ int pgsgd_engine_set_coords_2d(pgsgd_engine* e, const double* X, const double* Y
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
     cudaFree(dX); cudaFree(dY);
     if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "set_coords_2d: %s", cudaGetErrorString(err));
+    e->coords_in_slices = false;
     if (e->multi_mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, 2); if (rc) return rc; }
     e->have_2d = true;
     e->h2d_bytes += 4 * e->N * sizeof(double);
@@ -767,7 +819,7 @@ int pgsgd_engine_get_coords_2d(pgsgd_engine* e, double* X, double* Y) {
     if (!e || !X || !Y) return fail(PGSGD_ERR_ARG, "get_coords_2d: NULL argument");
     if (!e->have_2d) return fail(PGSGD_ERR_STATE, "no 2D coordinates on the device");
     CU(cudaSetDevice(e->device));
-    if (e->multi_mode == PGSGD_MULTI_PEER && e->peer_ready_2d) { int rc = peer_gather(e, 2); if (rc) return rc; }
+    if (e->coords_in_slices && e->peer_ready_2d) { int rc = peer_gather(e, 2); if (rc) return rc; }
     double *dX = nullptr, *dY = nullptr;
     CU(cudaMalloc(&dX, 2 * e->N * sizeof(double)));
     if (cudaMalloc(&dY, 2 * e->N * sizeof(double)) != cudaSuccess) { cudaFree(dX); return fail(PGSGD_ERR_NOMEM, "cudaMalloc failed"); }
@@ -786,6 +838,7 @@ int pgsgd_engine_set_coords_2d_f32(pgsgd_engine* e, const float* xy) {
     if (!e->d_xy) { int rc = dev_alloc(e, &e->d_xy, 4 * e->N); if (rc) return rc; }
     CU(cudaMemcpyAsync(e->d_xy, xy, 4 * e->N * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    e->coords_in_slices = false;
     if (e->multi_mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, 2); if (rc) return rc; }
     e->have_2d = true;
     e->h2d_bytes += 4 * e->N * sizeof(float);
@@ -796,7 +849,7 @@ int pgsgd_engine_get_coords_2d_f32(pgsgd_engine* e, float* xy) {
     if (!e || !xy) return fail(PGSGD_ERR_ARG, "get_coords_2d_f32: NULL argument");
     if (!e->have_2d) return fail(PGSGD_ERR_STATE, "no 2D coordinates on the device");
     CU(cudaSetDevice(e->device));
-    if (e->multi_mode == PGSGD_MULTI_PEER && e->peer_ready_2d) { int rc = peer_gather(e, 2); if (rc) return rc; }
+    if (e->coords_in_slices && e->peer_ready_2d) { int rc = peer_gather(e, 2); if (rc) return rc; }
     CU(cudaMemcpyAsync(xy, e->d_xy, 4 * e->N * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return PGSGD_OK;
@@ -809,6 +862,7 @@ int pgsgd_engine_set_coords_1d(pgsgd_engine* e, const double* X) {
     const double* src = X ? X : e->h_x1d_default.data();
     CU(cudaMemcpyAsync(e->d_x1d, src, e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    e->coords_in_slices = false;
     if (e->multi_mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, 1); if (rc) return rc; }
     e->have_1d = true;
     e->h2d_bytes += e->N * sizeof(double);
@@ -819,7 +873,7 @@ int pgsgd_engine_get_coords_1d(pgsgd_engine* e, double* X) {
     if (!e || !X) return fail(PGSGD_ERR_ARG, "get_coords_1d: NULL argument");
     if (!e->have_1d) return fail(PGSGD_ERR_STATE, "no 1D coordinates on the device");
     CU(cudaSetDevice(e->device));
-    if (e->multi_mode == PGSGD_MULTI_PEER && e->peer_ready_1d) { int rc = peer_gather(e, 1); if (rc) return rc; }
+    if (e->coords_in_slices && e->peer_ready_1d) { int rc = peer_gather(e, 1); if (rc) return rc; }
     CU(cudaMemcpyAsync(X, e->d_x1d, e->N * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return PGSGD_OK;
@@ -905,8 +959,8 @@ int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int 
 
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode) {
     if (!e) return fail(PGSGD_ERR_ARG, "set_multi_mode: NULL engine");
-    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_PEER) return fail(PGSGD_ERR_ARG, "unknown multi-GPU mode %d", mode);
-    if (mode == PGSGD_MULTI_PEER && (!e->comm || e->n_ranks < 2)) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator (pgsgd_engine_attach_comm) with >= 2 ranks");
+    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_PEER && mode != PGSGD_MULTI_HYBRID) return fail(PGSGD_ERR_ARG, "unknown multi-GPU mode %d", mode);
+    if (mode != PGSGD_MULTI_ALLREDUCE && (!e->comm || e->n_ranks < 2)) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator (pgsgd_engine_attach_comm) with >= 2 ranks");
     if (e->have_2d || e->have_1d) return fail(PGSGD_ERR_STATE, "select the multi-GPU mode before uploading coordinates");
     e->multi_mode = mode;
     return PGSGD_OK;

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_header():
-    assert C.sizeof(capi.ConfigC) == 112
+    assert C.sizeof(capi.ConfigC) == 120
     assert C.sizeof(capi.GraphView) == 64
     assert C.sizeof(capi.StatsC) == 72
 

@@ -60,11 +60,12 @@ with odgi_b200.Engine(gd, device=rank) as e:
 out["default_stress"] = orc.path_stress_2d(go, X, Y, 1000000, 12345)
 out["default_updates"] = int(st["term_updates"])
 # peer mode: ONE coordinate array partitioned over the GPUs, updated through NVLink peer memory
-for tag, sampling in (("peer_stream", capi.SAMPLING_STREAM), ("peer_tile", capi.SAMPLING_TILE)):
+for tag, sampling, mode in (("peer_stream", capi.SAMPLING_STREAM, capi.MULTI_PEER), ("peer_tile", capi.SAMPLING_TILE, capi.MULTI_PEER),
+                            ("hybrid_stream", capi.SAMPLING_STREAM, capi.MULTI_HYBRID), ("hybrid_tile", capi.SAMPLING_TILE, capi.MULTI_HYBRID)):
     cd = capi.layout_defaults(gd, sampling=sampling)
     with odgi_b200.Engine(gd, device=rank) as e:
         e.attach_comm(fresh_id(), world, rank)
-        e.set_multi_mode(capi.MULTI_PEER)
+        e.set_multi_mode(mode)
         e.set_coords_2d(X0, Y0)
         Xc, Yc = e.get_coords_2d()          # scatter -> gather round trip returns what was uploaded (as fp32)
         rt = bool(np.array_equal(Xc, X0.astype(np.float32).astype(np.float64)) and np.array_equal(Yc, Y0.astype(np.float32).astype(np.float64)))
@@ -110,7 +111,7 @@ def test_two_rank_nccl_run_matches_emulation(tmp_path):
     with open(os.path.join(ROOT, "tests", "golden", "stress_reference.json")) as f:
         bands = json.load(f)
     b2 = bands["DRB1-3123.layout2d"]
-    for tag in ("peer_stream", "peer_tile"):
+    for tag in ("peer_stream", "peer_tile", "hybrid_stream", "hybrid_tile"):
         r = res[tag]
         assert r["roundtrip"] and r["identical"] and r["finite"], res
         assert abs(r["updates"] - 30 * 10 * 35059) <= 30 * 2048, res
