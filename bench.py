@@ -236,6 +236,7 @@ def main():
         e.attach_comm(uid, world, rank)
         e.set_multi_mode({"peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE}[args.multi])
     e.set_coords_2d(X0, Y0)
+    stress_initial = e.path_stress(2, 4_000_000, 12345)
     barrier()
     e.run_range(cfg, 2, 0, W)                      # W untimed warm-up steps (iterations 0..W-1 of the schedule)
     sampler = ClockSampler(local_rank)
@@ -257,6 +258,14 @@ def main():
         total_updates = float(tt.item())
     assert abs(total_updates - K * U) <= 1e-3 * K * U, (total_updates, K * U)
     value = total_updates / dev_s / 1e6
+    # layout quality of the COMPLETE schedule: finish the remaining iterations (untimed) and evaluate the sampled path
+    # stress on the device (collective in multi-GPU runs)
+    quality = None
+    if W + K <= iter_max:
+        if W + K < iter_max:
+            e.run_range(cfg, 2, W + K, iter_max)
+        quality = {"stress_initial": stress_initial, "stress_final": e.path_stress(2, 4_000_000, 12345), "pairs": 4_000_000,
+                   "definition": "sampled path stress, SURVEY.md 8d / pgsgd_engine_path_stress; complete default schedule of " + str(iter_max) + " iterations"}
     Xf, Yf = e.get_coords_2d()
     finite = bool(np.all(np.isfinite(Xf)) and np.all(np.isfinite(Yf)))
     dev_bytes = e.device_bytes
@@ -331,6 +340,8 @@ def main():
                      "kernel_ms": step_s * 1e3},
         "clocks": clocks, "wall_s_timed_region": wall,
     }
+    if quality:
+        line["quality"] = quality
     if e2e:
         line["e2e"] = e2e
     if cb:

@@ -183,6 +183,12 @@ int pgsgd_engine_sample_terms(pgsgd_engine* e, const pgsgd_config* cfg, int dims
                               uint64_t* rank_b, uint32_t* node_a, uint32_t* node_b, uint64_t* pos_a, uint64_t* pos_b,
                               uint8_t* end_a, uint8_t* end_b, uint8_t* valid);
 
+/* Sampled path stress of the resident coordinates, evaluated on the device: n_pairs (rounded up to a multiple of 4096)
+ * step pairs — first step uniform over all steps, partner uniform in the same path, node ends uniform (2D) / node
+ * starts (1D) — stress = mean(((|p_a - p_b| - d) / d)^2), d = path distance in bp, pairs with d = 0 skipped.  The
+ * reference has no layout-quality readout on this path; this is the one the parity tests use. */
+int pgsgd_engine_path_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64_t seed, double* stress_out);
+
 /* Tile-sampling verification: with a trace buffer set, every term the tile kernel draws is recorded (first step,
  * partner step as global step indices, flips = flip_a | flip_b << 1) until the buffer is full. */
 int pgsgd_engine_set_trace(pgsgd_engine* e, uint64_t capacity);   /* 0 = off */

@@ -705,22 +705,13 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(PGSGD_ERR_CUDA, "cudaStreamCreate failed"));
     if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) return bail(fail(PGSGD_ERR_CUDA, "cudaEventCreate failed"));
 
-    // validate node ranks and derive the per-path bp offsets when the caller did not supply them (xp.cpp:607-616)
-    std::vector<uint64_t> pos_host;
+    // With caller-supplied positions the node ranks are validated here; without, validation and the per-path bp offsets
+    // (xp.cpp:607-616) are done on the device below — no O(S) host pass at all.
     const uint64_t* pos = g->step_pos;
-    for (uint64_t s = 0; s < g->step_count; ++s) {
-        if (g->step_node[s] >= g->node_count) return bail(fail(PGSGD_ERR_UNOPT, "step %llu refers to node rank %u >= node_count: ids are not compacted 1..N", (unsigned long long) s, g->step_node[s]));
-    }
-    if (!pos) {
-        pos_host.resize(g->step_count);
-        for (uint64_t p = 0; p < g->path_count; ++p) {
-            uint64_t off = 0;
-            for (uint64_t s = g->path_first_step[p]; s < g->path_first_step[p + 1]; ++s) {
-                pos_host[s] = off;
-                off += g->node_len[g->step_node[s]];
-            }
+    if (pos) {
+        for (uint64_t s = 0; s < g->step_count; ++s) {
+            if (g->step_node[s] >= g->node_count) return bail(fail(PGSGD_ERR_UNOPT, "step %llu refers to node rank %u >= node_count: ids are not compacted 1..N", (unsigned long long) s, g->step_node[s]));
         }
-        pos = pos_host.data();
     }
     {
         const uint64_t W = TILE_STEPS, nt = (g->step_count + W - 1) / W;
@@ -753,19 +744,40 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
     if (cudaMalloc(&d_node_len, e->N * sizeof(uint32_t)) != cudaSuccess) return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc node_len staging failed"));
     if ((err = cudaMemcpyAsync(d_node_len, g->node_len, e->N * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) { cudaFree(d_node_len); return cu_bail(err, "upload node_len"); }
     e->h2d_bytes += e->N * sizeof(uint32_t);
-    const uint64_t CH = 1ull << 26;  // 64 Mi steps per staging chunk (832 MiB of SoA)
-    const uint64_t ch = e->S < CH ? (e->S ? e->S : 1) : CH;
     uint32_t* d_sn = nullptr; uint8_t* d_sr = nullptr; uint64_t* d_sp = nullptr;
-    bool ok = cudaMalloc(&d_sn, ch * 4) == cudaSuccess && cudaMalloc(&d_sp, ch * 8) == cudaSuccess && (!g->step_rev || cudaMalloc(&d_sr, ch) == cudaSuccess);
-    if (!ok) { cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
-    for (uint64_t off = 0; off < e->S && err == cudaSuccess; off += ch) {
-        const uint64_t n = e->S - off < ch ? e->S - off : ch;
-        err = cudaMemcpyAsync(d_sn, g->step_node + off, n * 4, cudaMemcpyHostToDevice, e->stream);
-        if (err == cudaSuccess) err = cudaMemcpyAsync(d_sp, pos + off, n * 8, cudaMemcpyHostToDevice, e->stream);
-        if (err == cudaSuccess && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev + off, n, cudaMemcpyHostToDevice, e->stream);
-        if (err == cudaSuccess) err = launch_pack_steps(e->d_steps, d_sn, d_sr, d_sp, d_node_len, n, off, e->stream);
-        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);  // staging buffers and pageable sources are reused
-        e->h2d_bytes += n * (4 + 8 + (g->step_rev ? 1 : 0));
+    if (pos) {
+        const uint64_t CH = 1ull << 26;  // 64 Mi steps per staging chunk (832 MiB of SoA)
+        const uint64_t ch = e->S < CH ? (e->S ? e->S : 1) : CH;
+        bool ok = cudaMalloc(&d_sn, ch * 4) == cudaSuccess && cudaMalloc(&d_sp, ch * 8) == cudaSuccess && (!g->step_rev || cudaMalloc(&d_sr, ch) == cudaSuccess);
+        if (!ok) { cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
+        for (uint64_t off = 0; off < e->S && err == cudaSuccess; off += ch) {
+            const uint64_t n = e->S - off < ch ? e->S - off : ch;
+            err = cudaMemcpyAsync(d_sn, g->step_node + off, n * 4, cudaMemcpyHostToDevice, e->stream);
+            if (err == cudaSuccess) err = cudaMemcpyAsync(d_sp, pos + off, n * 8, cudaMemcpyHostToDevice, e->stream);
+            if (err == cudaSuccess && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev + off, n, cudaMemcpyHostToDevice, e->stream);
+            if (err == cudaSuccess) err = launch_pack_steps(e->d_steps, d_sn, d_sr, d_sp, d_node_len, n, off, e->stream);
+            if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);  // staging buffers and pageable sources are reused
+            e->h2d_bytes += n * (4 + 8 + (g->step_rev ? 1 : 0));
+        }
+    } else {
+        // whole-array staging (5 B per step in, 8 B per step of scan scratch), positions by a device-wide scan
+        const uint64_t n = e->S ? e->S : 1;
+        int* d_bad = nullptr;
+        bool ok = cudaMalloc(&d_sn, n * 4) == cudaSuccess && cudaMalloc(&d_sp, n * 8) == cudaSuccess && cudaMalloc(&d_bad, sizeof(int)) == cudaSuccess &&
+                  (!g->step_rev || cudaMalloc(&d_sr, n) == cudaSuccess);
+        if (!ok) { cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_bad); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
+        err = cudaMemsetAsync(d_bad, 0, sizeof(int), e->stream);
+        if (err == cudaSuccess) err = cudaMemcpyAsync(d_sn, g->step_node, e->S * 4, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev, e->S, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess) err = launch_flatten_on_device(e->d_steps, d_sn, d_sr, d_node_len, e->d_path_first, (uint32_t) e->P, (uint32_t) e->N, e->S, d_sp, d_bad, e->stream);
+        int bad = 0;
+        if (err == cudaSuccess) err = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(d_bad);
+        e->h2d_bytes += e->S * (4 + (g->step_rev ? 1 : 0));
+        if (err == cudaSuccess && bad) {
+            cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr);
+            return bail(fail(PGSGD_ERR_UNOPT, "a step refers to a node rank >= node_count: ids are not compacted 1..N"));
+        }
     }
     cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr);
     if (err != cudaSuccess) return cu_bail(err, "flatten-to-device");
@@ -954,6 +966,32 @@ int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int 
     ncclUniqueId id;
     memcpy(&id, unique_id, sizeof(id));
     NC(ncclCommInitRank(&e->comm, n_ranks, id, rank));
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_path_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64_t seed, double* stress_out) {
+    if (!e || !stress_out) return fail(PGSGD_ERR_ARG, "path_stress: NULL argument");
+    if (dims != 1 && dims != 2) return fail(PGSGD_ERR_ARG, "dims must be 1 or 2");
+    if (dims == 2 ? !e->have_2d : !e->have_1d) return fail(PGSGD_ERR_STATE, "no coordinates on the device");
+    CU(cudaSetDevice(e->device));
+    if (e->coords_in_slices) { int rc = peer_gather(e, dims); if (rc) return rc; }
+    double* d_acc = nullptr;
+    unsigned long long* d_used = nullptr;
+    CU(cudaMalloc(&d_acc, STRESS_STREAMS * sizeof(double)));
+    if (cudaMalloc(&d_used, STRESS_STREAMS * sizeof(unsigned long long)) != cudaSuccess) { cudaFree(d_acc); return fail(PGSGD_ERR_NOMEM, "cudaMalloc failed"); }
+    const uint64_t per = (n_pairs + STRESS_STREAMS - 1) / STRESS_STREAMS;
+    cudaError_t err = launch_stress(dims, e->d_path_first, (uint32_t) e->P, e->S, e->d_steps, e->d_xy, e->d_x1d, per, seed, d_acc, d_used, e->stream);
+    std::vector<double> acc(STRESS_STREAMS);
+    std::vector<unsigned long long> used(STRESS_STREAMS);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(acc.data(), d_acc, STRESS_STREAMS * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(used.data(), d_used, STRESS_STREAMS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(d_acc); cudaFree(d_used);
+    if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "path_stress: %s", cudaGetErrorString(err));
+    double total = 0;
+    unsigned long long n = 0;
+    for (int t = 0; t < STRESS_STREAMS; ++t) { total += acc[t]; n += used[t]; }
+    *stress_out = n ? total / (double) n : 0.0;
     return PGSGD_OK;
 }
 

@@ -15,6 +15,8 @@
 
 #include <cstdio>
 
+#include <cub/device/device_scan.cuh>
+
 namespace pgsgd {
 
 namespace {
@@ -472,6 +474,31 @@ __global__ void pack_steps_kernel(StepRec* out, const uint32_t* step_node, const
     out[out_offset + i] = r;
 }
 
+// flatten-to-device, positions derived on the GPU: len[i] = node_len[step_node[i]] (+ id validation), one device-wide
+// exclusive scan, then pos[i] = scan[i] - scan[first step of i's path] (== XP positions, xp.cpp:607-616)
+__global__ void gather_len_kernel(uint64_t* len, const uint32_t* step_node, const uint32_t* node_len, uint64_t n, uint32_t n_nodes, int* bad) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t node = step_node[i];
+    if (node >= n_nodes) { atomicExch(bad, 1); len[i] = 0; return; }
+    len[i] = node_len[node];
+}
+
+__global__ void pack_steps_scan_kernel(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* scan,
+                                       const uint32_t* node_len, const uint64_t* first, uint32_t P, uint64_t n) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t node = step_node[i];
+    const uint32_t p = find_path(first, P, i);
+    const uint64_t pos = scan[i] - scan[first[p]];
+    StepRec r;
+    r.handle = (node << 1) | (step_rev ? (uint32_t) (step_rev[i] != 0) : 0u);
+    r.len = node_len[node];
+    r.pos_lo = (uint32_t) pos;
+    r.pos_hi = (uint32_t) (pos >> 32);
+    out[i] = r;
+}
+
 __global__ void xy_from_XY_kernel(float4* xy, const double* X, const double* Y, uint64_t n) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -532,6 +559,51 @@ __global__ void sample_terms_kernel(SamplerParams sp, const StepRec* steps, uint
         if (out.end_b) out.end_b[k] = (uint8_t) end_b;
         if (out.valid) out.valid[k] = (uint8_t) t.valid;
     }
+}
+
+// Sampled path stress of the resident coordinates (definition: SURVEY.md §8d, oracle/pgsgd_oracle.c orc_path_stress_*):
+// STRESS_STREAMS generators (stream t seeded seed + t) draw `per` pairs each — step uniform over all steps, partner
+// uniform in the same path, ends uniform (2D) — and accumulate ((|p_a - p_b| - d) / d)^2 in fp64 with IEEE operations, so
+// the per-stream sums are bit-identical to the oracle's; the host adds them in stream order.
+template <int DIMS>
+__global__ void stress_kernel(const uint64_t* first, uint32_t P, uint64_t S, const StepRec* steps, const float* xy, const double* x1d,
+                              uint64_t per, uint64_t seed, double* acc_out, unsigned long long* used_out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= STRESS_STREAMS) return;
+    Xoshiro g;
+    xoshiro_seed(g, seed + t);
+    double acc = 0.0;
+    unsigned long long used = 0;
+    for (uint64_t k = 0; k < per; ++k) {
+        const uint64_t ia = draw_uniform(g, S);
+        const uint32_t p = find_path(first, P, ia);
+        const uint64_t f = first[p], cnt = first[p + 1] - f;
+        const uint64_t ib = f + draw_uniform(g, cnt);
+        const uint4 ra = load_step(steps, ia), rb = load_step(steps, ib);
+        uint64_t pa = step_pos(ra), pb = step_pos(rb);
+        if (DIMS == 2) {
+            const uint32_t fa = draw_flip(g), fb = draw_flip(g);
+            uint32_t ea = ra.x & 1u, eb = rb.x & 1u;
+            if (fa) { pa += ra.y; ea ^= 1u; }
+            if (fb) { pb += rb.y; eb ^= 1u; }
+            if (pa == pb) continue;
+            const double d = fabs(__dsub_rn(__ull2double_rn(pa), __ull2double_rn(pb)));
+            const float2 ca = __ldcg(reinterpret_cast<const float2*>(xy) + ((uint64_t) (ra.x >> 1) * 2 + ea));
+            const float2 cb = __ldcg(reinterpret_cast<const float2*>(xy) + ((uint64_t) (rb.x >> 1) * 2 + eb));
+            const double dx = __dsub_rn((double) ca.x, (double) cb.x), dy = __dsub_rn((double) ca.y, (double) cb.y);
+            const double e = __ddiv_rn(__dsub_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))), d), d);
+            acc = __dadd_rn(acc, __dmul_rn(e, e));
+        } else {
+            if (pa == pb) continue;
+            const double d = fabs(__dsub_rn(__ull2double_rn(pa), __ull2double_rn(pb)));
+            const double xa = __ldcg(x1d + (ra.x >> 1)), xb = __ldcg(x1d + (rb.x >> 1));
+            const double e = __ddiv_rn(__dsub_rn(fabs(__dsub_rn(xa, xb)), d), d);
+            acc = __dadd_rn(acc, __dmul_rn(e, e));
+        }
+        ++used;
+    }
+    acc_out[t] = acc;
+    used_out[t] = used;
 }
 
 template <int DIMS, int BATCH>
@@ -647,6 +719,29 @@ cudaError_t launch_pack_steps(StepRec* out, const uint32_t* step_node, const uin
     return cudaGetLastError();
 }
 
+cudaError_t launch_flatten_on_device(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint32_t* node_len,
+                                     const uint64_t* first, uint32_t P, uint32_t n_nodes, uint64_t n, uint64_t* scratch_len, int* bad,
+                                     cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    gather_len_kernel<<<grid_for(n, 256), 256, 0, stream>>>(scratch_len, step_node, node_len, n, n_nodes, bad);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, scratch_len, scratch_len, n, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, scratch_len, scratch_len, n, stream);
+    if (e == cudaSuccess) {
+        pack_steps_scan_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, step_node, step_rev, scratch_len, node_len, first, P, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(tmp);
+    return e;
+}
+
 cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n, cudaStream_t stream) {
     if (!n) return cudaSuccess;
     xy_from_XY_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<float4*>(xy), X, Y, n);
@@ -685,6 +780,14 @@ cudaError_t launch_sub_f64(double* out, const double* a, const double* b, uint64
 cudaError_t launch_add_f64(double* out, const double* a, const double* b, uint64_t n, cudaStream_t stream) {
     if (!n) return cudaSuccess;
     addsub_kernel<double, 1><<<grid_for(n, 256), 256, 0, stream>>>(out, a, b, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stress(int dims, const uint64_t* first, uint32_t P, uint64_t S, const StepRec* steps, const float* xy,
+                          const double* x1d, uint64_t per, uint64_t seed, double* acc_out, unsigned long long* used_out, cudaStream_t stream) {
+    if (dims == 2) stress_kernel<2><<<STRESS_STREAMS / 128, 128, 0, stream>>>(first, P, S, steps, xy, x1d, per, seed, acc_out, used_out);
+    else if (dims == 1) stress_kernel<1><<<STRESS_STREAMS / 128, 128, 0, stream>>>(first, P, S, steps, xy, x1d, per, seed, acc_out, used_out);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 

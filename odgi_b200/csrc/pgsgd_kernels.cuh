@@ -44,6 +44,7 @@ struct IterParams {
     uint64_t trace_cap;
 };
 
+constexpr int STRESS_STREAMS = 4096;   // generators of the sampled path stress (== ORC_STRESS_STREAMS of the oracle)
 constexpr int TILE_STEPS = 2048;   // steps staged in shared memory per tile visit (32 KB of 16-byte records)
 
 struct LaunchShape {
@@ -67,6 +68,12 @@ cudaError_t iteration_occupancy(int dims, int batch, int block, size_t smem, boo
 cudaError_t launch_pack_steps(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* step_pos,
                               const uint32_t* node_len, uint64_t n, uint64_t out_offset, cudaStream_t stream);
 
+// the same with the positions derived on the device (device-wide scan of node lengths); *bad is set to 1 when a step refers
+// to a node rank >= n_nodes
+cudaError_t launch_flatten_on_device(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint32_t* node_len,
+                                     const uint64_t* first, uint32_t P, uint32_t n_nodes, uint64_t n, uint64_t* scratch_len, int* bad,
+                                     cudaStream_t stream);
+
 // coordinate format conversion: reference X/Y (double, index 2*node+end) <-> device float4-per-node
 cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n_nodes, cudaStream_t stream);
 cudaError_t launch_XY_from_xy(double* X, double* Y, const float* xy, uint64_t n_nodes, cudaStream_t stream);
@@ -78,6 +85,10 @@ cudaError_t launch_sub_f32(float* out, const float* a, const float* b, uint64_t 
 cudaError_t launch_add_f32(float* out, const float* a, const float* b, uint64_t n, cudaStream_t stream);   // out = a + b
 cudaError_t launch_sub_f64(double* out, const double* a, const double* b, uint64_t n, cudaStream_t stream);
 cudaError_t launch_add_f64(double* out, const double* a, const double* b, uint64_t n, cudaStream_t stream);
+
+// sampled path stress: per-stream partial sums (STRESS_STREAMS entries each), `per` pairs per stream
+cudaError_t launch_stress(int dims, const uint64_t* first, uint32_t P, uint64_t S, const StepRec* steps, const float* xy,
+                          const double* x1d, uint64_t per, uint64_t seed, double* acc_out, unsigned long long* used_out, cudaStream_t stream);
 
 // verification hook: first n_terms draws of one stream, produced by the same device sampler
 struct SampleOut {

@@ -454,49 +454,63 @@ uint64_t orc_replay_single(const orc_graph* g, const orc_config* c, int dims, ui
  * sampled path stress (our definition)
  * ---------------------------------------------------------------------------------------------- */
 
+/* The K pairs are drawn by ORC_STRESS_STREAMS independent generators (stream t seeded seed + t, ceil(K / streams)
+ * pairs each) so that a GPU can evaluate the same definition with one thread per stream. */
+#define ORC_STRESS_STREAMS 4096
+
 double orc_path_stress_2d(const orc_graph* g, const double* X, const double* Y, uint64_t n_pairs, uint64_t seed) {
-    orc_rng rng;
-    orc_rng_seed(&rng, seed);
+    const uint64_t per = (n_pairs + ORC_STRESS_STREAMS - 1) / ORC_STRESS_STREAMS;
     double acc = 0;
     uint64_t used = 0;
-    for (uint64_t k = 0; k < n_pairs; ++k) {
-        uint64_t ia = orc_uniform(&rng, g->step_count);
-        uint64_t p = find_path(g, ia);
-        uint64_t first = g->path_first_step[p], cnt = g->path_first_step[p + 1] - first;
-        uint64_t ib = first + orc_uniform(&rng, cnt);
-        uint64_t fa = orc_uniform(&rng, 2), fb = orc_uniform(&rng, 2);
-        uint32_t na = g->step_node[ia], nb = g->step_node[ib];
-        uint64_t pa = g->step_pos[ia] + (fa ? g->node_len[na] : 0);
-        uint64_t pb = g->step_pos[ib] + (fb ? g->node_len[nb] : 0);
-        uint64_t ea = fa ? !g->step_rev[ia] : g->step_rev[ia];
-        uint64_t eb = fb ? !g->step_rev[ib] : g->step_rev[ib];
-        if (pa == pb) continue;
-        double d = fabs((double) pa - (double) pb);
-        double dx = X[2 * (uint64_t) na + ea] - X[2 * (uint64_t) nb + eb];
-        double dy = Y[2 * (uint64_t) na + ea] - Y[2 * (uint64_t) nb + eb];
-        double e = (sqrt(dx * dx + dy * dy) - d) / d;
-        acc += e * e;
-        ++used;
+    for (uint64_t t = 0; t < ORC_STRESS_STREAMS; ++t) {
+        orc_rng rng;
+        orc_rng_seed(&rng, seed + t);
+        double a = 0;
+        for (uint64_t k = 0; k < per; ++k) {
+            uint64_t ia = orc_uniform(&rng, g->step_count);
+            uint64_t p = find_path(g, ia);
+            uint64_t first = g->path_first_step[p], cnt = g->path_first_step[p + 1] - first;
+            uint64_t ib = first + orc_uniform(&rng, cnt);
+            uint64_t fa = orc_uniform(&rng, 2), fb = orc_uniform(&rng, 2);
+            uint32_t na = g->step_node[ia], nb = g->step_node[ib];
+            uint64_t pa = g->step_pos[ia] + (fa ? g->node_len[na] : 0);
+            uint64_t pb = g->step_pos[ib] + (fb ? g->node_len[nb] : 0);
+            uint64_t ea = fa ? !g->step_rev[ia] : g->step_rev[ia];
+            uint64_t eb = fb ? !g->step_rev[ib] : g->step_rev[ib];
+            if (pa == pb) continue;
+            double d = fabs((double) pa - (double) pb);
+            double dx = X[2 * (uint64_t) na + ea] - X[2 * (uint64_t) nb + eb];
+            double dy = Y[2 * (uint64_t) na + ea] - Y[2 * (uint64_t) nb + eb];
+            double e = (sqrt(dx * dx + dy * dy) - d) / d;
+            a += e * e;
+            ++used;
+        }
+        acc += a;
     }
     return used ? acc / (double) used : 0.0;
 }
 
 double orc_path_stress_1d(const orc_graph* g, const double* X, uint64_t n_pairs, uint64_t seed) {
-    orc_rng rng;
-    orc_rng_seed(&rng, seed);
+    const uint64_t per = (n_pairs + ORC_STRESS_STREAMS - 1) / ORC_STRESS_STREAMS;
     double acc = 0;
     uint64_t used = 0;
-    for (uint64_t k = 0; k < n_pairs; ++k) {
-        uint64_t ia = orc_uniform(&rng, g->step_count);
-        uint64_t p = find_path(g, ia);
-        uint64_t first = g->path_first_step[p], cnt = g->path_first_step[p + 1] - first;
-        uint64_t ib = first + orc_uniform(&rng, cnt);
-        uint64_t pa = g->step_pos[ia], pb = g->step_pos[ib];
-        if (pa == pb) continue;
-        double d = fabs((double) pa - (double) pb);
-        double e = (fabs(X[g->step_node[ia]] - X[g->step_node[ib]]) - d) / d;
-        acc += e * e;
-        ++used;
+    for (uint64_t t = 0; t < ORC_STRESS_STREAMS; ++t) {
+        orc_rng rng;
+        orc_rng_seed(&rng, seed + t);
+        double a = 0;
+        for (uint64_t k = 0; k < per; ++k) {
+            uint64_t ia = orc_uniform(&rng, g->step_count);
+            uint64_t p = find_path(g, ia);
+            uint64_t first = g->path_first_step[p], cnt = g->path_first_step[p + 1] - first;
+            uint64_t ib = first + orc_uniform(&rng, cnt);
+            uint64_t pa = g->step_pos[ia], pb = g->step_pos[ib];
+            if (pa == pb) continue;
+            double d = fabs((double) pa - (double) pb);
+            double e = (fabs(X[g->step_node[ia]] - X[g->step_node[ib]]) - d) / d;
+            a += e * e;
+            ++used;
+        }
+        acc += a;
     }
     return used ? acc / (double) used : 0.0;
 }

@@ -301,3 +301,46 @@ def test_tile_sampler_law_matches_reference_law(graphs, name, dims, cooling):
     assert abs(back_dev - back_ref) < 0.01
     if dims == 2:
         assert abs(np.mean(fl & 1) - 0.5) < 0.01 and abs(np.mean(fl >> 1) - 0.5) < 0.01
+
+
+def test_device_stress_equals_oracle_stress(graphs):
+    """pgsgd_engine_path_stress evaluates the oracle's definition with the same 4096 generators: identical pair sets,
+    IEEE fp64 arithmetic — equal up to the order of the final 4096-term sum (here: bit-identical)."""
+    gd, go = graphs["chr6.C4"]
+    X0, Y0 = orc.layout_init(go, 5)
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_2d(X0, Y0)
+        s_dev0 = e.path_stress(2, 300_000, 99)
+        e.run_2d(capi.layout_defaults(gd, iter_max=6))
+        X, Y = e.get_coords_2d()
+        s_dev = e.path_stress(2, 300_000, 99)
+    assert s_dev0 == orc.path_stress_2d(go, X0.astype(np.float32), Y0.astype(np.float32), 300_000, 99)
+    assert s_dev == orc.path_stress_2d(go, X, Y, 300_000, 99)
+    gd, go = graphs["LPA"]
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_1d(None)
+        e.run_1d(capi.sort_defaults(gd, iter_max=5))
+        x = e.get_coords_1d()
+        s1 = e.path_stress(1, 200_000, 7)
+    assert s1 == orc.path_stress_1d(go, x, 200_000, 7)
+
+
+def test_device_derived_positions_and_id_validation(golden_graphs):
+    """Without caller-supplied step_pos the engine derives the positions on the device (scan of node lengths): the
+    sampler must still produce XP's positions bit for bit; a step pointing past the node table is rejected like the
+    reference rejects non-compacted ids (layout.cu:320-323)."""
+    a = golden_graphs["chr6.C4"]
+    gd = odgi_b200.FlatGraph(a["node_len"], a["path_first_step"], a["step_node"], a["step_rev"], None)
+    go = orc.Graph.from_arrays(a)
+    cd, co = capi.layout_defaults(gd), orc.default_layout_config(go)
+    with odgi_b200.Engine(gd) as e:
+        dev = e.sample_terms(cd, 2, True, 20000, stream=3)
+    ref, valid = orc.sample_terms(go, co, 2, True, 20000, stream=3)
+    ok = valid.astype(bool)
+    for f in ("pos_a", "pos_b", "node_a", "node_b", "rank_a", "rank_b"):
+        assert np.array_equal(dev[f][ok], ref[f][ok].astype(dev[f].dtype)), f
+    bad = a["step_node"].copy()
+    bad[1234] = a["node_len"].size + 5
+    with pytest.raises(odgi_b200.PgsgdError) as ei:
+        odgi_b200.Engine(odgi_b200.FlatGraph(a["node_len"], a["path_first_step"], bad, a["step_rev"], None))
+    assert ei.value.code == -6
