@@ -70,8 +70,9 @@ typedef struct pgsgd_config {
     double   cooling_start;                /* first cooling iteration = floor(cooling_start * iter_max) */
     uint64_t seed;                         /* worker stream t is seeded seed + t; reference: 9399220 (path_sgd_layout.cpp:168) */
     uint32_t n_streams;                    /* device worker streams (one per GPU thread); 0 = automatic: fill the GPU, but keep
-                                              the terms in flight (n_streams * batch) below node_count / 4 — beyond that
-                                              Hogwild staleness measurably worsens the layout of small graphs */
+                                              the terms in flight (n_streams * batch) below node_count / 2 (/ 4 with the
+                                              racy write flavours) — beyond that Hogwild staleness measurably worsens the
+                                              layout of small graphs */
     uint32_t batch;                        /* terms a stream keeps in flight (1, 2 or 4); 0 = default (1).
                                               batch 1 applies a stream's terms strictly in order */
     uint32_t flags;                        /* PGSGD_FLAG_* */

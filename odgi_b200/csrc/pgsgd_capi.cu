@@ -371,6 +371,8 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     if (peer && !(dims == 2 ? e->peer_ready_2d : e->peer_ready_1d)) return fail(PGSGD_ERR_STATE, "peer mode: coordinates were not set after the mode was selected");
     // in peer mode all ranks update ONE coordinate array: the Hogwild in-flight cap is shared by the ranks
     const uint64_t cap_div = peer ? (uint64_t) e->n_ranks : 1;
+    // terms in flight <= N/2 with the lossless red.add write (stress parity measured up to ~2N), N/4 with the racy writes
+    const uint64_t cap_frac = (cfg->flags & (PGSGD_FLAG_EXCH_WRITE | PGSGD_FLAG_PLAIN_STORE)) ? 4 : 2;
 
     // ---- sampling mode and launch shape ----
     const int block = 256;
@@ -392,7 +394,7 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         uint64_t grid = (uint64_t) e->sm_count * blocks_per_sm;
         if (cfg->n_streams) grid = (cfg->n_streams + block - 1) / block;
         // Hogwild staleness cap (see below): terms in flight = grid * block * batch
-        const uint64_t cap_grid = (e->N / 4) / ((uint64_t) block * batch * cap_div);
+        const uint64_t cap_grid = (e->N / cap_frac) / ((uint64_t) block * batch * cap_div);
         if (!cfg->n_streams && grid > cap_grid) grid = cap_grid;
         if (grid == 0) {
             if (cfg->sampling == PGSGD_SAMPLING_TILE) grid = 1; else tile_mode = false;
@@ -413,7 +415,7 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
             n_streams = (uint64_t) e->sm_count * blocks_per_sm * block;
             // Hogwild staleness: with more than ~N/4 terms in flight the final stress of small graphs drifts away from the
             // reference's (measured: profiles/r01_stream_sweep.md); large graphs are not affected by this cap
-            uint64_t cap = (e->N / 4) / (batch * cap_div);
+            uint64_t cap = (e->N / cap_frac) / (batch * cap_div);
             if (cap < 32) cap = 32;
             if (n_streams > cap) n_streams = cap;
             // keep at least ~64 terms per stream so the launch is not all prologue
