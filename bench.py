@@ -167,6 +167,10 @@ def run_reference_arm(args):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: anything libraries print there (NCCL's version banner, ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
@@ -346,7 +350,7 @@ def main():
         line["e2e"] = e2e
     if cb:
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
