@@ -163,7 +163,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": cb["value"], "unit": cb["unit"], "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
             "e2e": {"value": cb["value"], "unit": "M updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():

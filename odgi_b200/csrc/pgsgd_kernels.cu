@@ -3,14 +3,16 @@
 // Replaces: cuda::gpu_layout_kernel / update_pos_gpu / cuda_rnd_zipf (src/cuda/layout.cu:89-287) and the CPU
 // worker lambdas (src/algorithms/path_sgd_layout.cpp:165-377, src/algorithms/path_sgd.cpp:205-406).
 //
-// Shape of one iteration kernel (one launch per cooling-schedule step):
-//   * persistent grid: a multiple of the SM count, every thread is one reference-style worker stream with its
-//     own register-resident Xoshiro256+ state (loaded/stored once per launch, SoA, coalesced);
-//   * the per-path step offsets live in shared memory (binary search, no global traffic for step -> path);
-//   * every term costs two random 16-byte step-record loads (HBM) and two 8-byte coordinate loads + two 8-byte
-//     coordinate stores (L2-resident for graphs up to ~7M nodes); BATCH independent terms are drawn first and
-//     all their loads issued together, so each thread keeps 2*BATCH HBM requests in flight;
-//   * no tensor cores: the path is integer/byte gather-scatter bound by HBM sector rate and L2.
+// Two iteration kernels, one launch per cooling-schedule step:
+//   pgsgd_iter_kernel  "stream sampling": a persistent grid in which every thread is one reference-style worker stream
+//       (register-resident Xoshiro256+, bit-identical draws to a CPU worker thread); two random 16-byte step-record
+//       loads, two 8-byte coordinate loads and two 8-byte coordinate reds per term.
+//   pgsgd_tile_kernel  "tile sampling": a CTA stages 2048 consecutive step records in shared memory with coalesced
+//       128-bit loads and uses each once as a term's first step; partners inside the tile come from shared memory.
+// Both: per-path step offsets in shared memory (binary search), L2::evict_first on the step stream and L2::evict_last
+// on the coordinates, red.global.add coordinate writes by default.  No tensor cores: the path is an integer/byte
+// gather-scatter bound by the random-sector rate of HBM, L2 tag lookups and instruction issue (profiles/).
+// Also here: flatten-to-device (record packing, scan-derived positions), the sampled path stress, helpers.
 #include "pgsgd_kernels.cuh"
 
 #include <cstdio>

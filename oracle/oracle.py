@@ -87,6 +87,8 @@ def lib():
         L.orc_run_range.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_run_range.restype = C.c_uint64
+        L.orc_peer_stale_2d_f32.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.orc_peer_stale_2d_f32.restype = C.c_uint64
         L.orc_replay_single.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_int, C.c_uint64, C.c_uint64, C.c_double,
                                         C.c_double, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_replay_single.restype = C.c_uint64
@@ -313,6 +315,11 @@ def emulate_multirank_2d_f32(g: Graph, cfg: Config, xy0, n_ranks: int, n_streams
             for r in range(n_ranks):
                 reps[r][...] = merged
     return reps[0]
+
+
+def peer_stale_2d_f32(g: Graph, cfg: Config, xy, n_ranks: int, streams_per_rank: int, refreshes: int, iter_begin: int, iter_end: int) -> int:
+    gc, cc = g.c(), cfg.c()
+    return int(lib().orc_peer_stale_2d_f32(C.byref(gc), C.byref(cc), n_ranks, streams_per_rank, refreshes, iter_begin, iter_end, _ptr(xy)))
 
 
 def replay_single(g: Graph, cfg: Config, dims: int, n_terms: int, switch_at: int, eta0: float, eta1: float,

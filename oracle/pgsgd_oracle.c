@@ -420,6 +420,62 @@ uint64_t orc_sort_1d(const orc_graph* g, const orc_config* c, uint64_t n_streams
     return run_streams(g, c, n_streams, 2, X, NULL, NULL, frozen);
 }
 
+/* Emulation of the multi-GPU "peer" schedule with STALE REMOTE READS: the coordinate array is partitioned by node range
+ * over n_ranks owners; every update is applied to the one true array (as the NVLink red.add does), but a rank reads the
+ * coordinates of nodes it does not own from a snapshot that is refreshed `refreshes` times per iteration.  Rank r only
+ * draws terms whose first node it owns (tile ownership).  2D fp32 model; iterations [iter_begin, iter_end). */
+uint64_t orc_peer_stale_2d_f32(const orc_graph* g, const orc_config* c, uint64_t n_ranks, uint64_t streams_per_rank, uint64_t refreshes,
+                               uint64_t iter_begin, uint64_t iter_end, float* xy) {
+    run_tables rt;
+    tables_init(&rt, c);
+    const uint64_t N = g->node_count, chunk = (N + n_ranks - 1) / n_ranks, T = n_ranks * streams_per_rank;
+    orc_rng* rngs = (orc_rng*) malloc(sizeof(orc_rng) * T);
+    for (uint64_t t = 0; t < T; ++t) orc_rng_seed(&rngs[t], c->seed + 0x51ED27 * (iter_begin + 1) + t);
+    float* snap = (float*) malloc(sizeof(float) * 4 * N);
+    uint64_t counted = 0;
+    uint64_t n_iters = c->iter_max < iter_end ? c->iter_max : iter_end;
+    for (uint64_t iter = iter_begin; iter < n_iters; ++iter) {
+        const double eta = rt.etas[iter];
+        const int cooling = iter >= rt.first_cooling_iteration;
+        for (uint64_t k = 0; k < refreshes; ++k) {
+            memcpy(snap, xy, sizeof(float) * 4 * N);
+            const uint64_t slice = c->min_term_updates / refreshes;
+            uint64_t left = slice;
+            while (left) {
+                for (uint64_t t = 0; t < T && left; ++t) {
+                    const uint64_t r = t / streams_per_rank;
+                    orc_term term;
+                    if (!orc_sample_term(g, c, rt.zetas, 2, cooling, c->theta, &rngs[t], &term)) continue;
+                    uint64_t oa = term.node_a / chunk, ob = term.node_b / chunk;
+                    if (oa != r) continue;  /* not this rank's tile: redraw */
+                    /* the update as the device computes it: a from the true array (own), b from the true array when owned
+                     * else from the snapshot; displacement added to the true array for both */
+                    float* pa = xy + 4 * (uint64_t) term.node_a + 2 * (term.end_a ? 1 : 0);
+                    float* pb_true = xy + 4 * (uint64_t) term.node_b + 2 * (term.end_b ? 1 : 0);
+                    const float* pb_read = ob == r ? pb_true : snap + 4 * (uint64_t) term.node_b + 2 * (term.end_b ? 1 : 0);
+                    uint64_t dpos = term.pos_a > term.pos_b ? term.pos_a - term.pos_b : term.pos_b - term.pos_a;
+                    float d_ij = dpos ? (float) dpos : 1e-9f;
+                    float mu = (float) eta / d_ij;
+                    if (mu > 1.0f) mu = 1.0f;
+                    float dx = pa[0] - pb_read[0], dy = pa[1] - pb_read[1];
+                    if (dx == 0.0f) dx = 1e-9f;
+                    float mag = sqrtf(dx * dx + dy * dy);
+                    float Delta = mu * (mag - d_ij) * 0.5f;
+                    float rr = Delta / mag, r_x = rr * dx, r_y = rr * dy;
+                    pa[0] -= r_x; pa[1] -= r_y;
+                    pb_true[0] += r_x; pb_true[1] += r_y;
+                    ++counted;
+                    --left;
+                }
+            }
+        }
+    }
+    free(snap);
+    free(rngs);
+    tables_free(&rt);
+    return counted;
+}
+
 uint64_t orc_replay_single(const orc_graph* g, const orc_config* c, int dims, uint64_t n_terms, uint64_t switch_at,
                            double eta0, double eta1, int cooling0, int cooling1, double theta1,
                            double* X, double* Y, orc_term* out_terms) {

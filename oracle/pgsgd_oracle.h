@@ -115,6 +115,10 @@ uint64_t orc_run_range(const orc_graph* g, const orc_config* c, uint64_t n_strea
                        uint64_t iter_begin, uint64_t iter_end, int mode, double* X, double* Y, float* xy,
                        const uint8_t* frozen, uint64_t* rng_state);
 
+/* Emulation of the multi-GPU peer schedule with stale remote reads (see the .c file); experiments only. */
+uint64_t orc_peer_stale_2d_f32(const orc_graph* g, const orc_config* c, uint64_t n_ranks, uint64_t streams_per_rank, uint64_t refreshes,
+                               uint64_t iter_begin, uint64_t iter_end, float* xy);
+
 /* Replay helper for pinning: runs ONE stream (seed+0) for n_terms emitted terms with the cooling flag /
  * eta switching at emitted-term index switch_at (use n_terms for "never"), applying fp64 updates;
  * optionally records the terms.  This is what scripts/pin_oracle.py aligns with the reference trace. */

@@ -344,3 +344,94 @@ def test_device_derived_positions_and_id_validation(golden_graphs):
     with pytest.raises(odgi_b200.PgsgdError) as ei:
         odgi_b200.Engine(odgi_b200.FlatGraph(a["node_len"], a["path_first_step"], bad, a["step_rev"], None))
     assert ei.value.code == -6
+
+
+def test_many_paths_use_the_global_path_table():
+    """More paths than the shared-memory table holds (> 25 k): both kernels fall back to the global path_first table."""
+    rng = np.random.Generator(np.random.PCG64(3))
+    P, N = 30_000, 5_000
+    counts = rng.integers(1, 6, size=P)
+    first = np.zeros(P + 1, dtype=np.uint64)
+    np.cumsum(counts, out=first[1:])
+    S = int(first[-1])
+    node_len = rng.integers(1, 30, size=N).astype(np.uint32)
+    step_node = rng.integers(0, N, size=S).astype(np.uint32)
+    step_rev = rng.integers(0, 2, size=S).astype(np.uint8)
+    gd = odgi_b200.FlatGraph(node_len, first, step_node, step_rev)
+    go = orc.Graph(node_len, first, step_node, step_rev)
+    cd, co = capi.layout_defaults(gd), orc.default_layout_config(go)
+    with odgi_b200.Engine(gd) as e:
+        dev = e.sample_terms(cd, 2, False, 8000, stream=1)
+        ref, valid = orc.sample_terms(go, co, 2, False, 8000, stream=1)
+        assert np.array_equal(dev["valid"], valid)
+        ok = valid.astype(bool)
+        for f in INT_FIELDS:
+            assert np.array_equal(dev[f][ok], ref[f][ok].astype(dev[f].dtype)), f
+        X0, Y0 = orc.layout_init(go, 2)
+        s0 = orc.path_stress_2d(go, X0, Y0, 200000, 1)
+        for sampling in (capi.SAMPLING_STREAM, capi.SAMPLING_TILE):
+            e.set_coords_2d(X0, Y0)
+            st = e.run_2d(capi.layout_defaults(gd, iter_max=10, sampling=sampling))
+            X, Y = e.get_coords_2d()
+            assert np.all(np.isfinite(X)) and orc.path_stress_2d(go, X, Y, 200000, 1) < s0
+            multi = int(np.repeat(counts > 1, counts).sum())
+            if sampling == capi.SAMPLING_STREAM:
+                assert st["term_updates"] == 10 * 10 * S            # 1-step paths are redrawn until the quota is met
+            else:
+                assert st["term_updates"] == 10 * 10 * multi        # tile sampling skips them (never counted)
+
+
+def test_positions_beyond_32_bits():
+    """Path positions above 2^32 bp: the 64-bit position field of the step record and the integer distance."""
+    node_len = np.array([2_000_000_000, 1_900_000_000, 7, 2_100_000_000, 13, 1_500_000_000], dtype=np.uint32)
+    first = np.array([0, 6, 11], dtype=np.uint64)
+    step_node = np.array([0, 1, 2, 3, 4, 5, 5, 3, 1, 0, 2], dtype=np.uint32)
+    step_rev = np.array([0, 1, 0, 0, 1, 0, 1, 1, 0, 0, 1], dtype=np.uint8)
+    gd = odgi_b200.FlatGraph(node_len, first, step_node, step_rev)
+    go = orc.Graph(node_len, first, step_node, step_rev)
+    assert int(go.step_pos.max()) > 2 ** 32
+    cd, co = capi.layout_defaults(gd), orc.default_layout_config(go)
+    with odgi_b200.Engine(gd) as e:
+        for cooling in (False, True):
+            dev = e.sample_terms(cd, 2, cooling, 3000)
+            ref, valid = orc.sample_terms(go, co, 2, cooling, 3000)
+            ok = valid.astype(bool)
+            for f in INT_FIELDS:
+                assert np.array_equal(dev[f][ok], ref[f][ok].astype(dev[f].dtype)), f
+    # single stream, strict order: arithmetic identical to the oracle's fp32 model at these magnitudes too
+    kw = dict(iter_max=3, min_term_updates=500)
+    cd, co = capi.layout_defaults(gd, n_streams=1, batch=1, sampling=capi.SAMPLING_STREAM, **kw), orc.default_layout_config(go, **kw)
+    X0, Y0 = orc.layout_init(go, 1)
+    X, Y, _ = odgi_b200.layout_2d(gd, cd, X0, Y0)
+    _, xy = orc.layout_2d_f32(go, co, orc.XY_to_xy(X0, Y0), n_streams=1)
+    Xr, Yr = orc.xy_to_XY(xy)
+    assert np.array_equal(X, Xr) and np.array_equal(Y, Yr)
+
+
+def test_scale_properties_on_a_graph_beyond_l2():
+    """Size-independent properties at a size the oracle cannot run in seconds (6e5 nodes, 4.6e7 steps, 0.7 GB of step
+    records): exact update counts, finite coordinates, the annealing half lowering the stress far below the initial
+    one, tile and stream sampling converging to the same stress, device stress == oracle stress on the downloaded
+    coordinates."""
+    from odgi_b200 import synth
+    gd = synth.preset("mid")
+    go = orc.Graph(gd.node_len, gd.path_first_step, gd.step_node, gd.step_rev)
+    X0, Y0 = odgi_b200.layout_init(gd, 42)
+    finals = {}
+    with odgi_b200.Engine(gd) as e:
+        for sampling in (capi.SAMPLING_TILE, capi.SAMPLING_STREAM):
+            cd = capi.layout_defaults(gd, sampling=sampling)
+            e.set_coords_2d(X0, Y0)
+            s_init = e.path_stress(2, 1_000_000, 3)
+            mids = []
+            for a, b in ((0, 15), (15, 22), (22, 30)):
+                st = e.run_range(cd, 2, a, b)
+                assert st["term_updates"] == (b - a) * 10 * gd.S and st["kernel_launches"] == b - a
+                mids.append(e.path_stress(2, 1_000_000, 3))
+            # the first half runs at learning rates that saturate every update; the annealing half must converge
+            assert mids[2] < mids[1] and mids[2] < 0.05 * s_init, (s_init, mids)
+            finals[sampling] = mids[2]
+        X, Y = e.get_coords_2d()
+    assert np.all(np.isfinite(X)) and np.all(np.isfinite(Y))
+    assert finals[capi.SAMPLING_STREAM] == orc.path_stress_2d(go, X, Y, 1_000_000, 3)
+    assert abs(finals[capi.SAMPLING_TILE] - finals[capi.SAMPLING_STREAM]) <= 0.05 * finals[capi.SAMPLING_STREAM], finals
