@@ -99,6 +99,8 @@ typedef struct pgsgd_config {
  * The other two reproduce the reference's racy last-writer-wins write (path_sgd_layout.cpp:360-363, layout.cu:184-187). */
 #define PGSGD_FLAG_EXCH_WRITE   1u  /* 64-bit atom.exch of the new (x,y) — the reference CUDA kernel's atomicExch semantics */
 #define PGSGD_FLAG_PLAIN_STORE  4u  /* st.global of the new (x,y) (slower on B200: 14 vs 21 G updates/s, profiles/) */
+#define PGSGD_FLAG_TMA_STAGING  8u  /* tile kernel: stage tiles with double-buffered TMA bulk copies (cp.async.bulk + mbarrier) instead of
+                                       coalesced LDG/STS into one buffer; measured slower on B200, kept for comparison */
 #define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
 
 typedef struct pgsgd_stats {

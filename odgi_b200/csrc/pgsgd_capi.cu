@@ -386,10 +386,11 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     uint64_t n_streams = 0;
     LaunchShape shape;
     if (tile_mode) {
-        const size_t tile_bytes = (size_t) TILE_STEPS * sizeof(StepRec);
+        const bool tma = (cfg->flags & PGSGD_FLAG_TMA_STAGING) != 0;
+        const size_t tile_bytes = (tma ? 2 : 1) * (size_t) TILE_STEPS * sizeof(StepRec);  // TMA staging is double-buffered
         smem_paths = tile_bytes + smem_first <= 200 * 1024;
         smem = tile_bytes + (smem_paths ? smem_first : 0);
-        CU(tile_occupancy(dims, batch, smem, smem_paths, &blocks_per_sm));
+        CU(tile_occupancy(dims, batch, smem, smem_paths, tma, &blocks_per_sm));
         if (blocks_per_sm < 1) return fail(PGSGD_ERR_CUDA, "tile kernel does not fit on an SM (smem %zu)", smem);
         uint64_t grid = (uint64_t) e->sm_count * blocks_per_sm;
         if (cfg->n_streams) grid = (cfg->n_streams + block - 1) / block;

@@ -255,22 +255,34 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
 // with the sampling noise of the first pick removed; the conditional law of the partner is unchanged.
 // Consecutive lanes hold consecutive steps, so their coordinate reads/reds of the first node coalesce as well.
 // --------------------------------------------------------------------------------------------------
-template <int DIMS, int BATCH, bool SMEM_PATHS>
+template <int DIMS, int BATCH, bool SMEM_PATHS, bool TMA>
 __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(const __grid_constant__ IterParams p) {
     constexpr int ROUNDS = TILE_STEPS / 256;
     static_assert(ROUNDS % BATCH == 0, "tile rounds must be a multiple of the batch");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long block_counted;
-    uint4* const tile = reinterpret_cast<uint4*>(smem_raw);
+    __shared__ __align__(8) uint64_t tile_bar[2];
+    // Staging flavours (PGSGD_FLAG_TMA_STAGING): TMA = two tile buffers, the TMA engine (cp.async.bulk) fills one while the
+    // CTA works on the other; default = one buffer filled with coalesced 128-bit LDG + STS.  Measured on B200 the second is
+    // faster (c4: 33-39 vs 29-36 G updates/s): the doubled shared-memory footprint costs more occupancy / L1 than the
+    // exposed ~2 us of tile latency per 2048 terms, which the other resident CTAs already hide.
+    uint4* const tile_buf0 = reinterpret_cast<uint4*>(smem_raw);
+    uint4* const tile_buf1 = tile_buf0 + TILE_STEPS;
     const uint64_t* first;
     if (SMEM_PATHS) {
-        uint64_t* sfirst = reinterpret_cast<uint64_t*>(smem_raw + (size_t) TILE_STEPS * sizeof(uint4));
+        uint64_t* sfirst = reinterpret_cast<uint64_t*>(smem_raw + (TMA ? 2 : 1) * (size_t) TILE_STEPS * sizeof(uint4));
         for (uint32_t i = threadIdx.x; i <= p.sp.path_count; i += blockDim.x) sfirst[i] = p.sp.path_first[i];
         first = sfirst;
     } else {
         first = p.sp.path_first;
     }
-    if (threadIdx.x == 0) block_counted = 0;
+    if (threadIdx.x == 0) {
+        block_counted = 0;
+        mbar_init(&tile_bar[0], 1);
+        mbar_init(&tile_bar[1], 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
 
     const uint64_t tid = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     Xoshiro g;
@@ -287,26 +299,49 @@ __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(con
     float delta_max = 0.0f;
 
     // visits of this rank: v = visit_rank + k * visit_nranks; CTA c takes k = c, c + gridDim.x, ...
-    for (uint64_t k = blockIdx.x;; k += gridDim.x) {
-        const uint64_t v = (uint64_t) p.visit_rank + k * p.visit_nranks;
-        if (v >= p.n_visits) break;
+    auto tile_base_of = [&](uint64_t v) -> uint64_t {
         const uint64_t pass = v / p.n_tiles, i = v - pass * p.n_tiles;
         uint64_t t_idx = (i * p.perm_mul[pass & 15] + p.perm_add[pass & 15]) % p.n_tiles;
         if (p.tile_list) t_idx = p.tile_list[t_idx];  // peer mode: the k-th tile this rank owns
-        const uint64_t base = t_idx * (uint64_t) TILE_STEPS;
+        return t_idx * (uint64_t) TILE_STEPS;
+    };
+    auto issue_tile = [&](uint64_t v, uint32_t buf) {   // one elected thread: TMA bulk copy of the tile's step records
+        const uint64_t b0 = tile_base_of(v);
+        const uint64_t n = b0 + TILE_STEPS <= p.sp.step_count ? (uint64_t) TILE_STEPS : p.sp.step_count - b0;
+        const uint32_t bytes = (uint32_t) (n * sizeof(uint4));
+        mbar_expect_tx(&tile_bar[buf], bytes);
+        tma_load_1d(buf ? tile_buf1 : tile_buf0, p.steps + b0, bytes, &tile_bar[buf], pol_stream);
+    };
+    const uint64_t v0 = (uint64_t) p.visit_rank + (uint64_t) blockIdx.x * p.visit_nranks;
+    const uint64_t v_stride = (uint64_t) gridDim.x * p.visit_nranks;
+    if (TMA && threadIdx.x == 0 && v0 < p.n_visits) issue_tile(v0, 0);
+    uint32_t it = 0;
+    for (uint64_t v = v0; v < p.n_visits; v += v_stride, ++it) {
+        const uint32_t buf = TMA ? (it & 1u) : 0u;
+        uint4* const tile = buf ? tile_buf1 : tile_buf0;
+        const uint64_t base = tile_base_of(v);
         const uint32_t terms = v + 1 == p.n_visits ? (uint32_t) p.last_visit_terms : (uint32_t) TILE_STEPS;
+        // TMA: prefetch the next visit's tile into the other buffer (its readers finished at the barrier ending the last visit)
+        if (TMA && threadIdx.x == 0 && v + v_stride < p.n_visits) {
+            fence_proxy_async();
+            issue_tile(v + v_stride, buf ^ 1u);
+        }
         // path of the tile's first and last step (one search each per visit instead of one per term)
         const uint64_t last_step = (base + TILE_STEPS <= p.sp.step_count ? base + TILE_STEPS : p.sp.step_count) - 1;
         const uint32_t p_lo = find_path(first, p.sp.path_count, base);
         const bool tile_one_path = first[p_lo + 1] > last_step;
         const uint64_t tile_f = first[p_lo], tile_count = first[p_lo + 1] - tile_f;
-        __syncthreads();  // the previous visit's readers are done with the tile
+        if (TMA) {
+            mbar_wait(&tile_bar[buf], (it >> 1) & 1u);   // this visit's tile has landed
+        } else {
+            __syncthreads();  // the previous visit's readers are done with the tile
 #pragma unroll
-        for (int r = 0; r < ROUNDS; ++r) {
-            const uint32_t j = r * 256 + threadIdx.x;
-            if (base + j < p.sp.step_count) tile[j] = load_step(p.steps, base + j, pol_stream);
+            for (int r = 0; r < ROUNDS; ++r) {
+                const uint32_t j = r * 256 + threadIdx.x;
+                if (base + j < p.sp.step_count) tile[j] = load_step(p.steps, base + j, pol_stream);
+            }
+            __syncthreads();
         }
-        __syncthreads();
 #pragma unroll 1
         for (int r0 = 0; r0 < ROUNDS; r0 += BATCH) {
             Term t[BATCH];
@@ -432,6 +467,7 @@ __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(con
                 }
             }
         }
+        if (TMA) __syncthreads();  // every reader is done with this buffer before the TMA engine may refill it
     }
     p.rng[tid] = g.s0;
     p.rng[p.rng_stride + tid] = g.s1;
@@ -640,37 +676,48 @@ inline unsigned grid_for(uint64_t n, int block) { return (unsigned) ((n + block 
 
 }  // namespace
 
-template <int DIMS, int BATCH, bool SP>
+template <int DIMS, int BATCH, bool SP, bool TMA>
 cudaError_t tile_launch_one(const IterParams& p, const LaunchShape& s, cudaStream_t stream) {
-    auto k = pgsgd_tile_kernel<DIMS, BATCH, SP>;
+    auto k = pgsgd_tile_kernel<DIMS, BATCH, SP, TMA>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s.smem);
     if (e != cudaSuccess) return e;
     k<<<s.grid, s.block, s.smem, stream>>>(p);
     return cudaGetLastError();
 }
-template <int DIMS, int BATCH, bool SP>
+template <int DIMS, int BATCH, bool SP, bool TMA>
 cudaError_t tile_occ_one(size_t smem, int* out) {
-    auto k = pgsgd_tile_kernel<DIMS, BATCH, SP>;
+    auto k = pgsgd_tile_kernel<DIMS, BATCH, SP, TMA>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, 256, smem);
 }
 
+template <int DIMS, int BATCH>
+cudaError_t tile_launch_pick(bool sp, bool tma, const IterParams& p, const LaunchShape& shape, cudaStream_t stream) {
+    if (tma) return sp ? tile_launch_one<DIMS, BATCH, true, true>(p, shape, stream) : tile_launch_one<DIMS, BATCH, false, true>(p, shape, stream);
+    return sp ? tile_launch_one<DIMS, BATCH, true, false>(p, shape, stream) : tile_launch_one<DIMS, BATCH, false, false>(p, shape, stream);
+}
+template <int DIMS, int BATCH>
+cudaError_t tile_occ_pick(bool sp, bool tma, size_t smem, int* out) {
+    if (tma) return sp ? tile_occ_one<DIMS, BATCH, true, true>(smem, out) : tile_occ_one<DIMS, BATCH, false, true>(smem, out);
+    return sp ? tile_occ_one<DIMS, BATCH, true, false>(smem, out) : tile_occ_one<DIMS, BATCH, false, false>(smem, out);
+}
+
 cudaError_t launch_tile_iteration(int dims, int batch, const IterParams& p, const LaunchShape& shape, cudaStream_t stream) {
     if (shape.block != 256) return cudaErrorInvalidValue;
-    const bool sp = p.smem_paths != 0;
-    if (dims == 2 && batch == 4) return sp ? tile_launch_one<2, 4, true>(p, shape, stream) : tile_launch_one<2, 4, false>(p, shape, stream);
-    if (dims == 2 && batch == 2) return sp ? tile_launch_one<2, 2, true>(p, shape, stream) : tile_launch_one<2, 2, false>(p, shape, stream);
-    if (dims == 1 && batch == 4) return sp ? tile_launch_one<1, 4, true>(p, shape, stream) : tile_launch_one<1, 4, false>(p, shape, stream);
-    if (dims == 1 && batch == 2) return sp ? tile_launch_one<1, 2, true>(p, shape, stream) : tile_launch_one<1, 2, false>(p, shape, stream);
+    const bool sp = p.smem_paths != 0, tma = (p.flags & 8u) != 0;
+    if (dims == 2 && batch == 4) return tile_launch_pick<2, 4>(sp, tma, p, shape, stream);
+    if (dims == 2 && batch == 2) return tile_launch_pick<2, 2>(sp, tma, p, shape, stream);
+    if (dims == 1 && batch == 4) return tile_launch_pick<1, 4>(sp, tma, p, shape, stream);
+    if (dims == 1 && batch == 2) return tile_launch_pick<1, 2>(sp, tma, p, shape, stream);
     return cudaErrorInvalidValue;
 }
 
-cudaError_t tile_occupancy(int dims, int batch, size_t smem, bool sp, int* out) {
-    if (dims == 2 && batch == 4) return sp ? tile_occ_one<2, 4, true>(smem, out) : tile_occ_one<2, 4, false>(smem, out);
-    if (dims == 2 && batch == 2) return sp ? tile_occ_one<2, 2, true>(smem, out) : tile_occ_one<2, 2, false>(smem, out);
-    if (dims == 1 && batch == 4) return sp ? tile_occ_one<1, 4, true>(smem, out) : tile_occ_one<1, 4, false>(smem, out);
-    if (dims == 1 && batch == 2) return sp ? tile_occ_one<1, 2, true>(smem, out) : tile_occ_one<1, 2, false>(smem, out);
+cudaError_t tile_occupancy(int dims, int batch, size_t smem, bool sp, bool tma, int* out) {
+    if (dims == 2 && batch == 4) return tile_occ_pick<2, 4>(sp, tma, smem, out);
+    if (dims == 2 && batch == 2) return tile_occ_pick<2, 2>(sp, tma, smem, out);
+    if (dims == 1 && batch == 4) return tile_occ_pick<1, 4>(sp, tma, smem, out);
+    if (dims == 1 && batch == 2) return tile_occ_pick<1, 2>(sp, tma, smem, out);
     return cudaErrorInvalidValue;
 }
 

@@ -60,7 +60,7 @@ cudaError_t launch_seed_streams(uint64_t* rng, uint64_t rng_stride, uint64_t n, 
 cudaError_t launch_iteration(int dims, int batch, const IterParams& p, const LaunchShape& shape, cudaStream_t stream);
 // the same with tile sampling (TILE_STEPS consecutive steps staged in shared memory per visit)
 cudaError_t launch_tile_iteration(int dims, int batch, const IterParams& p, const LaunchShape& shape, cudaStream_t stream);
-cudaError_t tile_occupancy(int dims, int batch, size_t smem, bool smem_paths, int* blocks_per_sm);
+cudaError_t tile_occupancy(int dims, int batch, size_t smem, bool smem_paths, bool tma, int* blocks_per_sm);
 // occupancy query for the kernel variant (resident blocks per SM for the given block size / smem)
 cudaError_t iteration_occupancy(int dims, int batch, int block, size_t smem, bool smem_paths, int* blocks_per_sm);
 

@@ -235,6 +235,18 @@ def test_1d_tile_sampling_stress_within_reference_band(graphs, golden_dir, name)
     _assert_in_band(vals, band)
 
 
+def test_tile_tma_staging_variant(graphs, golden_dir):
+    """PGSGD_FLAG_TMA_STAGING: tiles staged by double-buffered TMA bulk copies + mbarrier; same results statistically"""
+    gd, go = graphs["chr6.C4"]
+    band = _stress_band(golden_dir, "chr6.C4.layout2d")
+    X0, Y0 = orc.layout_init(go, seed=42)
+    cd = capi.layout_defaults(gd, sampling=capi.SAMPLING_TILE, flags=capi.PGSGD_FLAG_TMA_STAGING)
+    X, Y, st = odgi_b200.layout_2d(gd, cd, X0, Y0)
+    assert st["term_updates"] == 30 * 10 * gd.S
+    s = orc.path_stress_2d(go, X, Y, n_pairs=band["n_pairs"], seed=band["seed"])
+    assert abs(s - band["mean"]) <= 0.025 * band["mean"], (s, band["mean"])
+
+
 def test_tile_sampling_partial_pass_counts(graphs):
     """U not a multiple of S: full passes + a truncated one; the counted updates are exact when the truncated pass
     does not reach the short last tile"""
