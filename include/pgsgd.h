@@ -112,6 +112,8 @@ typedef struct pgsgd_stats {
     double   last_delta_max;               /* max |Delta| of the last iteration (only tracked when delta > 0) */
     uint64_t kernel_launches;              /* SGD kernel launches */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t flags_used;                   /* PGSGD_FLAG_* actually in effect (the engine switches to EXCH_WRITE by itself
+                                              when a hub node would see too many concurrent red.adds) */
 } pgsgd_stats;
 
 typedef struct pgsgd_engine pgsgd_engine;   /* opaque: device-resident graph + coordinates + RNG streams */

@@ -115,6 +115,7 @@ struct pgsgd_engine {
     int sm_count = 0;
     uint64_t N = 0, P = 0, S = 0;
     uint64_t max_path_steps = 0;
+    uint64_t max_node_depth = 0;             // most steps on one node (hub nodes bound the safe Hogwild concurrency)
     bool any_multi_step_path = false;
     StepRec* d_steps = nullptr;
     uint64_t* d_path_first = nullptr;
@@ -378,8 +379,7 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     const int block = 256;
     const size_t smem_first = (e->P + 1) * sizeof(uint64_t);
     bool tile_mode = cfg->sampling == PGSGD_SAMPLING_TILE || (cfg->sampling == PGSGD_SAMPLING_AUTO && e->S >= (1ull << 22));
-    int batch = cfg->batch ? (int) cfg->batch : (tile_mode ? 2 : 1);
-    if (tile_mode && batch == 1) batch = 2;
+    int batch = cfg->batch ? (int) cfg->batch : 1;  // 64 registers, 4 CTAs/SM: occupancy beats per-thread batching (profiles/)
     bool smem_paths = false;
     size_t smem = 0;
     int blocks_per_sm = 0;
@@ -395,7 +395,9 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         uint64_t grid = (uint64_t) e->sm_count * blocks_per_sm;
         if (cfg->n_streams) grid = (cfg->n_streams + block - 1) / block;
         // Hogwild staleness cap (see below): terms in flight = grid * block * batch
-        const uint64_t cap_grid = (e->N / cap_frac) / ((uint64_t) block * batch * cap_div);
+        // tile sampling concentrates the in-flight first steps on (grid) tiles of consecutive steps: nodes a path revisits
+        // within a tile (tandem repeats, LPA) see several concurrent terms, so the cap is 4x tighter than for stream sampling
+        const uint64_t cap_grid = (e->N / (4 * cap_frac)) / ((uint64_t) block * batch * cap_div);
         if (!cfg->n_streams && grid > cap_grid) grid = cap_grid;
         if (grid == 0) {
             if (cfg->sampling == PGSGD_SAMPLING_TILE) grid = 1; else tile_mode = false;
@@ -470,6 +472,19 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     p.delta_max_bits = track_delta ? e->d_delta : nullptr;
     p.counted = e->d_counted;
     p.flags = cfg->flags;
+    {
+        // Hub safeguard.  red.add accumulates every concurrent (stale) displacement of a node; that is stable while a node
+        // end sees a few terms in flight (measured: parity up to ~2.3, divergence from ~9) and unstable beyond.  The node
+        // with the most steps sees in_flight * 2 * depth / S of them.  Past the margin the run uses the reference kernel's
+        // last-writer-wins exchange instead, which cannot overshoot (it drops concurrent updates, as the reference does).
+        const double in_flight = (double) n_streams * batch * (peer ? e->n_ranks : 1);
+        const double hub_terms = e->S ? in_flight * 2.0 * (double) e->max_node_depth / (double) e->S : 0.0;
+        if (hub_terms > 4.0 && !(p.flags & (PGSGD_FLAG_EXCH_WRITE | PGSGD_FLAG_PLAIN_STORE))) {
+            p.flags |= PGSGD_FLAG_EXCH_WRITE;
+            st.flags_used |= PGSGD_FLAG_EXCH_WRITE;
+        }
+    }
+    st.flags_used |= p.flags;
     p.smem_paths = smem_paths ? 1u : 0u;
     p.trace = e->d_trace;
     p.trace_count = e->d_trace_count;
@@ -627,6 +642,7 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
             st.seconds_iterations += b.seconds_iterations;
             st.kernel_launches += b.kernel_launches;
             st.last_delta_max = b.last_delta_max;
+            st.flags_used |= b.flags_used;
         }
         *stats = st;
     }
@@ -748,6 +764,11 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
     if ((err = cudaMemcpyAsync(d_node_len, g->node_len, e->N * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) { cudaFree(d_node_len); return cu_bail(err, "upload node_len"); }
     e->h2d_bytes += e->N * sizeof(uint32_t);
     uint32_t* d_sn = nullptr; uint8_t* d_sr = nullptr; uint64_t* d_sp = nullptr;
+    uint32_t* d_depth = nullptr;  // steps per node, counted while packing
+    if (cudaMalloc(&d_depth, e->N * sizeof(uint32_t)) != cudaSuccess || cudaMemsetAsync(d_depth, 0, e->N * sizeof(uint32_t), e->stream) != cudaSuccess) {
+        cudaFree(d_node_len); cudaFree(d_depth);
+        return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc depth table failed"));
+    }
     if (pos) {
         const uint64_t CH = 1ull << 26;  // 64 Mi steps per staging chunk (832 MiB of SoA)
         const uint64_t ch = e->S < CH ? (e->S ? e->S : 1) : CH;
@@ -758,7 +779,7 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
             err = cudaMemcpyAsync(d_sn, g->step_node + off, n * 4, cudaMemcpyHostToDevice, e->stream);
             if (err == cudaSuccess) err = cudaMemcpyAsync(d_sp, pos + off, n * 8, cudaMemcpyHostToDevice, e->stream);
             if (err == cudaSuccess && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev + off, n, cudaMemcpyHostToDevice, e->stream);
-            if (err == cudaSuccess) err = launch_pack_steps(e->d_steps, d_sn, d_sr, d_sp, d_node_len, n, off, e->stream);
+            if (err == cudaSuccess) err = launch_pack_steps(e->d_steps, d_sn, d_sr, d_sp, d_node_len, n, off, d_depth, e->stream);
             if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);  // staging buffers and pageable sources are reused
             e->h2d_bytes += n * (4 + 8 + (g->step_rev ? 1 : 0));
         }
@@ -772,17 +793,22 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
         err = cudaMemsetAsync(d_bad, 0, sizeof(int), e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(d_sn, g->step_node, e->S * 4, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev, e->S, cudaMemcpyHostToDevice, e->stream);
-        if (err == cudaSuccess) err = launch_flatten_on_device(e->d_steps, d_sn, d_sr, d_node_len, e->d_path_first, (uint32_t) e->P, (uint32_t) e->N, e->S, d_sp, d_bad, e->stream);
+        if (err == cudaSuccess) err = launch_flatten_on_device(e->d_steps, d_sn, d_sr, d_node_len, e->d_path_first, (uint32_t) e->P, (uint32_t) e->N, e->S, d_sp, d_bad, d_depth, e->stream);
         int bad = 0;
         if (err == cudaSuccess) err = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
         cudaFree(d_bad);
         e->h2d_bytes += e->S * (4 + (g->step_rev ? 1 : 0));
         if (err == cudaSuccess && bad) {
-            cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr);
+            cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
             return bail(fail(PGSGD_ERR_UNOPT, "a step refers to a node rank >= node_count: ids are not compacted 1..N"));
         }
     }
-    cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr);
+    if (err == cudaSuccess) {
+        std::vector<uint32_t> depth(e->N);
+        err = cudaMemcpy(depth.data(), d_depth, e->N * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        for (uint32_t d : depth) if (d > e->max_node_depth) e->max_node_depth = d;
+    }
+    cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
     if (err != cudaSuccess) return cu_bail(err, "flatten-to-device");
     if ((err = cudaStreamSynchronize(e->stream)) != cudaSuccess) return cu_bail(err, "engine create sync");
     e->seconds_upload = now_s() - t0;

@@ -56,6 +56,10 @@ __device__ __forceinline__ double* coord1_ptr(const IterParams& p, uint32_t node
     return p.part_x1d[q] + node;
 }
 
+#ifndef TILE_B1_CTAS
+#define TILE_B1_CTAS 4
+#endif
+
 template <int BATCH>
 struct MinBlocks {
     static constexpr int value = BATCH >= 4 ? 2 : (BATCH == 2 ? 3 : 4);
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(256, MinBlocks<BATCH>::value) pgsgd_iter_kerne
 // Consecutive lanes hold consecutive steps, so their coordinate reads/reds of the first node coalesce as well.
 // --------------------------------------------------------------------------------------------------
 template <int DIMS, int BATCH, bool SMEM_PATHS, bool TMA>
-__global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : 3) pgsgd_tile_kernel(const __grid_constant__ IterParams p) {
+__global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : (BATCH == 2 ? 3 : TILE_B1_CTAS)) pgsgd_tile_kernel(const __grid_constant__ IterParams p) {
     constexpr int ROUNDS = TILE_STEPS / 256;
     static_assert(ROUNDS % BATCH == 0, "tile rounds must be a multiple of the batch");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -499,10 +503,11 @@ __global__ void seed_streams_kernel(uint64_t* rng, uint64_t stride, uint64_t n, 
 }
 
 __global__ void pack_steps_kernel(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* pos,
-                                  const uint32_t* node_len, uint64_t n, uint64_t out_offset) {
+                                  const uint32_t* node_len, uint64_t n, uint64_t out_offset, uint32_t* depth) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t node = step_node[i];
+    if (depth) atomicAdd(depth + node, 1u);
     StepRec r;
     r.handle = (node << 1) | (step_rev ? (uint32_t) (step_rev[i] != 0) : 0u);
     r.len = node_len[node];
@@ -523,10 +528,11 @@ __global__ void gather_len_kernel(uint64_t* len, const uint32_t* step_node, cons
 }
 
 __global__ void pack_steps_scan_kernel(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* scan,
-                                       const uint32_t* node_len, const uint64_t* first, uint32_t P, uint64_t n) {
+                                       const uint32_t* node_len, const uint64_t* first, uint32_t P, uint64_t n, uint32_t* depth) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t node = step_node[i];
+    if (depth) atomicAdd(depth + node, 1u);
     const uint32_t p = find_path(first, P, i);
     const uint64_t pos = scan[i] - scan[first[p]];
     StepRec r;
@@ -708,6 +714,8 @@ cudaError_t launch_tile_iteration(int dims, int batch, const IterParams& p, cons
     const bool sp = p.smem_paths != 0, tma = (p.flags & 8u) != 0;
     if (dims == 2 && batch == 4) return tile_launch_pick<2, 4>(sp, tma, p, shape, stream);
     if (dims == 2 && batch == 2) return tile_launch_pick<2, 2>(sp, tma, p, shape, stream);
+    if (dims == 2 && batch == 1) return tile_launch_pick<2, 1>(sp, tma, p, shape, stream);
+    if (dims == 1 && batch == 1) return tile_launch_pick<1, 1>(sp, tma, p, shape, stream);
     if (dims == 1 && batch == 4) return tile_launch_pick<1, 4>(sp, tma, p, shape, stream);
     if (dims == 1 && batch == 2) return tile_launch_pick<1, 2>(sp, tma, p, shape, stream);
     return cudaErrorInvalidValue;
@@ -716,6 +724,8 @@ cudaError_t launch_tile_iteration(int dims, int batch, const IterParams& p, cons
 cudaError_t tile_occupancy(int dims, int batch, size_t smem, bool sp, bool tma, int* out) {
     if (dims == 2 && batch == 4) return tile_occ_pick<2, 4>(sp, tma, smem, out);
     if (dims == 2 && batch == 2) return tile_occ_pick<2, 2>(sp, tma, smem, out);
+    if (dims == 2 && batch == 1) return tile_occ_pick<2, 1>(sp, tma, smem, out);
+    if (dims == 1 && batch == 1) return tile_occ_pick<1, 1>(sp, tma, smem, out);
     if (dims == 1 && batch == 4) return tile_occ_pick<1, 4>(sp, tma, smem, out);
     if (dims == 1 && batch == 2) return tile_occ_pick<1, 2>(sp, tma, smem, out);
     return cudaErrorInvalidValue;
@@ -762,15 +772,15 @@ cudaError_t iteration_occupancy(int dims, int batch, int block, size_t smem, boo
 }
 
 cudaError_t launch_pack_steps(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* step_pos,
-                              const uint32_t* node_len, uint64_t n, uint64_t out_offset, cudaStream_t stream) {
+                              const uint32_t* node_len, uint64_t n, uint64_t out_offset, uint32_t* depth, cudaStream_t stream) {
     if (!n) return cudaSuccess;
-    pack_steps_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, step_node, step_rev, step_pos, node_len, n, out_offset);
+    pack_steps_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, step_node, step_rev, step_pos, node_len, n, out_offset, depth);
     return cudaGetLastError();
 }
 
 cudaError_t launch_flatten_on_device(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint32_t* node_len,
                                      const uint64_t* first, uint32_t P, uint32_t n_nodes, uint64_t n, uint64_t* scratch_len, int* bad,
-                                     cudaStream_t stream) {
+                                     uint32_t* depth, cudaStream_t stream) {
     if (!n) return cudaSuccess;
     gather_len_kernel<<<grid_for(n, 256), 256, 0, stream>>>(scratch_len, step_node, node_len, n, n_nodes, bad);
     cudaError_t e = cudaGetLastError();
@@ -783,7 +793,10 @@ cudaError_t launch_flatten_on_device(StepRec* out, const uint32_t* step_node, co
     if (e != cudaSuccess) return e;
     e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, scratch_len, scratch_len, n, stream);
     if (e == cudaSuccess) {
-        pack_steps_scan_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, step_node, step_rev, scratch_len, node_len, first, P, n);
+        int h_bad = 0;  // the packing kernel indexes node tables: only run it on validated ids
+        e = cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess && !h_bad) pack_steps_scan_kernel<<<grid_for(n, 256), 256, 0, stream>>>(out, step_node, step_rev, scratch_len, node_len, first, P, n, depth);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);

@@ -66,13 +66,13 @@ cudaError_t iteration_occupancy(int dims, int batch, int block, size_t smem, boo
 
 // packs SoA step arrays into StepRec records on the device
 cudaError_t launch_pack_steps(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* step_pos,
-                              const uint32_t* node_len, uint64_t n, uint64_t out_offset, cudaStream_t stream);
+                              const uint32_t* node_len, uint64_t n, uint64_t out_offset, uint32_t* depth, cudaStream_t stream);
 
 // the same with the positions derived on the device (device-wide scan of node lengths); *bad is set to 1 when a step refers
 // to a node rank >= n_nodes
 cudaError_t launch_flatten_on_device(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint32_t* node_len,
                                      const uint64_t* first, uint32_t P, uint32_t n_nodes, uint64_t n, uint64_t* scratch_len, int* bad,
-                                     cudaStream_t stream);
+                                     uint32_t* depth, cudaStream_t stream);
 
 // coordinate format conversion: reference X/Y (double, index 2*node+end) <-> device float4-per-node
 cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n_nodes, cudaStream_t stream);

@@ -11,7 +11,7 @@ print(f"workload={wl} N={g.N} S={g.S}", flush=True)
 with odgi_b200.Engine(g) as e:
     e.set_coords_2d(X0, Y0)
     for sampling, name, flags in ((1, "stream", 0), (2, "tile", 0), (2, "tileTMA", 8)):
-        for batch in ((1, 4) if sampling == 1 else (2, 4)):
+        for batch in ((1,) if sampling == 1 else ((1, 2, 4) if flags == 0 else (4,))):
             cd = capi.layout_defaults(g, batch=batch, sampling=sampling, flags=flags)
             e.run_range(cd, 2, 0, 1)
             st = e.run_range(cd, 2, 1, 4)

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log | cut -c1-300
+timeout 900 python scripts/gpu_exp_tile_small.py > gpurun_out/exp_tile_small.log 2>&1; cat gpurun_out/exp_tile_small.log

@@ -33,7 +33,7 @@ def test_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     assert C.sizeof(capi.ConfigC) == 120
     assert C.sizeof(capi.GraphView) == 64
-    assert C.sizeof(capi.StatsC) == 72
+    assert C.sizeof(capi.StatsC) == 80
 
 
 @pytest.mark.parametrize("kw", [dict(iter_max=30, eta_max=3100.0 ** 2, eps=0.01), dict(iter_max=100, eta_max=21901.0 ** 2, eps=0.01),

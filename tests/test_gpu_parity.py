@@ -447,3 +447,24 @@ def test_scale_properties_on_a_graph_beyond_l2():
     assert np.all(np.isfinite(X)) and np.all(np.isfinite(Y))
     assert finals[capi.SAMPLING_STREAM] == orc.path_stress_2d(go, X, Y, 1_000_000, 3)
     assert abs(finals[capi.SAMPLING_TILE] - finals[capi.SAMPLING_STREAM]) <= 0.05 * finals[capi.SAMPLING_STREAM], finals
+
+
+def test_hub_node_switches_to_exchange_writes():
+    """A node carrying a large share of all steps would see dozens of concurrent red.adds: the engine falls back to the
+    reference kernel's last-writer-wins exchange by itself (stats.flags_used) and the layout stays finite."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    N, P, L = 20_000, 8, 40_000
+    node_len = rng.integers(1, 20, size=N).astype(np.uint32)
+    first = (np.arange(P + 1) * L).astype(np.uint64)
+    step_node = rng.integers(1, N, size=P * L).astype(np.uint32)
+    step_node[::3] = 0                      # every third step of every path sits on node 0
+    gd = odgi_b200.FlatGraph(node_len, first, step_node, np.zeros(P * L, dtype=np.uint8))
+    go = orc.Graph(node_len, first, step_node, np.zeros(P * L, dtype=np.uint8))
+    X0, Y0 = orc.layout_init(go, 1)
+    X, Y, st = odgi_b200.layout_2d(gd, capi.layout_defaults(gd, iter_max=10), X0, Y0)
+    assert st["flags_used"] & capi.PGSGD_FLAG_EXCH_WRITE
+    assert np.all(np.isfinite(X)) and np.all(np.isfinite(Y))
+    # an ordinary graph keeps the lossless default
+    a = odgi_b200.FlatGraph(node_len, first, rng.integers(0, N, size=P * L).astype(np.uint32), np.zeros(P * L, dtype=np.uint8))
+    _, _, st2 = odgi_b200.layout_2d(a, capi.layout_defaults(a, iter_max=3), X0, Y0)
+    assert not (st2["flags_used"] & capi.PGSGD_FLAG_EXCH_WRITE)
