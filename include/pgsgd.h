@@ -194,6 +194,12 @@ int pgsgd_engine_sample_terms(pgsgd_engine* e, const pgsgd_config* cfg, int dims
  * reference has no layout-quality readout on this path; this is the one the parity tests use. */
 int pgsgd_engine_path_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64_t seed, double* stress_out);
 
+/* The node order `odgi sort -Y` derives from the 1D layout (path_linear_sgd_order, src/algorithms/path_sgd.cpp:638-683):
+ * node ranks sorted by position, ties by handle, computed on the device (stable radix sort).  order_out: [N] node ranks.
+ * (The reference also keys on the weak component, but clears that map before reading it, path_sgd.cpp:588 — the key is
+ * constant there and here.) */
+int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out);
+
 /* Tile-sampling verification: with a trace buffer set, every term the tile kernel draws is recorded (first step,
  * partner step as global step indices, flips = flip_a | flip_b << 1) until the buffer is full. */
 int pgsgd_engine_set_trace(pgsgd_engine* e, uint64_t capacity);   /* 0 = off */

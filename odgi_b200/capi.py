@@ -59,7 +59,7 @@ EXPORTED_SYMBOLS = [
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
     "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
-    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_path_stress", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
+    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_path_stress", "pgsgd_engine_order_1d", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ def lib():
         L.pgsgd_engine_attach_comm.argtypes = [vp, vp, i32, i32]
         L.pgsgd_engine_set_multi_mode.argtypes = [vp, i32]
         L.pgsgd_engine_path_stress.argtypes = [vp, i32, u64, u64, vp]
+        L.pgsgd_engine_order_1d.argtypes = [vp, vp]
         L.pgsgd_engine_sample_terms.argtypes = [vp, C.POINTER(ConfigC), i32, i32, dbl, u64, u64] + [vp] * 11
         L.pgsgd_engine_set_trace.argtypes = [vp, u64]
         L.pgsgd_engine_get_trace.argtypes = [vp, vp, vp, vp, vp]
@@ -335,6 +336,11 @@ class Engine:
         out = C.c_double(0.0)
         _check(lib().pgsgd_engine_path_stress(self._h, dims, n_pairs, seed, C.byref(out)))
         return float(out.value)
+
+    def order_1d(self) -> np.ndarray:
+        order = np.empty(self.g.N, dtype=np.uint64)
+        _check(lib().pgsgd_engine_order_1d(self._h, _ptr(order)))
+        return order
 
     def set_multi_mode(self, mode: int):
         """0 = all-reduce of replicated coordinates, 1 = NVLink peer memory (partitioned coordinates)"""

@@ -1024,6 +1024,20 @@ int pgsgd_engine_path_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64
     return PGSGD_OK;
 }
 
+int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out) {
+    if (!e || !order_out) return fail(PGSGD_ERR_ARG, "order_1d: NULL argument");
+    if (!e->have_1d) return fail(PGSGD_ERR_STATE, "no 1D coordinates on the device");
+    CU(cudaSetDevice(e->device));
+    if (e->coords_in_slices) { int rc = peer_gather(e, 1); if (rc) return rc; }
+    uint64_t* d_order = nullptr;
+    CU(cudaMalloc(&d_order, e->N * sizeof(uint64_t)));
+    cudaError_t err = launch_order_1d(e->d_x1d, d_order, e->N, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpy(order_out, d_order, e->N * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    cudaFree(d_order);
+    if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "order_1d: %s", cudaGetErrorString(err));
+    return PGSGD_OK;
+}
+
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode) {
     if (!e) return fail(PGSGD_ERR_ARG, "set_multi_mode: NULL engine");
     if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_PEER && mode != PGSGD_MULTI_HYBRID) return fail(PGSGD_ERR_ARG, "unknown multi-GPU mode %d", mode);

@@ -17,6 +17,7 @@
 
 #include <cstdio>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 namespace pgsgd {
@@ -801,6 +802,30 @@ cudaError_t launch_flatten_on_device(StepRec* out, const uint32_t* step_node, co
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(tmp);
+    return e;
+}
+
+__global__ void iota_kernel(uint64_t* v, uint64_t n) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+
+// 1D node order (path_linear_sgd_order's sort, path_sgd.cpp:650-658, with its constant component key): node ranks sorted
+// by position, ties by handle — a STABLE radix sort of (x, rank) pairs that start in rank order gives exactly that.
+cudaError_t launch_order_1d(const double* x, uint64_t* order_out, uint64_t n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    double* keys_out = nullptr;
+    uint64_t* vals_in = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cudaMalloc(&keys_out, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&vals_in, n * sizeof(uint64_t));
+    if (e == cudaSuccess) { iota_kernel<<<grid_for(n, 256), 256, 0, stream>>>(vals_in, n); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, x, keys_out, vals_in, order_out, n, 0, 64, stream);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, x, keys_out, vals_in, order_out, n, 0, 64, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(tmp); cudaFree(vals_in); cudaFree(keys_out);
     return e;
 }
 

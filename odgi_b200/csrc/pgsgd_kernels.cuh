@@ -74,6 +74,9 @@ cudaError_t launch_flatten_on_device(StepRec* out, const uint32_t* step_node, co
                                      const uint64_t* first, uint32_t P, uint32_t n_nodes, uint64_t n, uint64_t* scratch_len, int* bad,
                                      uint32_t* depth, cudaStream_t stream);
 
+// 1D node order on the device: node ranks sorted by (x, rank), stable radix sort
+cudaError_t launch_order_1d(const double* x, uint64_t* order_out, uint64_t n, cudaStream_t stream);
+
 // coordinate format conversion: reference X/Y (double, index 2*node+end) <-> device float4-per-node
 cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n_nodes, cudaStream_t stream);
 cudaError_t launch_XY_from_xy(double* X, double* Y, const float* xy, uint64_t n_nodes, cudaStream_t stream);

@@ -468,3 +468,33 @@ def test_hub_node_switches_to_exchange_writes():
     a = odgi_b200.FlatGraph(node_len, first, rng.integers(0, N, size=P * L).astype(np.uint32), np.zeros(P * L, dtype=np.uint8))
     _, _, st2 = odgi_b200.layout_2d(a, capi.layout_defaults(a, iter_max=3), X0, Y0)
     assert not (st2["flags_used"] & capi.PGSGD_FLAG_EXCH_WRITE)
+
+
+def test_device_order_equals_reference_sort(graphs):
+    """pgsgd_engine_order_1d == the (pos, handle) sort of path_linear_sgd_order on the same X — including ties"""
+    gd, go = graphs["DRB1-3123"]
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_1d(None)
+        e.run_1d(capi.sort_defaults(gd, iter_max=20))
+        x = e.get_coords_1d()
+        assert np.array_equal(e.order_1d(), orc.order_from_x(x))
+        xt = np.round(x / 50.0) * 50.0 - 1e4       # many exact ties, negative values
+        e.set_coords_1d(xt)
+        assert np.array_equal(e.order_1d(), orc.order_from_x(xt))
+
+
+def test_run_range_continues_the_schedule(graphs):
+    """run_range(0, k) + run_range(k, n) == run(0, n): same streams, same schedule (single stream: bit-exact)"""
+    gd, go = graphs["DRB1-3123"]
+    cd = capi.layout_defaults(gd, iter_max=6, min_term_updates=3000, n_streams=1, batch=1, sampling=capi.SAMPLING_STREAM)
+    X0, Y0 = orc.layout_init(go, 4)
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_2d(X0, Y0)
+        e.run_2d(cd)
+        full = e.get_coords_2d_f32()
+        e.set_coords_2d(X0, Y0)
+        a = e.run_range(cd, 2, 0, 2)
+        b = e.run_range(cd, 2, 2, 6)
+        split = e.get_coords_2d_f32()
+    assert a["iterations_run"] == 2 and b["iterations_run"] == 4
+    assert np.array_equal(full, split)
