@@ -116,6 +116,7 @@ struct pgsgd_engine {
     uint64_t N = 0, P = 0, S = 0;
     uint64_t max_path_steps = 0;
     uint64_t max_node_depth = 0;             // most steps on one node (hub nodes bound the safe Hogwild concurrency)
+    uint64_t tile_repeats = 0;               // steps that revisit a node already seen in their tile (tandem repeats; bounds the tile-mode shape)
     bool any_multi_step_path = false;
     StepRec* d_steps = nullptr;
     uint64_t* d_path_first = nullptr;
@@ -396,8 +397,10 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         if (cfg->n_streams) grid = (cfg->n_streams + block - 1) / block;
         // Hogwild staleness cap (see below): terms in flight = grid * block * batch
         // tile sampling concentrates the in-flight first steps on (grid) tiles of consecutive steps: nodes a path revisits
-        // within a tile (tandem repeats, LPA) see several concurrent terms, so the cap is 4x tighter than for stream sampling
-        const uint64_t cap_grid = (e->N / (4 * cap_frac)) / ((uint64_t) block * batch * cap_div);
+        // within a tile (tandem repeats, LPA) see several concurrent terms, so the cap is 2x tighter than for stream sampling
+        // ... scaled by the share of a tile's steps that are first visits of their node (1 for a path without repeats)
+        const double distinct = e->S ? 1.0 - (double) e->tile_repeats / (double) e->S : 1.0;
+        const uint64_t cap_grid = (uint64_t) ((double) (e->N / (2 * cap_frac)) * distinct) / ((uint64_t) block * batch * cap_div);
         if (!cfg->n_streams && grid > cap_grid) grid = cap_grid;
         if (grid == 0) {
             if (cfg->sampling == PGSGD_SAMPLING_TILE) grid = 1; else tile_mode = false;
@@ -765,8 +768,10 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
     e->h2d_bytes += e->N * sizeof(uint32_t);
     uint32_t* d_sn = nullptr; uint8_t* d_sr = nullptr; uint64_t* d_sp = nullptr;
     uint32_t* d_depth = nullptr;  // steps per node, counted while packing
-    if (cudaMalloc(&d_depth, e->N * sizeof(uint32_t)) != cudaSuccess || cudaMemsetAsync(d_depth, 0, e->N * sizeof(uint32_t), e->stream) != cudaSuccess) {
-        cudaFree(d_node_len); cudaFree(d_depth);
+    unsigned long long* d_maxdup = nullptr;
+    if (cudaMalloc(&d_depth, e->N * sizeof(uint32_t)) != cudaSuccess || cudaMemsetAsync(d_depth, 0, e->N * sizeof(uint32_t), e->stream) != cudaSuccess ||
+        cudaMalloc(&d_maxdup, sizeof(unsigned long long)) != cudaSuccess || cudaMemsetAsync(d_maxdup, 0, sizeof(unsigned long long), e->stream) != cudaSuccess) {
+        cudaFree(d_node_len); cudaFree(d_depth); cudaFree(d_maxdup);
         return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc depth table failed"));
     }
     if (pos) {
@@ -780,6 +785,7 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
             if (err == cudaSuccess) err = cudaMemcpyAsync(d_sp, pos + off, n * 8, cudaMemcpyHostToDevice, e->stream);
             if (err == cudaSuccess && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev + off, n, cudaMemcpyHostToDevice, e->stream);
             if (err == cudaSuccess) err = launch_pack_steps(e->d_steps, d_sn, d_sr, d_sp, d_node_len, n, off, d_depth, e->stream);
+            if (err == cudaSuccess) err = launch_tile_repeats(d_sn, n, d_maxdup, e->stream);  // chunks start on tile boundaries
             if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);  // staging buffers and pageable sources are reused
             e->h2d_bytes += n * (4 + 8 + (g->step_rev ? 1 : 0));
         }
@@ -796,6 +802,7 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
         if (err == cudaSuccess) err = launch_flatten_on_device(e->d_steps, d_sn, d_sr, d_node_len, e->d_path_first, (uint32_t) e->P, (uint32_t) e->N, e->S, d_sp, d_bad, d_depth, e->stream);
         int bad = 0;
         if (err == cudaSuccess) err = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess && !bad) err = launch_tile_repeats(d_sn, e->S, d_maxdup, e->stream);
         cudaFree(d_bad);
         e->h2d_bytes += e->S * (4 + (g->step_rev ? 1 : 0));
         if (err == cudaSuccess && bad) {
@@ -807,7 +814,11 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
         std::vector<uint32_t> depth(e->N);
         err = cudaMemcpy(depth.data(), d_depth, e->N * sizeof(uint32_t), cudaMemcpyDeviceToHost);
         for (uint32_t d : depth) if (d > e->max_node_depth) e->max_node_depth = d;
+        unsigned long long md = 0;
+        if (err == cudaSuccess) err = cudaMemcpy(&md, d_maxdup, sizeof(md), cudaMemcpyDeviceToHost);
+        e->tile_repeats = md;
     }
+    cudaFree(d_maxdup);
     cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
     if (err != cudaSuccess) return cu_bail(err, "flatten-to-device");
     if ((err = cudaStreamSynchronize(e->stream)) != cudaSuccess) return cu_bail(err, "engine create sync");

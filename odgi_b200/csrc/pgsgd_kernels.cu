@@ -544,6 +544,36 @@ __global__ void pack_steps_scan_kernel(StepRec* out, const uint32_t* step_node, 
     out[i] = r;
 }
 
+// How often does a path revisit a node within one tile of TILE_STEPS consecutive steps?  One CTA per tile inserts the
+// tile's nodes into a shared-memory hash set and counts the repeated visits; the total over all tiles gives the share of
+// steps that are repeats (tandem repeats, LPA: high; SNP-dense pangenome graphs: ~0), which the tile-sampling launch
+// shape has to respect because the concurrent terms of a tile land on that tile's distinct nodes.
+__global__ void tile_repeat_kernel(const uint32_t* step_node, uint64_t n, unsigned long long* total_dups) {
+    constexpr uint32_t SLOTS = 2 * TILE_STEPS, EMPTY = 0xFFFFFFFFu;
+    __shared__ uint32_t slot[SLOTS];
+    __shared__ unsigned int dups;
+    for (uint32_t i = threadIdx.x; i < SLOTS; i += blockDim.x) slot[i] = EMPTY;
+    if (threadIdx.x == 0) dups = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t) blockIdx.x * TILE_STEPS;
+    unsigned int mine = 0;
+    for (uint32_t j = threadIdx.x; j < (uint32_t) TILE_STEPS; j += blockDim.x) {
+        if (base + j >= n) break;
+        const uint32_t node = step_node[base + j];
+        uint32_t h = (node * 2654435761u) >> 20;
+        for (;;) {
+            h &= SLOTS - 1;
+            const uint32_t old = atomicCAS(&slot[h], EMPTY, node);
+            if (old == EMPTY) break;
+            if (old == node) { ++mine; break; }
+            ++h;
+        }
+    }
+    if (mine) atomicAdd(&dups, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && dups) atomicAdd(total_dups, (unsigned long long) dups);
+}
+
 __global__ void xy_from_XY_kernel(float4* xy, const double* X, const double* Y, uint64_t n) {
     const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -827,6 +857,13 @@ cudaError_t launch_order_1d(const double* x, uint64_t* order_out, uint64_t n, cu
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(tmp); cudaFree(vals_in); cudaFree(keys_out);
     return e;
+}
+
+cudaError_t launch_tile_repeats(const uint32_t* step_node, uint64_t n, unsigned long long* total_dups, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    const uint64_t tiles = (n + TILE_STEPS - 1) / TILE_STEPS;
+    tile_repeat_kernel<<<(unsigned) tiles, 256, 0, stream>>>(step_node, n, total_dups);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n, cudaStream_t stream) {

@@ -74,6 +74,9 @@ cudaError_t launch_flatten_on_device(StepRec* out, const uint32_t* step_node, co
                                      const uint64_t* first, uint32_t P, uint32_t n_nodes, uint64_t n, uint64_t* scratch_len, int* bad,
                                      uint32_t* depth, cudaStream_t stream);
 
+// repeated node visits inside tiles of TILE_STEPS consecutive steps, summed over all tiles (n must start on a tile boundary)
+cudaError_t launch_tile_repeats(const uint32_t* step_node, uint64_t n, unsigned long long* total_dups, cudaStream_t stream);
+
 // 1D node order on the device: node ranks sorted by (x, rank), stable radix sort
 cudaError_t launch_order_1d(const double* x, uint64_t* order_out, uint64_t n, cudaStream_t stream);
 
