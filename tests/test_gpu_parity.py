@@ -498,3 +498,22 @@ def test_run_range_continues_the_schedule(graphs):
         split = e.get_coords_2d_f32()
     assert a["iterations_run"] == 2 and b["iterations_run"] == 4
     assert np.array_equal(full, split)
+
+
+def test_degenerate_graphs_do_nothing_like_the_reference():
+    """No path with more than one step: the reference returns without touching the layout (path_sgd_layout.cpp:64-74;
+    its own unit test of this corner: src/unittest/sort.cpp:129-255 — ten 1-node paths).  Also: a graph without paths."""
+    node_len = np.array([1] * 10, dtype=np.uint32)
+    first = np.arange(11, dtype=np.uint64)                      # ten paths of one step each
+    step_node = np.arange(10, dtype=np.uint32)
+    gd = odgi_b200.FlatGraph(node_len, first, step_node, np.zeros(10, dtype=np.uint8))
+    X0 = np.arange(20, dtype=np.float64)
+    Y0 = np.arange(20, dtype=np.float64) * 0.5
+    X, Y, st = odgi_b200.layout_2d(gd, capi.layout_defaults(gd, min_term_updates=1000, eta_max=4.0, space=1), X0, Y0)
+    assert st["term_updates"] == 0 and st["iterations_run"] == 0
+    assert np.array_equal(X, X0) and np.array_equal(Y, Y0)
+    x, st = odgi_b200.sort_1d(gd, capi.sort_defaults(gd, min_term_updates=1000, eta_max=4.0, space=1))
+    assert st["term_updates"] == 0 and np.array_equal(x, np.arange(10, dtype=np.float64))   # cumulative-bp initialisation
+    empty = odgi_b200.FlatGraph(node_len, np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.uint8))
+    X, Y, st = odgi_b200.layout_2d(empty, capi.Config(iter_max=3, min_term_updates=10, eta_max=4.0, space=1), X0, Y0)
+    assert st["term_updates"] == 0 and np.array_equal(X, X0)
