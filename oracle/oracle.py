@@ -92,6 +92,8 @@ def lib():
         L.orc_replay_single.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_int, C.c_uint64, C.c_uint64, C.c_double,
                                         C.c_double, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_replay_single.restype = C.c_uint64
+        L.orc_replay_single_frozen.argtypes = L.orc_replay_single.argtypes + [C.c_void_p]
+        L.orc_replay_single_frozen.restype = C.c_uint64
         L.orc_path_stress_2d.argtypes = [C.POINTER(_Graph), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
         L.orc_path_stress_2d.restype = C.c_double
         L.orc_path_stress_1d.argtypes = [C.POINTER(_Graph), C.c_void_p, C.c_uint64, C.c_uint64]
@@ -323,11 +325,12 @@ def peer_stale_2d_f32(g: Graph, cfg: Config, xy, n_ranks: int, streams_per_rank:
 
 
 def replay_single(g: Graph, cfg: Config, dims: int, n_terms: int, switch_at: int, eta0: float, eta1: float,
-                  cooling0: bool, cooling1: bool, theta1: float, X=None, Y=None, want_terms: bool = True):
+                  cooling0: bool, cooling1: bool, theta1: float, X=None, Y=None, want_terms: bool = True, frozen=None):
     terms = np.zeros(n_terms, dtype=TERM_DTYPE) if want_terms else None
+    fz = None if frozen is None else np.ascontiguousarray(frozen, dtype=np.uint8)
     gc, cc = g.c(), cfg.c()
-    lib().orc_replay_single(C.byref(gc), C.byref(cc), dims, n_terms, switch_at, eta0, eta1, int(cooling0), int(cooling1),
-                            theta1, _ptr(X), _ptr(Y), _ptr(terms))
+    lib().orc_replay_single_frozen(C.byref(gc), C.byref(cc), dims, n_terms, switch_at, eta0, eta1, int(cooling0), int(cooling1),
+                                   theta1, _ptr(X), _ptr(Y), _ptr(terms), _ptr(fz))
     return terms
 
 

@@ -479,6 +479,12 @@ uint64_t orc_peer_stale_2d_f32(const orc_graph* g, const orc_config* c, uint64_t
 uint64_t orc_replay_single(const orc_graph* g, const orc_config* c, int dims, uint64_t n_terms, uint64_t switch_at,
                            double eta0, double eta1, int cooling0, int cooling1, double theta1,
                            double* X, double* Y, orc_term* out_terms) {
+    return orc_replay_single_frozen(g, c, dims, n_terms, switch_at, eta0, eta1, cooling0, cooling1, theta1, X, Y, out_terms, NULL);
+}
+
+uint64_t orc_replay_single_frozen(const orc_graph* g, const orc_config* c, int dims, uint64_t n_terms, uint64_t switch_at,
+                                  double eta0, double eta1, int cooling0, int cooling1, double theta1,
+                                  double* X, double* Y, orc_term* out_terms, const uint8_t* frozen) {
     run_tables rt;
     tables_init(&rt, c);
     orc_rng rng;
@@ -496,8 +502,10 @@ uint64_t orc_replay_single(const orc_graph* g, const orc_config* c, int dims, ui
         } else {
             /* the reference prints its trace line after the d == 0 `continue` (path_sgd.cpp:320-327):
              * skipped terms are not emitted */
+            /* ... and after the both-frozen `continue` (path_sgd.cpp:298-302), which comes first */
+            if (frozen && frozen[term.node_a] && frozen[term.node_b]) continue;
             if (term.pos_a == term.pos_b) continue;
-            if (X) orc_apply_1d(&term, eta, X, NULL);
+            if (X) orc_apply_1d(&term, eta, X, frozen);
         }
         if (out_terms) out_terms[emitted] = term;
         ++emitted;

@@ -126,6 +126,11 @@ uint64_t orc_replay_single(const orc_graph* g, const orc_config* c, int dims, ui
                            double eta0, double eta1, int cooling0, int cooling1, double theta1,
                            double* X, double* Y, orc_term* out_terms /* nullable, n_terms */);
 
+/* the same with frozen nodes (1D, `odgi sort -H`): terms with both nodes frozen are counted but not traced */
+uint64_t orc_replay_single_frozen(const orc_graph* g, const orc_config* c, int dims, uint64_t n_terms, uint64_t switch_at,
+                                  double eta0, double eta1, int cooling0, int cooling1, double theta1,
+                                  double* X, double* Y, orc_term* out_terms, const uint8_t* frozen);
+
 /* Sampled path stress (our definition — the reference has none).  K pairs drawn with a
  * fixed seed: step uniform over all steps (=> path ∝ step count), partner uniform in the same path,
  * ends uniform (2D) / node starts (1D); d = |pos_a - pos_b| in bp, d == 0 skipped;

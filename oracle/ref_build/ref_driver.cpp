@@ -20,7 +20,7 @@
 //   ref_driver sort   <in.gfa> <out.arr> [k=v...]               1D PG-SGD (+ order)
 //   ref_driver schedule <eta_max> <iter_max> <iter_lr> <eps>     the reference schedule as hex floats
 // keys: threads iter_max iter_lr updates_x (U = updates_x * sum steps) updates (absolute U) delta eps
-//       eta_max theta space space_max space_q cooling order(0/1)
+//       eta_max theta space space_max space_q cooling order(0/1) freeze_mod (sort: freeze every k-th node rank, as -H does for target paths)
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -252,7 +252,15 @@ static int cmd_sort(int argc, char** argv) {
     }
     double cooling = getd(kv, "cooling", 0.5);
     bool want_order = getu(kv, "order", 0) != 0;
-    std::vector<bool> target_nodes;  // no -H
+    // `odgi sort -H`: nodes of the target paths are frozen (sort_main.cpp:266-311 fills target_nodes); here every
+    // freeze_mod-th node rank is frozen so the frozen branch (path_sgd.cpp:290-302,387-392) can be pinned
+    const uint64_t freeze_mod = getu(kv, "freeze_mod", 0);
+    std::vector<bool> target_nodes;
+    if (freeze_mod) {
+        target_nodes.resize(N);
+        for (uint64_t i = 0; i < N; ++i) target_nodes[i] = (i % freeze_mod) == 0;
+    }
+    const bool target_sorting = freeze_mod != 0;
     std::vector<std::string> snapshots;
     std::vector<double> x;
     std::vector<uint64_t> order;
@@ -260,11 +268,11 @@ static int cmd_sort(int argc, char** argv) {
     if (want_order) {
         std::vector<handle_t> o = algorithms::path_linear_sgd_order(L.graph, L.xp, L.paths, iter_max, iter_lr, U, delta, eps, eta_max, theta,
                                                                     space, space_max, space_q, cooling, threads, false, "", false, "",
-                                                                    false, "", false, target_nodes);
+                                                                    false, "", target_sorting, target_nodes);
         for (auto& h : o) order.push_back(as_integer(h));
     } else {
         x = algorithms::path_linear_sgd(L.graph, L.xp, L.paths, iter_max, iter_lr, U, delta, eps, eta_max, theta, space, space_max,
-                                        space_q, cooling, threads, false, false, snapshots, false, target_nodes);
+                                        space_q, cooling, threads, false, false, snapshots, target_sorting, target_nodes);
     }
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     pgsgd::ArrayWriter w(argv[3]);

@@ -72,12 +72,12 @@ def parse_trace(stderr: str, names):
     return a[:, 0], a[:, 1], a[:, 2]
 
 
-def align(g, cfg, dims, tr_path, tr_a, tr_b, eta, cooling1, theta1):
+def align(g, cfg, dims, tr_path, tr_a, tr_b, eta, cooling1, theta1, frozen=None):
     """Find the term index at which the reference's checker switched the cooling flag."""
     n = len(tr_path)
 
     def matches(switch_at):
-        terms = orc.replay_single(g, cfg, dims, n, switch_at, eta, eta, False, cooling1, theta1)
+        terms = orc.replay_single(g, cfg, dims, n, switch_at, eta, eta, False, cooling1, theta1, frozen=frozen)
         ok = ((terms["path"] == tr_path) | (tr_path == UNKNOWN_PATH)) & (terms["pos_a"] == tr_a) & (terms["pos_b"] == tr_b)
         bad = np.nonzero(~ok)[0]
         return (n if bad.size == 0 else int(bad[0])), terms
@@ -122,12 +122,16 @@ def pin_2d(name, arrs, tmp, cooling_start, updates, tag):
         "init_seed": np.array([42], dtype=np.uint64), "X": res["X"], "Y": res["Y"]})
 
 
-def pin_1d(name, arrs, tmp, updates):
+def pin_1d(name, arrs, tmp, updates, freeze_mod=0):
     g = orc.Graph.from_arrays(arrs, use_xp_perm=True)
     out = os.path.join(tmp, "out1d.arr")
     eta = 50.0
     cfg = orc.default_sort_config(g, iter_max=2, min_term_updates=updates, eps=eta, eta_max=eta, cooling_start=0.0)
     kv = dict(threads=1, iter_max=2, updates=updates, eta_max=eta, eps=eta, cooling=0.0)
+    frozen = None
+    if freeze_mod:
+        kv["freeze_mod"] = freeze_mod
+        frozen = (np.arange(g.N) % freeze_mod == 0).astype(np.uint8)
     r = run([os.path.join(REF, "ref_driver_trace"), "sort", os.path.join(TEST, GRAPHS[name]), out] +
             [f"{k}={v}" for k, v in kv.items()], cwd=tmp)
     info = json.loads(r.stdout.strip().splitlines()[-1])
@@ -135,15 +139,19 @@ def pin_1d(name, arrs, tmp, updates):
     names = bytes(arrs["path_names"]).decode().split("\n")[:-1]
     tp, ta, tb = parse_trace(r.stderr, names)
     res = read_arrays(out)
-    k = align(g, cfg, 1, tp, ta, tb, eta, True, 0.001)
+    k = align(g, cfg, 1, tp, ta, tb, eta, True, 0.001, frozen)
     X = orc.sort_init(g)
-    terms = orc.replay_single(g, cfg, 1, len(tp), k, eta, eta, False, True, 0.001, X, None)
+    terms = orc.replay_single(g, cfg, 1, len(tp), k, eta, eta, False, True, 0.001, X, None, frozen=frozen)
     assert np.array_equal(terms["pos_a"], ta) and np.array_equal(terms["pos_b"], tb) and np.all((terms["path"] == tp) | (tp == UNKNOWN_PATH))
     exact = np.array_equal(X, res["X"])
-    print(f"[pin 1D] {name:10s}: {len(tp)} terms, checker switched at term {k}, trace bit-exact, final coords bit-exact: {exact}")
+    tag = f"pin1d_frozen{freeze_mod}" if freeze_mod else "pin1d"
+    print(f"[pin 1D] {name:10s} {tag}: {len(tp)} terms, checker switched at term {k}, trace bit-exact, final coords bit-exact: {exact}")
     if not exact:
         raise SystemExit("final 1D coordinates differ from the reference")
-    write_arrays(os.path.join(GOLD, f"{name}.pin1d.arr.gz"), {
+    if frozen is not None:
+        assert np.array_equal(X[frozen == 1], orc.sort_init(g)[frozen == 1])
+    write_arrays(os.path.join(GOLD, f"{name}.{tag}.arr.gz"), {
+        "freeze_mod": np.array([freeze_mod], dtype=np.uint64),
         "trace_path": tp.astype(np.uint32), "trace_pos_a": ta, "trace_pos_b": tb, "switch_at": np.array([k], dtype=np.uint64),
         "updates": np.array([updates], dtype=np.uint64), "eta": np.array([eta]), "X": res["X"]})
 
@@ -187,6 +195,8 @@ def main():
         for name in ("DRB1-3123", "LPA"):
             arrs = dump_graph(name, tmp)
             pin_1d(name, arrs, tmp, updates=8000)
+        pin_1d("DRB1-3123", dump_graph("DRB1-3123", tmp), tmp, updates=8000, freeze_mod=3)
+        pin_2d("LPA", dump_graph("LPA", tmp), tmp, cooling_start=0.5, updates=8000, tag="cool")
 
 
 if __name__ == "__main__":

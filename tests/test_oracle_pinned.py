@@ -51,7 +51,7 @@ def test_schedule_bit_exact(golden_dir):
         assert np.array_equal(ref, mine)
 
 
-@pytest.mark.parametrize("name,tag", [("DRB1-3123", "nocool"), ("DRB1-3123", "cool"), ("chr6.C4", "nocool"), ("chr6.C4", "cool")])
+@pytest.mark.parametrize("name,tag", [("DRB1-3123", "nocool"), ("DRB1-3123", "cool"), ("chr6.C4", "nocool"), ("chr6.C4", "cool"), ("LPA", "cool")])
 def test_2d_trace_and_coords_bit_exact(golden_dir, golden_graphs, name, tag):
     pin = _load(golden_dir, f"{name}.pin2d_{tag}.arr.gz")
     g = orc.Graph.from_arrays(golden_graphs[name], use_xp_perm=True)
@@ -81,6 +81,23 @@ def test_1d_trace_and_coords_bit_exact(golden_dir, golden_graphs, name):
     assert np.array_equal(terms["pos_a"], pin["trace_pos_a"])
     assert np.array_equal(terms["pos_b"], pin["trace_pos_b"])
     assert np.array_equal(X, pin["X"])
+
+
+def test_1d_frozen_nodes_bit_exact(golden_dir, golden_graphs):
+    """`odgi sort -H` semantics (target nodes stay put, path_sgd.cpp:290-302,387-392): reference run with every third
+    node frozen, replayed by the oracle — trace and final coordinates bit-exact; frozen nodes never moved."""
+    pin = _load(golden_dir, "DRB1-3123.pin1d_frozen3.arr.gz")
+    g = orc.Graph.from_arrays(golden_graphs["DRB1-3123"], use_xp_perm=True)
+    mod = int(pin["freeze_mod"][0])
+    frozen = (np.arange(g.N) % mod == 0).astype(np.uint8)
+    eta = float(pin["eta"][0])
+    cfg = orc.default_sort_config(g, iter_max=2, min_term_updates=int(pin["updates"][0]), eps=eta, eta_max=eta, cooling_start=0.0)
+    X = orc.sort_init(g)
+    n = len(pin["trace_pos_a"])
+    terms = orc.replay_single(g, cfg, 1, n, int(pin["switch_at"][0]), eta, eta, False, True, 0.001, X, None, frozen=frozen)
+    assert np.array_equal(terms["pos_a"], pin["trace_pos_a"]) and np.array_equal(terms["pos_b"], pin["trace_pos_b"])
+    assert np.array_equal(X, pin["X"])
+    assert np.array_equal(X[frozen == 1], orc.sort_init(g)[frozen == 1])
 
 
 def test_zipf_range_and_edge_cases():
