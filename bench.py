@@ -344,6 +344,14 @@ def main():
                      "kernel_ms": step_s * 1e3},
         "clocks": clocks, "wall_s_timed_region": wall,
     }
+    # the reference's own CUDA kernel (src/cuda/layout.cu recompiled for sm_100a), measured on this pool on the same graph:
+    # reported context, not a target (oracle/_ref/ref_gpu_driver; the driver needs the graph as GFA + odgi's ingest, minutes at c4)
+    rp = os.path.join(ROOT, "profiles", f"r01_reference_cuda_kernel_{args.workload}.json")
+    if os.path.exists(rp):
+        with open(rp) as f:
+            rk = json.load(f)
+        line["reference_cuda_kernel"] = {"value": rk["updates_per_sec"] / 1e6, "unit": "M updates/s", "n_gpus": 1,
+                                         "source": os.path.relpath(rp, ROOT), "note": "recorded measurement, not re-run by bench.py"}
     if quality:
         line["quality"] = quality
     if e2e:

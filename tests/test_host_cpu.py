@@ -41,3 +41,41 @@ def test_cli_refuses_without_gpu_flag_and_on_unoptimized_graph(tmp_path):
     assert r.returncode == 1 and "--gpu" in r.stderr
     r = subprocess.run([CLI, "flatten", "-i", str(gfa), "-o", str(tmp_path / "x.arr")], capture_output=True, text=True)
     assert r.returncode == 1 and "not optimized" in r.stderr
+
+
+def test_gfa_reader_details(tmp_path):
+    """S lines with '*' sequences and LN:i: tags, L lines and other records skipped, reverse steps, overlaps column absent."""
+    gfa = tmp_path / "g.gfa"
+    gfa.write_text("H\tVN:Z:1.0\n"
+                   "S\t1\tACGT\n"
+                   "S\t2\t*\tLN:i:7\n"
+                   "S\t3\tGG\tRC:i:4\n"
+                   "L\t1\t+\t2\t+\t0M\n"
+                   "W\tsample\t1\tchr\t0\t9\t>1>2\n"
+                   "P\tfwd\t1+,2+,3+\t*\n"
+                   "P\trev\t3-,2-,1-\n")
+    out = tmp_path / "g.arr"
+    subprocess.run([CLI, "flatten", "-i", str(gfa), "-o", str(out)], check=True, capture_output=True)
+    a = read_arrays(str(out))
+    assert a["node_len"].tolist() == [4, 7, 2]
+    assert a["path_first_step"].tolist() == [0, 3, 6]
+    assert a["step_node"].tolist() == [0, 1, 2, 2, 1, 0]
+    assert a["step_rev"].tolist() == [0, 0, 0, 1, 1, 1]
+    assert a["step_pos"].tolist() == [0, 4, 11, 0, 2, 9]
+    assert bytes(a["path_names"]).decode() == "fwd\nrev\n"
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` times the reference's CPU implementation (oracle/_ref when built, else the oracle port)
+    and prints ONE JSON line with the contract's keys; it needs no GPU."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "M updates/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
