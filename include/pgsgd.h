@@ -134,6 +134,15 @@ int pgsgd_layout_2d(const pgsgd_graph_view* g, const pgsgd_config* cfg, double* 
 int pgsgd_sort_1d(const pgsgd_graph_view* g, const pgsgd_config* cfg, const uint8_t* frozen, int x_is_initialised,
                   double* X, pgsgd_stats* stats);
 
+/* The same on n_gpus devices of ONE process (one host thread per GPU inside the call; multi_mode = PGSGD_MULTI_*): how a
+ * single-process host such as odgi uses a whole box.  pgsgd_layout_2d / pgsgd_sort_1d dispatch here when the environment
+ * variable PGSGD_GPUS is > 1 (PGSGD_MULTI = hybrid | allreduce | peer, default hybrid), so `PGSGD_GPUS=8 odgi layout --gpu`
+ * needs no source change. */
+int pgsgd_layout_2d_multi(const pgsgd_graph_view* g, const pgsgd_config* cfg, int n_gpus, int multi_mode, double* X, double* Y,
+                          pgsgd_stats* stats);
+int pgsgd_sort_1d_multi(const pgsgd_graph_view* g, const pgsgd_config* cfg, int n_gpus, int multi_mode, const uint8_t* frozen,
+                        int x_is_initialised, double* X, pgsgd_stats* stats);
+
 /* ---- engine API (graph stays resident in HBM; used by the one-shot calls, by bench.py and by multi-GPU runs) ---- */
 int  pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** out);
 void pgsgd_engine_destroy(pgsgd_engine* e);

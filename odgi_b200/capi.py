@@ -54,7 +54,8 @@ class StatsC(C.Structure):
 
 # every symbol include/pgsgd.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "pgsgd_last_error", "pgsgd_version", "pgsgd_device_count", "pgsgd_layout_2d", "pgsgd_sort_1d",
+    "pgsgd_last_error", "pgsgd_version", "pgsgd_device_count", "pgsgd_layout_2d", "pgsgd_sort_1d", "pgsgd_layout_2d_multi",
+    "pgsgd_sort_1d_multi",
     "pgsgd_engine_create", "pgsgd_engine_destroy", "pgsgd_engine_device", "pgsgd_engine_device_bytes",
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
@@ -77,6 +78,8 @@ def lib():
         L.pgsgd_device_count.restype = i32
         L.pgsgd_layout_2d.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), vp, vp, C.POINTER(StatsC)]
         L.pgsgd_sort_1d.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), vp, i32, vp, C.POINTER(StatsC)]
+        L.pgsgd_layout_2d_multi.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), i32, i32, vp, vp, C.POINTER(StatsC)]
+        L.pgsgd_sort_1d_multi.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), i32, i32, vp, i32, vp, C.POINTER(StatsC)]
         L.pgsgd_engine_create.argtypes = [C.POINTER(GraphView), i32, C.POINTER(vp)]
         L.pgsgd_engine_destroy.argtypes = [vp]
         L.pgsgd_engine_destroy.restype = None
@@ -373,6 +376,15 @@ def layout_2d(g: FlatGraph, cfg: Config, X, Y):
     Y = np.ascontiguousarray(Y, dtype=np.float64).copy()
     st, cc, gv = StatsC(), cfg.c(), g.view()
     _check(lib().pgsgd_layout_2d(C.byref(gv), C.byref(cc), _ptr(X), _ptr(Y), C.byref(st)))
+    return X, Y, st.as_dict()
+
+
+def layout_2d_multi(g: FlatGraph, cfg: Config, X, Y, n_gpus: int, multi_mode: int = 2):
+    """pgsgd_layout_2d_multi: one process, one host thread per GPU inside the call"""
+    X = np.ascontiguousarray(X, dtype=np.float64).copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).copy()
+    st, cc, gv = StatsC(), cfg.c(), g.view()
+    _check(lib().pgsgd_layout_2d_multi(C.byref(gv), C.byref(cc), n_gpus, multi_mode, _ptr(X), _ptr(Y), C.byref(st)))
     return X, Y, st.as_dict()
 
 

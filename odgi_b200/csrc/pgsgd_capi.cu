@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -255,22 +257,37 @@ int setup_peer(pgsgd_engine* e, int dims) {
         mine = e->d_x1d_part;
     }
     CU(cudaMemsetAsync(mine, 0, bytes, e->stream));
-    cudaIpcMemHandle_t h;
-    CU(cudaIpcGetMemHandle(&h, mine));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    // what every rank publishes about its slice: the CUDA IPC handle (other processes map it) and, for ranks that are
+    // threads of THIS process (single-process multi-GPU, e.g. the odgi shim), the raw pointer + device (peer access)
+    struct SliceInfo { cudaIpcMemHandle_t ipc; uint64_t pid; uint64_t ptr; int32_t device; int32_t pad; };
+    static_assert(sizeof(SliceInfo) == 88, "SliceInfo layout");
+    SliceInfo info;
+    memset(&info, 0, sizeof(info));
+    CU(cudaIpcGetMemHandle(&info.ipc, mine));
+    info.pid = (uint64_t) getpid();
+    info.ptr = (uint64_t) (uintptr_t) mine;
+    info.device = e->device;
     uint8_t* d_h = nullptr;
-    CU(cudaMalloc(&d_h, 64 * (size_t) (n + 1)));
-    CU(cudaMemcpyAsync(d_h, &h, 64, cudaMemcpyHostToDevice, e->stream));
-    NC(ncclAllGather(d_h, d_h + 64, 64, ncclUint8, e->comm, e->stream));
-    std::vector<cudaIpcMemHandle_t> all(n);
-    CU(cudaMemcpyAsync(all.data(), d_h + 64, 64 * (size_t) n, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMalloc(&d_h, sizeof(SliceInfo) * (size_t) (n + 1)));
+    CU(cudaMemcpyAsync(d_h, &info, sizeof(SliceInfo), cudaMemcpyHostToDevice, e->stream));
+    NC(ncclAllGather(d_h, d_h + sizeof(SliceInfo), sizeof(SliceInfo), ncclUint8, e->comm, e->stream));
+    std::vector<SliceInfo> all(n);
+    CU(cudaMemcpyAsync(all.data(), d_h + sizeof(SliceInfo), sizeof(SliceInfo) * (size_t) n, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     cudaFree(d_h);
     for (int q = 0; q < n; ++q) {
         void* ptr = mine;
         if (q != e->rank) {
-            CU(cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess));
-            e->ipc_opened.push_back(ptr);
+            if (all[q].pid == info.pid) {
+                // same process: the allocation is directly addressable once peer access is enabled
+                cudaError_t pe = cudaDeviceEnablePeerAccess(all[q].device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(PGSGD_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", all[q].device, cudaGetErrorString(pe));
+                cudaGetLastError();
+                ptr = (void*) (uintptr_t) all[q].ptr;
+            } else {
+                CU(cudaIpcOpenMemHandle(&ptr, all[q].ipc, cudaIpcMemLazyEnablePeerAccess));
+                e->ipc_opened.push_back(ptr);
+            }
         }
         if (dims == 2) e->peer_xy[q] = reinterpret_cast<float*>(ptr) - 4 * (ptrdiff_t) e->part_lo[q];
         else e->peer_x1d[q] = reinterpret_cast<double*>(ptr) - (ptrdiff_t) e->part_lo[q];
@@ -1117,8 +1134,82 @@ static int pick_device() {
     return s ? atoi(s) : 0;
 }
 
+// One process, n_gpus devices: one host thread per GPU runs the multi-rank sequence of INTEGRATION.md §5 (this is how a
+// single-process host such as odgi uses a whole box).  dims 2: X,Y [2N]; dims 1: X [N] (Y, frozen as in the 1-GPU calls).
+static int run_multi_in_process(const pgsgd_graph_view* g, const pgsgd_config* cfg, int dims, int n_gpus, int multi_mode,
+                                const uint8_t* frozen, int x_is_initialised, double* X, double* Y, pgsgd_stats* stats) {
+    uint8_t id[128];
+    int rc = pgsgd_comm_unique_id(id);
+    if (rc) return rc;
+    const uint64_t n_out = dims == 2 ? 2 * g->node_count : g->node_count;
+    std::vector<int> rcs(n_gpus, PGSGD_OK);
+    std::vector<std::string> errs(n_gpus);
+    std::vector<pgsgd_stats> sts(n_gpus);
+    std::vector<std::vector<double>> outX(n_gpus), outY(n_gpus);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < n_gpus; ++r) {
+        threads.emplace_back([&, r]() {
+            pgsgd_engine* e = nullptr;
+            int c = pgsgd_engine_create(g, r, &e);
+            if (!c) c = pgsgd_engine_attach_comm(e, id, n_gpus, r);
+            if (!c) c = pgsgd_engine_set_multi_mode(e, multi_mode);
+            if (!c) c = dims == 2 ? pgsgd_engine_set_coords_2d(e, X, Y) : pgsgd_engine_set_coords_1d(e, x_is_initialised ? X : nullptr);
+            if (!c && dims == 1) c = pgsgd_engine_set_frozen_1d(e, frozen);
+            memset(&sts[r], 0, sizeof(pgsgd_stats));
+            if (!c) c = dims == 2 ? pgsgd_engine_run_2d(e, cfg, &sts[r]) : pgsgd_engine_run_1d(e, cfg, &sts[r]);
+            if (!c) {
+                outX[r].resize(n_out);
+                if (dims == 2) { outY[r].resize(n_out); c = pgsgd_engine_get_coords_2d(e, outX[r].data(), outY[r].data()); }
+                else c = pgsgd_engine_get_coords_1d(e, outX[r].data());
+            }
+            if (c) errs[r] = pgsgd_last_error();
+            rcs[r] = c;
+            if (e) pgsgd_engine_destroy(e);
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (int r = 0; r < n_gpus; ++r) if (rcs[r]) return fail(rcs[r], "GPU %d: %s", r, errs[r].c_str());
+    memcpy(X, outX[0].data(), n_out * sizeof(double));
+    if (dims == 2) memcpy(Y, outY[0].data(), n_out * sizeof(double));
+    if (stats) {
+        *stats = sts[0];
+        for (int r = 1; r < n_gpus; ++r) {
+            stats->term_updates += sts[r].term_updates;
+            stats->kernel_launches += sts[r].kernel_launches;
+            if (sts[r].seconds_iterations > stats->seconds_iterations) stats->seconds_iterations = sts[r].seconds_iterations;
+        }
+    }
+    return PGSGD_OK;
+}
+
+static int env_gpus() {
+    const char* s = getenv("PGSGD_GPUS");
+    return s ? atoi(s) : 1;
+}
+static int env_multi_mode() {
+    const char* s = getenv("PGSGD_MULTI");
+    if (!s) return PGSGD_MULTI_HYBRID;
+    if (!strcmp(s, "allreduce")) return PGSGD_MULTI_ALLREDUCE;
+    if (!strcmp(s, "peer")) return PGSGD_MULTI_PEER;
+    return PGSGD_MULTI_HYBRID;
+}
+
+int pgsgd_layout_2d_multi(const pgsgd_graph_view* g, const pgsgd_config* cfg, int n_gpus, int multi_mode, double* X, double* Y, pgsgd_stats* stats) {
+    if (!g || !X || !Y) return fail(PGSGD_ERR_ARG, "pgsgd_layout_2d_multi: NULL argument");
+    if (n_gpus < 2 || n_gpus > pgsgd_device_count()) return fail(PGSGD_ERR_ARG, "n_gpus %d out of range (2..%d)", n_gpus, pgsgd_device_count());
+    return run_multi_in_process(g, cfg, 2, n_gpus, multi_mode, nullptr, 1, X, Y, stats);
+}
+
+int pgsgd_sort_1d_multi(const pgsgd_graph_view* g, const pgsgd_config* cfg, int n_gpus, int multi_mode, const uint8_t* frozen,
+                        int x_is_initialised, double* X, pgsgd_stats* stats) {
+    if (!g || !X) return fail(PGSGD_ERR_ARG, "pgsgd_sort_1d_multi: NULL argument");
+    if (n_gpus < 2 || n_gpus > pgsgd_device_count()) return fail(PGSGD_ERR_ARG, "n_gpus %d out of range (2..%d)", n_gpus, pgsgd_device_count());
+    return run_multi_in_process(g, cfg, 1, n_gpus, multi_mode, frozen, x_is_initialised, X, nullptr, stats);
+}
+
 int pgsgd_layout_2d(const pgsgd_graph_view* g, const pgsgd_config* cfg, double* X, double* Y, pgsgd_stats* stats) {
     if (!X || !Y) return fail(PGSGD_ERR_ARG, "pgsgd_layout_2d: X/Y are NULL");
+    if (env_gpus() > 1) return pgsgd_layout_2d_multi(g, cfg, env_gpus(), env_multi_mode(), X, Y, stats);   // PGSGD_GPUS=8 odgi layout --gpu
     pgsgd_engine* e = nullptr;
     int rc = pgsgd_engine_create(g, pick_device(), &e);
     if (rc) return rc;
@@ -1140,6 +1231,7 @@ int pgsgd_layout_2d(const pgsgd_graph_view* g, const pgsgd_config* cfg, double* 
 int pgsgd_sort_1d(const pgsgd_graph_view* g, const pgsgd_config* cfg, const uint8_t* frozen, int x_is_initialised, double* X,
                   pgsgd_stats* stats) {
     if (!X) return fail(PGSGD_ERR_ARG, "pgsgd_sort_1d: X is NULL");
+    if (env_gpus() > 1) return pgsgd_sort_1d_multi(g, cfg, env_gpus(), env_multi_mode(), frozen, x_is_initialised, X, stats);
     pgsgd_engine* e = nullptr;
     int rc = pgsgd_engine_create(g, pick_device(), &e);
     if (rc) return rc;

@@ -118,3 +118,54 @@ def test_two_rank_nccl_run_matches_emulation(tmp_path):
         assert abs(r["stress"] - b2["mean"]) <= 0.03 * b2["mean"], (tag, r["stress"], b2["mean"])
     b1 = bands["LPA.sort1d"]
     assert res["peer_1d"]["finite"] and abs(res["peer_1d"]["stress"] - b1["mean"]) <= 0.03 * b1["mean"] + 2 * b1["sd"], res
+
+
+INPROC = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.environ["PGSGD_ROOT"])
+import odgi_b200
+from odgi_b200 import capi
+from odgi_b200.arrays import read_arrays
+from oracle import oracle as orc
+a = read_arrays(os.path.join(os.environ["PGSGD_ROOT"], "tests/golden/DRB1-3123.graph.arr.gz"))
+gd, go = odgi_b200.graph_from_arrays(a), orc.Graph.from_arrays(a)
+X0, Y0 = orc.layout_init(go, 42)
+out = {}
+# strict single-stream ranks, all-reduce mode: identical to the oracle's emulation of the 2-rank schedule
+kw = dict(iter_max=4, min_term_updates=6000, eta_max=2000.0)
+cd = capi.layout_defaults(gd, n_streams=1, batch=1, sampling=capi.SAMPLING_STREAM, **kw)
+X, Y, st = odgi_b200.layout_2d_multi(gd, cd, X0, Y0, 2, capi.MULTI_ALLREDUCE)
+ref = orc.emulate_multirank_2d_f32(go, orc.default_layout_config(go, **kw), orc.XY_to_xy(X0, Y0), 2, 1, sum_deltas=False)
+Xr, Yr = orc.xy_to_XY(ref)
+out["allreduce_equal"] = bool(np.array_equal(X, Xr) and np.array_equal(Y, Yr))
+out["allreduce_updates"] = int(st["term_updates"])
+# default-shaped runs: threads of one process map each other's slices by peer access instead of CUDA IPC
+for tag, mode in (("peer", capi.MULTI_PEER), ("hybrid", capi.MULTI_HYBRID)):
+    X, Y, st = odgi_b200.layout_2d_multi(gd, capi.layout_defaults(gd), X0, Y0, 2, mode)
+    out[tag] = {"stress": orc.path_stress_2d(go, X, Y, 1000000, 12345), "updates": int(st["term_updates"]),
+                "finite": bool(np.all(np.isfinite(X)) and np.all(np.isfinite(Y)))}
+# the environment switch the odgi shim relies on: PGSGD_GPUS=2 turns the one-shot call into the in-process multi-GPU run
+os.environ["PGSGD_GPUS"] = "2"
+X, Y, st = odgi_b200.layout_2d(gd, capi.layout_defaults(gd), X0, Y0)
+out["env"] = {"stress": orc.path_stress_2d(go, X, Y, 1000000, 12345), "updates": int(st["term_updates"])}
+print("RESULT " + json.dumps(out))
+'''
+
+
+@pytest.mark.skipif(odgi_b200.device_count() < 2, reason="needs 2 GPUs")
+def test_single_process_two_gpus(tmp_path):
+    """pgsgd_layout_2d_multi: one host thread per GPU inside one call (how a single-process host such as odgi uses a box)."""
+    import json
+    script = tmp_path / "inproc.py"
+    script.write_text(INPROC)
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=dict(os.environ, PGSGD_ROOT=ROOT), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
+    assert res["allreduce_equal"] and res["allreduce_updates"] == 4 * 6000, res
+    with open(os.path.join(ROOT, "tests", "golden", "stress_reference.json")) as f:
+        b2 = json.load(f)["DRB1-3123.layout2d"]
+    for tag in ("peer", "hybrid", "env"):
+        r = res[tag]
+        assert abs(r["updates"] - 30 * 10 * 35059) <= 30 * 2048, res
+        assert abs(r["stress"] - b2["mean"]) <= 0.03 * b2["mean"], (tag, r["stress"], b2["mean"])
