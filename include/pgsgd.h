@@ -21,7 +21,9 @@
 extern "C" {
 #endif
 
-#define PGSGD_VERSION 100 /* 0.1.0 */
+/* Bumped whenever a struct below changes size or meaning.  Callers compare PGSGD_VERSION (what they were compiled against)
+ * with pgsgd_version() (what they loaded) before the first call: a stale binary would otherwise pass short structs. */
+#define PGSGD_VERSION 101 /* 0.1.1 */
 
 typedef enum pgsgd_status {
     PGSGD_OK = 0,

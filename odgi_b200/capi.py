@@ -63,6 +63,7 @@ EXPORTED_SYMBOLS = [
     "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_path_stress", "pgsgd_engine_order_1d", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
 ]
 
+ABI_VERSION = 101  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
 _lib = None
 
 
@@ -75,6 +76,9 @@ def lib():
         vp, u64, i32, dbl = C.c_void_p, C.c_uint64, C.c_int, C.c_double
         L.pgsgd_last_error.restype = C.c_char_p
         L.pgsgd_version.restype = i32
+        if L.pgsgd_version() != ABI_VERSION:
+            raise PgsgdError(-2, f"{LIB_PATH} has ABI {L.pgsgd_version()}, this binding mirrors include/pgsgd.h version {ABI_VERSION}: "
+                                 "rebuild with `python -m odgi_b200.build`")
         L.pgsgd_device_count.restype = i32
         L.pgsgd_layout_2d.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), vp, vp, C.POINTER(StatsC)]
         L.pgsgd_sort_1d.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), vp, i32, vp, C.POINTER(StatsC)]

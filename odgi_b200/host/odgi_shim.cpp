@@ -30,6 +30,14 @@ namespace {
     std::exit(EXIT_FAILURE);
 }
 
+void check_abi() {
+    // a shim compiled against another include/pgsgd.h than the library it loaded would pass structs of the wrong size
+    if (pgsgd_version() != PGSGD_VERSION) {
+        std::printf("Failed: libpgsgd_b200 ABI %d, this binary was built against %d: rebuild\n", pgsgd_version(), PGSGD_VERSION);
+        std::exit(EXIT_FAILURE);
+    }
+}
+
 pgsgd::FlatGraph flatten_or_exit(const odgi::graph_t& graph) {
     try {
         return pgsgd::flatten_handle_graph<odgi::graph_t, handlegraph::path_handle_t, handlegraph::step_handle_t>(graph);
@@ -47,6 +55,7 @@ void gpu_layout(layout_config_t config, const odgi::graph_t& graph, std::vector<
                 std::vector<std::atomic<double>>& Y) {
     std::cout << "===== Use GPU to compute odgi-layout =====" << std::endl;  // layout.cu:293
     const pgsgd::FlatGraph fg = flatten_or_exit(graph);
+    check_abi();
     pgsgd_config c{};
     c.iter_max = config.iter_max;
     c.iter_with_max_learning_rate = (uint64_t) config.iter_with_max_learning_rate;
@@ -88,6 +97,7 @@ std::vector<double> path_linear_sgd_gpu(const graph_t& graph, const xp::XP& /*pa
                                         const bool& /*snapshot*/, std::vector<std::string>& /*snapshots*/,
                                         const bool& target_sorting, std::vector<bool>& target_nodes) {
     const pgsgd::FlatGraph fg = flatten_or_exit(graph);
+    check_abi();
     pgsgd_config c{};
     c.iter_max = iter_max;
     c.iter_with_max_learning_rate = iter_with_max_learning_rate;

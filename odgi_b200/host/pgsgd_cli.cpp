@@ -142,6 +142,10 @@ void common_config(const Args& a, const pgsgd::FlatGraph& fg, bool is_sort, pgsg
 }
 
 int need_gpu(const Args& a, const char* sub) {
+    if (pgsgd_version() != PGSGD_VERSION) {
+        std::cerr << "[odgi::" << sub << "] error: libpgsgd_b200 ABI " << pgsgd_version() << ", this binary was built against " << PGSGD_VERSION << ": rebuild." << std::endl;
+        return 1;
+    }
     if (!a.has("gpu")) {
         std::cerr << "[odgi::" << sub << "] error: this build provides only the GPU path of the path-guided SGD; pass --gpu "
                      "(the CPU path is odgi's own: src/algorithms/path_sgd" << (std::string(sub) == "layout" ? "_layout" : "") << ".cpp)." << std::endl;

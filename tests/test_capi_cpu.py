@@ -27,7 +27,7 @@ def test_exports_every_declared_symbol():
     L = C.CDLL(capi.LIB_PATH)
     for s in declared:
         assert hasattr(L, s), s
-    assert L.pgsgd_version() == 100
+    assert L.pgsgd_version() == capi.ABI_VERSION
 
 
 def test_struct_sizes_match_header():
@@ -69,3 +69,11 @@ def test_argument_validation(golden_graphs):
     with pytest.raises(odgi_b200.PgsgdError) as ei:
         odgi_b200.Engine(bad)
     assert ei.value.code == -1
+
+
+def test_abi_version_is_one_number_everywhere():
+    """include/pgsgd.h, the ctypes binding and the loaded library agree (a stale caller would pass short structs)."""
+    import re
+    with open(os.path.join(ROOT, "include", "pgsgd.h")) as f:
+        m = re.search(r"#define\s+PGSGD_VERSION\s+(\d+)", f.read())
+    assert m and int(m.group(1)) == capi.ABI_VERSION == capi.lib().pgsgd_version()

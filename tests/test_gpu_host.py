@@ -75,3 +75,22 @@ def test_reference_call_chain_with_our_shim(drb1, tmp_path):
     b1 = _band("DRB1-3123.sort1d")
     s1 = orc.path_stress_1d(go, x, b1["n_pairs"], b1["seed"])
     assert abs(s1 - b1["mean"]) <= 0.03 * b1["mean"] + 2 * b1["sd"], (s1, b1["mean"])
+
+
+@pytest.mark.skipif(not os.path.exists(SHIM) or odgi_b200.device_count() < 2, reason="needs oracle/_ref/shim_driver and 2 GPUs")
+def test_reference_call_chain_on_two_gpus(drb1, tmp_path):
+    """The same unmodified reference call chain, one process, PGSGD_GPUS=2: the one-shot C-ABI call fans out over host threads."""
+    gfa, go = drb1
+    env = dict(os.environ, PGSGD_GPUS="2")
+    out = tmp_path / "shim2.arr"
+    subprocess.run([SHIM, "layout", gfa, str(out)], check=True, cwd=str(tmp_path), env=env, timeout=300)
+    r = read_arrays(str(out))
+    band = _band("DRB1-3123.layout2d")
+    s = orc.path_stress_2d(go, r["X"], r["Y"], band["n_pairs"], band["seed"])
+    assert abs(s - band["mean"]) <= 0.03 * band["mean"], (s, band["mean"])
+    out1 = tmp_path / "shim2_1d.arr"
+    subprocess.run([SHIM, "sort", gfa, str(out1)], check=True, cwd=str(tmp_path), env=env, timeout=300)
+    x = read_arrays(str(out1))["X"]
+    b1 = _band("DRB1-3123.sort1d")
+    s1 = orc.path_stress_1d(go, x, b1["n_pairs"], b1["seed"])
+    assert abs(s1 - b1["mean"]) <= 0.03 * b1["mean"] + 2 * b1["sd"], (s1, b1["mean"])
