@@ -46,7 +46,12 @@ GRAPHS = {
     "DRB1-3123": "DRB1-3123.gfa",
     "chr6.C4": "chr6.C4.gfa",
     "LPA": "LPA.gfa",
+    # small odd shapes: a single-step path and a node repeated back to back (overlap), a reverse-strand step (note5), two
+    # 10-step paths (k)
+    "overlap": "overlap.gfa",
+    "k": "k.gfa",
 }
+EDGE_GRAPHS = ("overlap", "k", "note5")
 
 
 def run(cmd, **kw):
@@ -170,7 +175,35 @@ def pin_schedule():
     print(f"[schedule] {len(cases)} schedules bit-exact vs path_linear_sgd_layout_schedule")
 
 
+def write_graph_fixture(name, arrs):
+    # integer half: our walk == XP's tables (pathindex.cpp:126-131 is the reference's own KAT for these)
+    assert np.array_equal(arrs["step_pos"], arrs["xp_position_of_step"])
+    assert np.array_equal((arrs["step_node"].astype(np.uint64) << np.uint64(1)) | arrs["step_rev"], arrs["xp_handle_of_step"])
+    assert np.array_equal(orc.positions_from_lengths(arrs["node_len"], arrs["path_first_step"], arrs["step_node"]), arrs["step_pos"])
+    keep = {k: arrs[k] for k in ("node_len", "path_first_step", "step_node", "step_rev", "step_pos", "path_names")}
+    keep["xp_nr_iv"] = arrs["xp_nr_iv"].astype(np.uint32)
+    keep["xp_npi_iv"] = arrs["xp_npi_iv"].astype(np.uint32)
+    keep["xp_path_id"] = arrs["xp_path_id"]
+    keep["xp_path_length"] = arrs["xp_path_length"]
+    write_arrays(os.path.join(GOLD, f"{name}.graph.arr.gz"), keep)
+    print(f"[graph] {name}: N={arrs['node_len'].size} P={arrs['path_first_step'].size - 1} S={arrs['step_node'].size} "
+          f"positions/handles identical to XP")
+
+
+def main_edge():
+    """`pin_oracle.py --edge`: only the small odd-shaped graphs (leaves the other fixtures untouched; the checker's switch
+    point is timing dependent, so a full re-run rewrites every trace)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in EDGE_GRAPHS:
+            arrs = dump_graph(name, tmp)
+            write_graph_fixture(name, arrs)
+            pin_2d(name, arrs, tmp, cooling_start=0.5, updates=3000, tag="cool")
+            pin_1d(name, arrs, tmp, updates=3000)
+
+
 def main():
+    if "--edge" in sys.argv[1:]:
+        return main_edge()
     os.makedirs(GOLD, exist_ok=True)
     pin_schedule()
     with tempfile.TemporaryDirectory() as tmp:

@@ -24,6 +24,6 @@ def golden_graphs():
     """name -> dict of arrays (flattened graph + XP sampling tables dumped by the reference)."""
     from odgi_b200.arrays import read_arrays
     out = {}
-    for name in ("note5", "t", "DRB1-3123", "chr6.C4", "LPA"):
+    for name in ("note5", "t", "overlap", "k", "DRB1-3123", "chr6.C4", "LPA"):
         out[name] = read_arrays(os.path.join(GOLDEN, f"{name}.graph.arr.gz"))
     return out

@@ -93,6 +93,37 @@ def test_2d_single_stream_bit_exact(graphs, name, flags):
 
 
 @pytest.mark.parametrize("flags", [0, capi.PGSGD_FLAG_EXCH_WRITE])
+@pytest.mark.parametrize("name", ["overlap", "k", "note5"])
+def test_odd_shaped_graphs_single_stream_bit_exact(graphs, name, flags):
+    """The reference's small test graphs with the corners of the path: a 1-step path and a node repeated back to back
+    (overlap.gfa: terms whose two ends are the SAME coordinate), two short paths (k.gfa), a reverse-strand step (note5.gfa).
+    The oracle is pinned on exactly these against the reference (tests/golden/{overlap,k,note5}.pin*)."""
+    gd, go = graphs[name]
+    kw = dict(iter_max=3, min_term_updates=2000, eta_max=50.0)
+    cd, co = _cfgs(gd, go, 2, **kw)
+    cd.n_streams, cd.batch, cd.flags = 1, 1, flags
+    X0, Y0 = orc.layout_init(go, seed=5)
+    xy0 = orc.XY_to_xy(X0, Y0)
+    n_ref, xy_ref = orc.layout_2d_f32(go, co, xy0.copy(), n_streams=1)
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_2d_f32(xy0)
+        st = e.run_2d(cd)
+        xy_dev = e.get_coords_2d_f32()
+    assert st["term_updates"] == n_ref == 3 * 2000
+    assert np.array_equal(xy_dev, xy_ref)
+    kw = dict(iter_max=2, min_term_updates=2000, eta_max=50.0)
+    cd, co = _cfgs(gd, go, 1, **kw)
+    cd.n_streams, cd.batch, cd.flags = 1, 1, flags
+    n_ref, x_ref = orc.sort_1d(go, co, orc.sort_init(go), n_streams=1)
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_1d(None)
+        st = e.run_1d(cd)
+        x_dev = e.get_coords_1d()
+    assert st["term_updates"] == n_ref == 3 * 2000
+    assert np.array_equal(x_dev, x_ref)
+
+
+@pytest.mark.parametrize("flags", [0, capi.PGSGD_FLAG_EXCH_WRITE])
 @pytest.mark.parametrize("name", ["LPA", "DRB1-3123"])
 def test_1d_single_stream_bit_exact(graphs, name, flags):
     gd, go = graphs[name]

@@ -51,7 +51,9 @@ def test_schedule_bit_exact(golden_dir):
         assert np.array_equal(ref, mine)
 
 
-@pytest.mark.parametrize("name,tag", [("DRB1-3123", "nocool"), ("DRB1-3123", "cool"), ("chr6.C4", "nocool"), ("chr6.C4", "cool"), ("LPA", "cool")])
+@pytest.mark.parametrize("name,tag", [("DRB1-3123", "nocool"), ("DRB1-3123", "cool"), ("chr6.C4", "nocool"), ("chr6.C4", "cool"), ("LPA", "cool"),
+                                      # odd shapes: single-step path + back-to-back repeat, two short paths, a reverse-strand step
+                                      ("overlap", "cool"), ("k", "cool"), ("note5", "cool")])
 def test_2d_trace_and_coords_bit_exact(golden_dir, golden_graphs, name, tag):
     pin = _load(golden_dir, f"{name}.pin2d_{tag}.arr.gz")
     g = orc.Graph.from_arrays(golden_graphs[name], use_xp_perm=True)
@@ -69,7 +71,7 @@ def test_2d_trace_and_coords_bit_exact(golden_dir, golden_graphs, name, tag):
     assert np.array_equal(X, pin["X"]) and np.array_equal(Y, pin["Y"])
 
 
-@pytest.mark.parametrize("name", ["DRB1-3123", "LPA"])
+@pytest.mark.parametrize("name", ["DRB1-3123", "LPA", "overlap", "k", "note5"])
 def test_1d_trace_and_coords_bit_exact(golden_dir, golden_graphs, name):
     pin = _load(golden_dir, f"{name}.pin1d.arr.gz")
     g = orc.Graph.from_arrays(golden_graphs[name], use_xp_perm=True)
