@@ -1,6 +1,6 @@
 // pgsgd_cli.cpp — `pgsgd layout|sort ... --gpu`: the `odgi layout` / `odgi sort -Y` command-line surface for the PG-SGD
 // path (same short/long flags and defaults: src/subcommand/layout_main.cpp:28-107,198-266; sort_main.cpp:313-414),
-// standalone: GFA in -> flattened graph -> C-ABI (include/pgsgd.h) -> TSV layout / node order out.
+// standalone: GFA in -> flattened graph -> C-ABI (include/pgsgd.h) -> .lay / TSV layout / node order out.
 // Everything that is not the PG-SGD path (the .og container, other sort pipelines, drawing) stays in odgi.
 #include <algorithm>
 #include <cmath>
@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "gfa_lite.hpp"
+#include "lay_format.hpp"
 #include "pgsgd_arrays.hpp"
 
 namespace {
@@ -161,12 +162,13 @@ int need_gpu(const Args& a, const char* sub) {
 int main_layout(int argc, char** argv) {
     Args a;
     if (!parse(argc, argv, LAYOUT_FLAGS, a, "layout") || a.has("help") || argc == 2) {
-        std::cout << "pgsgd layout -i g.gfa (-T out.tsv) --gpu [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-N d|r|u|g|h] [-t N] [-P]\n"
+        std::cout << "pgsgd layout -i g.gfa (-o out.lay | -T out.tsv) --gpu [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-N d|r|u|g|h] [-t N] [-P]\n"
                      "  the `odgi layout` PG-SGD flags with the same defaults; --seed N (worker streams), --init-seed N (layout initialisation)\n";
         return a.has("help") ? 0 : 1;
     }
     if (!a.has("idx")) { std::cerr << "[odgi::layout] error: Please specify an input file from where to load the graph via -i=[FILE], --idx=[FILE]." << std::endl; return 1; }
-    if (!a.has("tsv")) { std::cerr << "[odgi::layout] error: Please specify an output file to where to store the layout via -T/--tsv=[FILE] (the binary .lay container is written by odgi itself)." << std::endl; return 1; }
+    // layout_main.cpp:110-114
+    if (!a.has("tsv") && !a.has("out")) { std::cerr << "[odgi::layout] error: Please specify an output file to where to store the layout via -o/--out=[FILE], -T/--tsv=[FILE]" << std::endl; return 1; }
     if (int rc = need_gpu(a, "layout")) return rc;
     pgsgd::FlatGraph fg;
     try { fg = pgsgd::read_gfa_flat(a.str("idx")); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
@@ -218,17 +220,26 @@ int main_layout(int argc, char** argv) {
     for (uint64_t r = 0; r < N; ++r)
         for (uint64_t j = 2 * r; j <= 2 * r + 1; ++j) { X[j] -= x_off[comp[r]]; Y[j] += y_off[comp[r]]; }
     // layout::to_tsv (src/algorithms/layout.cpp:10-34): idx X Y component, two rows per node, grouped by component
-    std::ofstream fout;
-    std::ostream* out = &std::cout;
-    if (a.str("tsv") != "-") { fout.open(a.str("tsv")); out = &fout; }
-    *out << std::setprecision(std::numeric_limits<double>::digits10 + 1);
-    *out << "idx\tX\tY\tcomponent" << std::endl;
-    for (uint32_t k = 0; k < n_comp; ++k)
-        for (uint64_t r = 0; r < N; ++r) {
-            if (comp[r] != k) continue;
-            *out << 2 * r << "\t" << X[2 * r] << "\t" << Y[2 * r] << "\t" << k << '\n';
-            *out << 2 * r + 1 << "\t" << X[2 * r + 1] << "\t" << Y[2 * r + 1] << "\t" << k << '\n';
-        }
+    if (a.has("tsv")) {
+        std::ofstream fout;
+        std::ostream* out = &std::cout;
+        if (a.str("tsv") != "-") { fout.open(a.str("tsv")); out = &fout; }
+        *out << std::setprecision(std::numeric_limits<double>::digits10 + 1);
+        *out << "idx\tX\tY\tcomponent" << std::endl;
+        for (uint32_t k = 0; k < n_comp; ++k)
+            for (uint64_t r = 0; r < N; ++r) {
+                if (comp[r] != k) continue;
+                *out << 2 * r << "\t" << X[2 * r] << "\t" << Y[2 * r] << "\t" << k << '\n';
+                *out << 2 * r + 1 << "\t" << X[2 * r + 1] << "\t" << Y[2 * r + 1] << "\t" << k << '\n';
+            }
+    }
+    // the binary container `odgi draw` reads (layout_main.cpp:451-463, layout.cpp:43-61)
+    if (a.has("out")) {
+        try {
+            if (a.str("out") == "-") pgsgd::lay::write_lay(std::cout, X, Y);
+            else { std::ofstream f(a.str("out"), std::ios::binary); pgsgd::lay::write_lay(f, X, Y); }
+        } catch (const std::exception& e) { std::cerr << "[odgi::layout] error: " << e.what() << std::endl; return 1; }
+    }
     return 0;
 }
 
@@ -294,6 +305,44 @@ int main_flatten(int argc, char** argv) {
     return 0;
 }
 
+// pgsgd lay -i in.lay -T out.tsv      a .lay as `idx X Y` rows (Layout::to_tsv, layout.cpp:68-74)
+// pgsgd lay -i in.lay -a out.arr      ... or as a PGSGDARR container with X and Y
+// pgsgd lay -c xy.arr -o out.lay      a .lay from X and Y arrays (what `pgsgd layout -o` writes after the run)
+int main_lay(int argc, char** argv) {
+    std::string in, coords, tsv, arr, out;
+    for (int i = 2; i + 1 < argc; i += 2) {
+        if (!std::strcmp(argv[i], "-i")) in = argv[i + 1];
+        else if (!std::strcmp(argv[i], "-c")) coords = argv[i + 1];
+        else if (!std::strcmp(argv[i], "-T")) tsv = argv[i + 1];
+        else if (!std::strcmp(argv[i], "-a")) arr = argv[i + 1];
+        else if (!std::strcmp(argv[i], "-o")) out = argv[i + 1];
+    }
+    try {
+        std::vector<double> X, Y;
+        if (!in.empty()) {
+            std::ifstream f(in, std::ios::binary);
+            if (!f) throw std::runtime_error("cannot open " + in);
+            pgsgd::lay::read_lay(f, X, Y);
+        } else if (!coords.empty()) {
+            auto arrs = pgsgd::read_arrays(coords);
+            X = arrs.at("X").vec<double>();
+            Y = arrs.at("Y").vec<double>();
+        } else {
+            std::cerr << "usage: pgsgd lay (-i in.lay | -c xy.arr) [-T out.tsv] [-a out.arr] [-o out.lay]" << std::endl;
+            return 1;
+        }
+        if (!tsv.empty()) {
+            std::ofstream f(tsv);
+            f << std::setprecision(std::numeric_limits<double>::digits10 + 1);
+            f << "idx\tX\tY" << std::endl;
+            for (uint64_t i = 0; i < X.size(); ++i) f << i << "\t" << X[i] << "\t" << Y[i] << '\n';
+        }
+        if (!arr.empty()) { pgsgd::ArrayWriter w(arr); w.add("X", X); w.add("Y", Y); w.close(); }
+        if (!out.empty()) { std::ofstream f(out, std::ios::binary); pgsgd::lay::write_lay(f, X, Y); }
+    } catch (const std::exception& e) { std::cerr << "[pgsgd::lay] error: " << e.what() << std::endl; return 1; }
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -302,6 +351,7 @@ int main(int argc, char** argv) {
     if (sub == "layout") return main_layout(argc, argv);
     if (sub == "sort") return main_sort(argc, argv);
     if (sub == "flatten") return main_flatten(argc, argv);
-    std::cerr << "unknown subcommand " << sub << " (layout, sort)" << std::endl;
+    if (sub == "lay") return main_lay(argc, argv);
+    std::cerr << "unknown subcommand " << sub << " (layout, sort, flatten, lay)" << std::endl;
     return 1;
 }

@@ -19,6 +19,8 @@
 //   ref_driver layout <in.gfa> <init.arr|-> <out.arr> [k=v...]  2D PG-SGD (X,Y injected from init.arr)
 //   ref_driver sort   <in.gfa> <out.arr> [k=v...]               1D PG-SGD (+ order)
 //   ref_driver schedule <eta_max> <iter_max> <iter_lr> <eps>     the reference schedule as hex floats
+//   ref_driver lay_write <xy.arr> <out.lay>                      algorithms::layout::Layout(X, Y).serialize (layout.cpp:43-61)
+//   ref_driver lay_read  <in.lay> <out.arr>                      Layout::load + get_X / get_Y (layout.cpp:63-113)
 // keys: threads iter_max iter_lr updates_x (U = updates_x * sum steps) updates (absolute U) delta eps
 //       eta_max theta space space_max space_q cooling order(0/1) freeze_mod (sort: freeze every k-th node rank, as -H does for target paths)
 #include <atomic>
@@ -36,6 +38,8 @@
 #include "gfa_to_handle.hpp"
 #include "algorithms/xp.hpp"
 #include "algorithms/path_sgd_layout.hpp"
+#include "algorithms/layout.hpp"
+#include <fstream>
 
 #include "../../odgi_b200/host/pgsgd_arrays.hpp"
 
@@ -302,6 +306,27 @@ static int cmd_schedule(int argc, char** argv) {
     return 0;
 }
 
+// the .lay container exactly as `odgi layout -o` writes it / `odgi draw` reads it
+static int cmd_lay_write(int argc, char** argv) {
+    if (argc < 4) return 2;
+    auto arrs = pgsgd::read_arrays(argv[2]);
+    algorithms::layout::Layout lay(arrs.at("X").vec<double>(), arrs.at("Y").vec<double>());
+    std::ofstream f(argv[3], std::ios::binary);
+    lay.serialize(f);
+    return 0;
+}
+
+static int cmd_lay_read(int argc, char** argv) {
+    if (argc < 4) return 2;
+    algorithms::layout::Layout lay;
+    std::ifstream f(argv[2], std::ios::binary);
+    lay.load(f);
+    pgsgd::ArrayWriter w(argv[3]);
+    w.add("X", lay.get_X());
+    w.add("Y", lay.get_Y());
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) { std::cerr << "usage: ref_driver dump|layout|sort ..." << std::endl; return 2; }
     std::string cmd = argv[1];
@@ -310,6 +335,8 @@ int main(int argc, char** argv) {
         if (cmd == "layout") return cmd_layout(argc, argv);
         if (cmd == "sort") return cmd_sort(argc, argv);
         if (cmd == "schedule") return cmd_schedule(argc, argv);
+        if (cmd == "lay_write") return cmd_lay_write(argc, argv);
+        if (cmd == "lay_read") return cmd_lay_read(argc, argv);
     } catch (const std::exception& e) {
         std::cerr << "[ref_driver] error: " << e.what() << std::endl;
         return 1;

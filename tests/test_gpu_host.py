@@ -35,9 +35,15 @@ def drb1(golden_graphs, tmp_path_factory):
 def test_cli_layout_tsv(drb1, tmp_path):
     gfa, go = drb1
     tsv = tmp_path / "lay.tsv"
-    subprocess.run([CLI, "layout", "-i", gfa, "-T", str(tsv), "--gpu", "--init-seed", "42", "-P"], check=True)
+    lay = tmp_path / "lay.lay"
+    subprocess.run([CLI, "layout", "-i", gfa, "-T", str(tsv), "-o", str(lay), "--gpu", "--init-seed", "42", "-P"], check=True)
     rows = np.loadtxt(str(tsv), skiprows=1)
     assert rows.shape == (2 * go.N, 4) and np.array_equal(rows[:, 0], np.arange(2 * go.N))
+    # the binary container holds the same coordinates (writer is byte-identical to odgi's: tests/test_host_cpu.py)
+    back = tmp_path / "back.arr"
+    subprocess.run([CLI, "lay", "-i", str(lay), "-a", str(back)], check=True)
+    b = read_arrays(str(back))
+    assert np.allclose(b["X"], rows[:, 1], rtol=1e-12, atol=1e-6) and np.allclose(b["Y"], rows[:, 2], rtol=1e-12, atol=1e-6)
     band = _band("DRB1-3123.layout2d")
     s = orc.path_stress_2d(go, rows[:, 1], rows[:, 2], band["n_pairs"], band["seed"])
     assert abs(s - band["mean"]) <= 0.03 * band["mean"], (s, band["mean"])

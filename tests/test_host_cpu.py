@@ -79,3 +79,46 @@ def test_bench_reference_arm_runs_on_cpu():
     assert d["impl"] == "reference" and d["unit"] == "M updates/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+LAY_CASES = ["gauss300", "one", "n64", "n65", "repeats", "monotone"]
+
+
+@pytest.mark.parametrize("name", LAY_CASES)
+def test_lay_writer_is_byte_identical_to_the_reference(golden_dir, tmp_path, name):
+    """`.lay` (layout.cpp:43-61 = min_value + sdsl::enc_vector<> of bit-cast doubles) restated without sdsl:
+    tests/golden/lay_*.lay were written by the reference's own Layout::serialize (scripts/make_lay_golden.py)."""
+    from odgi_b200.arrays import write_arrays
+    a = read_arrays(os.path.join(golden_dir, f"lay_{name}.arr.gz"))
+    plain = tmp_path / "xy.arr"
+    write_arrays(str(plain), {"X": a["X"], "Y": a["Y"]})
+    out = tmp_path / "mine.lay"
+    subprocess.run([CLI, "lay", "-c", str(plain), "-o", str(out)], check=True)
+    with open(os.path.join(golden_dir, f"lay_{name}.lay"), "rb") as f:
+        assert out.read_bytes() == f.read()
+
+
+@pytest.mark.parametrize("name", LAY_CASES)
+def test_lay_reader_returns_what_layout_get_x_returns(golden_dir, tmp_path, name):
+    """Layout::get_x / get_y (layout.cpp:86-97): (X - min_value) + min_value, in that order of fp64 operations."""
+    a = read_arrays(os.path.join(golden_dir, f"lay_{name}.arr.gz"))
+    back, tsv = tmp_path / "back.arr", tmp_path / "back.tsv"
+    subprocess.run([CLI, "lay", "-i", os.path.join(golden_dir, f"lay_{name}.lay"), "-a", str(back), "-T", str(tsv)], check=True)
+    b = read_arrays(str(back))
+    m = min(a["X"].min(), a["Y"].min())
+    assert np.array_equal(b["X"], (a["X"] - m) + m) and np.array_equal(b["Y"], (a["Y"] - m) + m)
+    rows = np.loadtxt(str(tsv), skiprows=1, ndmin=2)   # Layout::to_tsv: idx X Y with 16 significant digits
+    assert rows.shape == (a["X"].size, 3) and np.array_equal(rows[:, 0], np.arange(a["X"].size))
+    assert np.allclose(rows[:, 1], b["X"], rtol=1e-15, atol=0) and np.allclose(rows[:, 2], b["Y"], rtol=1e-15, atol=0)
+
+
+def test_lay_reader_rejects_garbage(tmp_path):
+    bad = tmp_path / "bad.lay"
+    bad.write_bytes(b"\x00" * 7)
+    r = subprocess.run([CLI, "lay", "-i", str(bad), "-a", str(tmp_path / "x.arr")], capture_output=True, text=True)
+    assert r.returncode == 1 and "truncated" in r.stderr
+    with open(os.path.join(ROOT, "tests", "golden", "lay_gauss300.lay"), "rb") as f:
+        data = f.read()
+    bad.write_bytes(data[: len(data) // 2])
+    r = subprocess.run([CLI, "lay", "-i", str(bad), "-a", str(tmp_path / "x.arr")], capture_output=True, text=True)
+    assert r.returncode == 1 and "lay:" in r.stderr
