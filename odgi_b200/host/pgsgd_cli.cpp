@@ -47,7 +47,7 @@ const Flag SORT_FLAGS[] = {
     {"v", "path-sgd-eta-max", true}, {"a", "path-sgd-zipf-theta", true}, {"x", "path-sgd-iter-max", true}, {"K", "path-sgd-cooling", true},
     {"F", "path-sgd-iteration-max-learning-rate", true}, {"k", "path-sgd-zipf-space", true}, {"I", "path-sgd-zipf-space-max", true},
     {"l", "path-sgd-zipf-space-quantization-step", true}, {"t", "threads", true}, {"", "gpu", false}, {"P", "progress", false},
-    {"h", "help", false}, {"", "seed", true}, {"", "sampling", true}, {"", "layout-out", true}};
+    {"h", "help", false}, {"", "seed", true}, {"", "sampling", true}, {"", "layout-out", true}, {"e", "path-sgd-layout", true}};
 
 template <size_t NF>
 bool parse(int argc, char** argv, const Flag (&flags)[NF], Args& a, const char* sub) {
@@ -246,7 +246,7 @@ int main_layout(int argc, char** argv) {
 int main_sort(int argc, char** argv) {
     Args a;
     if (!parse(argc, argv, SORT_FLAGS, a, "sort") || a.has("help") || argc == 2) {
-        std::cout << "pgsgd sort -i g.gfa -o order.txt -Y --gpu [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-t N] [-P]\n"
+        std::cout << "pgsgd sort -i g.gfa -o order.txt [-e sorted.lay] -Y --gpu [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-t N] [-P]\n"
                      "  the `odgi sort -Y` PG-SGD flags with the same defaults; writes the node order (one node id per line) that\n"
                      "  path_linear_sgd_order derives (sorted by position, then handle); odgi applies it with apply_ordering.\n";
         return a.has("help") ? 0 : 1;
@@ -277,6 +277,15 @@ int main_sort(int argc, char** argv) {
         std::ofstream l(a.str("layout-out"));
         l << std::setprecision(std::numeric_limits<double>::digits10 + 1) << "node\tstart\tend\n";
         for (uint64_t r : order) l << r + 1 << "\t" << X[r] << "\t" << X[r] + (double) fg.node_len[r] << '\n';
+    }
+    if (a.has("path-sgd-layout")) {  // -e in odgi sort: the same as a .lay, X = (start, start + length) per sorted node, Y = 0 (path_sgd.cpp:659-677)
+        std::vector<double> sorted_layout(2 * N), dummy(2 * N, 0.0);
+        for (uint64_t i = 0; i < N; ++i) {
+            sorted_layout[2 * i] = X[order[i]];
+            sorted_layout[2 * i + 1] = X[order[i]] + (double) fg.node_len[order[i]];
+        }
+        try { std::ofstream l(a.str("path-sgd-layout"), std::ios::binary); pgsgd::lay::write_lay(l, sorted_layout, dummy); }
+        catch (const std::exception& e) { std::cerr << "[odgi::sort] error: " << e.what() << std::endl; return 1; }
     }
     return 0;
 }

@@ -52,10 +52,17 @@ def test_cli_layout_tsv(drb1, tmp_path):
 def test_cli_sort_order(drb1, tmp_path):
     gfa, go = drb1
     out, lay = tmp_path / "order.txt", tmp_path / "lay1d.tsv"
-    subprocess.run([CLI, "sort", "-i", gfa, "-o", str(out), "-Y", "--gpu", "--layout-out", str(lay)], check=True)
+    lay_bin = tmp_path / "sorted.lay"
+    subprocess.run([CLI, "sort", "-i", gfa, "-o", str(out), "-Y", "--gpu", "--layout-out", str(lay), "-e", str(lay_bin)], check=True)
     order = np.loadtxt(str(out), dtype=np.int64)
     assert np.array_equal(np.sort(order), np.arange(1, go.N + 1))
     rows = np.loadtxt(str(lay), skiprows=1)
+    # -e: the 1D layout as a .lay, (start, start + length) per sorted node on X and zeros on Y (path_sgd.cpp:659-677)
+    back = tmp_path / "sorted.arr"
+    subprocess.run([CLI, "lay", "-i", str(lay_bin), "-a", str(back)], check=True)
+    b = read_arrays(str(back))
+    assert b["X"].size == 2 * go.N and not b["Y"].any()
+    assert np.allclose(b["X"][0::2], rows[:, 1], rtol=1e-12, atol=1e-6) and np.allclose(b["X"][1::2], rows[:, 2], rtol=1e-12, atol=1e-6)
     x = np.empty(go.N)
     x[rows[:, 0].astype(np.int64) - 1] = rows[:, 1]
     assert np.array_equal(order - 1, orc.order_from_x(x).astype(np.int64))  # the reference's (pos, handle) sort on the same X
