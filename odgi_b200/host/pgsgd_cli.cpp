@@ -159,6 +159,55 @@ int need_gpu(const Args& a, const char* sub) {
     return 0;
 }
 
+// Hilbert curve: distance d along the curve -> cell (x, y).  The reference walks quadrant sizes s = 1, 2, 4, ... < n
+// with n = 2 * node count, not rounded to a power of two (src/algorithms/hilbert.hpp:30-41, layout_main.cpp:287,312-318).
+void hilbert_d2xy(uint64_t n, uint64_t d, uint64_t& x, uint64_t& y) {
+    x = y = 0;
+    for (uint64_t s = 1, t = d; s < n; s <<= 1, t >>= 2) {
+        const uint64_t rx = (t >> 1) & 1, ry = (t ^ rx) & 1;
+        if (ry == 0) {
+            if (rx == 1) { x = s - 1 - x; y = s - 1 - y; }
+            std::swap(x, y);
+        }
+        x += s * rx;
+        y += s * ry;
+    }
+}
+
+// the five coordinate initialisations of `odgi layout -N` (layout_main.cpp:268-330); the reference seeds its mt19937 from
+// std::random_device, --init-seed makes runs reproducible
+bool init_layout(const pgsgd::FlatGraph& fg, char mode, bool seeded, uint64_t seed, std::vector<double>& X, std::vector<double>& Y) {
+    const uint64_t N = fg.node_len.size();
+    X.assign(2 * N, 0.0);
+    Y.assign(2 * N, 0.0);
+    std::mt19937 rng(seeded ? (uint32_t) seed : std::random_device{}());
+    std::uniform_real_distribution<double> uniform_noise(0, std::sqrt((double) N * 2));
+    std::normal_distribution<double> gaussian_noise(0, std::sqrt((double) N * 2));
+    uint64_t total_length = 0;
+    for (uint32_t l : fg.node_len) total_length += l;
+    std::uniform_real_distribution<double> uniform_noise_in_length(0, (double) total_length);
+    uint64_t len = 0;
+    for (uint64_t r = 0; r < N; ++r) {
+        const uint64_t pos = 2 * r;
+        switch (mode) {
+            case 'g': X[pos] = gaussian_noise(rng); Y[pos] = gaussian_noise(rng); X[pos + 1] = gaussian_noise(rng); Y[pos + 1] = gaussian_noise(rng); break;
+            case 'u': X[pos] = (double) len; Y[pos] = uniform_noise(rng); len += fg.node_len[r]; X[pos + 1] = (double) len; Y[pos + 1] = uniform_noise(rng); break;
+            case 'r': X[pos] = uniform_noise_in_length(rng); Y[pos] = uniform_noise_in_length(rng); X[pos + 1] = uniform_noise_in_length(rng); Y[pos + 1] = uniform_noise_in_length(rng); break;
+            case 'h': {
+                uint64_t x, y;
+                hilbert_d2xy(2 * N, pos, x, y); X[pos] = (double) x; Y[pos] = (double) y;
+                hilbert_d2xy(2 * N, pos + 1, x, y); X[pos + 1] = (double) x; Y[pos + 1] = (double) y;
+                break;
+            }
+            case 'd': X[pos] = (double) len; Y[pos] = gaussian_noise(rng); len += fg.node_len[r]; X[pos + 1] = (double) len; Y[pos + 1] = gaussian_noise(rng); break;
+            default:
+                std::cerr << "[odgi::layout] error: unknown layout initialization '" << mode << "' (d, r, u, g, h)." << std::endl;
+                return false;
+        }
+    }
+    return true;
+}
+
 int main_layout(int argc, char** argv) {
     Args a;
     if (!parse(argc, argv, LAYOUT_FLAGS, a, "layout") || a.has("help") || argc == 2) {
@@ -175,26 +224,8 @@ int main_layout(int argc, char** argv) {
     pgsgd_config c;
     common_config(a, fg, false, c);
     const uint64_t N = fg.node_len.size();
-    std::vector<double> X(2 * N), Y(2 * N);
-    // layout_main.cpp:268-330 — the reference seeds from std::random_device; --init-seed makes runs reproducible
-    std::mt19937 rng(a.has("init-seed") ? (uint32_t) a.u64("init-seed", 0) : std::random_device{}());
-    std::uniform_real_distribution<double> uniform_noise(0, std::sqrt((double) N * 2));
-    std::normal_distribution<double> gaussian_noise(0, std::sqrt((double) N * 2));
-    uint64_t total_length = 0;
-    for (uint32_t l : fg.node_len) total_length += l;
-    std::uniform_real_distribution<double> uniform_noise_in_length(0, (double) total_length);
-    const char init = a.str("layout-initialization", "d")[0];
-    uint64_t len = 0;
-    for (uint64_t r = 0; r < N; ++r) {
-        const uint64_t pos = 2 * r;
-        switch (init) {
-            case 'g': X[pos] = gaussian_noise(rng); Y[pos] = gaussian_noise(rng); X[pos + 1] = gaussian_noise(rng); Y[pos + 1] = gaussian_noise(rng); break;
-            case 'u': X[pos] = (double) len; Y[pos] = uniform_noise(rng); len += fg.node_len[r]; X[pos + 1] = (double) len; Y[pos + 1] = uniform_noise(rng); break;
-            case 'r': X[pos] = uniform_noise_in_length(rng); Y[pos] = uniform_noise_in_length(rng); X[pos + 1] = uniform_noise_in_length(rng); Y[pos + 1] = uniform_noise_in_length(rng); break;
-            case 'h': std::cerr << "[odgi::layout] error: the Hilbert initialisation is not available in this build." << std::endl; return 1;
-            default: X[pos] = (double) len; Y[pos] = gaussian_noise(rng); len += fg.node_len[r]; X[pos + 1] = (double) len; Y[pos + 1] = gaussian_noise(rng);
-        }
-    }
+    std::vector<double> X, Y;
+    if (!init_layout(fg, a.str("layout-initialization", "d")[0], a.has("init-seed"), a.u64("init-seed", 0), X, Y)) return 1;
     pgsgd_stats st;
     const pgsgd_graph_view v = fg.view();
     if (pgsgd_layout_2d(&v, &c, X.data(), Y.data(), &st) != PGSGD_OK) { std::cerr << "[odgi::layout] error: " << pgsgd_last_error() << std::endl; return 1; }
@@ -314,6 +345,27 @@ int main_flatten(int argc, char** argv) {
     return 0;
 }
 
+// pgsgd init -i g.gfa -N d|r|u|g|h [--init-seed S] -a out.arr : the coordinates `pgsgd layout` would start from
+int main_init(int argc, char** argv) {
+    std::string in, arr, mode = "d", seed;
+    for (int i = 2; i + 1 < argc; i += 2) {
+        if (!std::strcmp(argv[i], "-i")) in = argv[i + 1];
+        else if (!std::strcmp(argv[i], "-a")) arr = argv[i + 1];
+        else if (!std::strcmp(argv[i], "-N")) mode = argv[i + 1];
+        else if (!std::strcmp(argv[i], "--init-seed")) seed = argv[i + 1];
+    }
+    if (in.empty() || arr.empty() || mode.empty()) { std::cerr << "usage: pgsgd init -i g.gfa -N d|r|u|g|h [--init-seed S] -a out.arr" << std::endl; return 1; }
+    pgsgd::FlatGraph fg;
+    try { fg = pgsgd::read_gfa_flat(in); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
+    std::vector<double> X, Y;
+    if (!init_layout(fg, mode[0], !seed.empty(), seed.empty() ? 0 : std::stoull(seed), X, Y)) return 1;
+    pgsgd::ArrayWriter w(arr);
+    w.add("X", X);
+    w.add("Y", Y);
+    w.close();
+    return 0;
+}
+
 // pgsgd lay -i in.lay -T out.tsv      a .lay as `idx X Y` rows (Layout::to_tsv, layout.cpp:68-74)
 // pgsgd lay -i in.lay -a out.arr      ... or as a PGSGDARR container with X and Y
 // pgsgd lay -c xy.arr -o out.lay      a .lay from X and Y arrays (what `pgsgd layout -o` writes after the run)
@@ -361,6 +413,7 @@ int main(int argc, char** argv) {
     if (sub == "sort") return main_sort(argc, argv);
     if (sub == "flatten") return main_flatten(argc, argv);
     if (sub == "lay") return main_lay(argc, argv);
-    std::cerr << "unknown subcommand " << sub << " (layout, sort, flatten, lay)" << std::endl;
+    if (sub == "init") return main_init(argc, argv);
+    std::cerr << "unknown subcommand " << sub << " (layout, sort, flatten, lay, init)" << std::endl;
     return 1;
 }

@@ -122,3 +122,40 @@ def test_lay_reader_rejects_garbage(tmp_path):
     bad.write_bytes(data[: len(data) // 2])
     r = subprocess.run([CLI, "lay", "-i", str(bad), "-a", str(tmp_path / "x.arr")], capture_output=True, text=True)
     assert r.returncode == 1 and "lay:" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["t", "overlap", "DRB1-3123", "LPA"])
+def test_hilbert_initialisation_matches_the_reference(golden_dir, golden_graphs, tmp_path, name):
+    """`-N h`: d2xy(2N, 2r), d2xy(2N, 2r+1) per node rank r, with the reference's non-power-of-two side length
+    (tests/golden/hilbert.json holds the reference function's output, scripts/make_hilbert_golden.py)."""
+    import hashlib
+    import json
+    g = odgi_b200.graph_from_arrays(golden_graphs[name])
+    gfa, arr = tmp_path / "g.gfa", tmp_path / "init.arr"
+    synth.write_gfa(g, str(gfa))
+    subprocess.run([CLI, "init", "-i", str(gfa), "-N", "h", "-a", str(arr)], check=True)
+    b = read_arrays(str(arr))
+    with open(os.path.join(golden_dir, "hilbert.json")) as f:
+        gold = json.load(f)[str(2 * g.N)]
+    text = "".join(f"{int(x)} {int(y)}\n" for x, y in zip(b["X"], b["Y"]))
+    assert hashlib.sha256(text.encode()).hexdigest() == gold["sha256"]
+    pts = np.array(gold["points"], dtype=np.float64)
+    assert np.array_equal(b["X"][: len(pts)], pts[:, 0]) and np.array_equal(b["Y"][: len(pts)], pts[:, 1])
+
+
+def test_default_initialisation_shape(golden_graphs, tmp_path):
+    """`-N d` (layout_main.cpp:322-328): X = cumulative bp at both node ends, Y ~ N(0, sqrt(2N)); seeded runs repeat."""
+    a = golden_graphs["DRB1-3123"]
+    g = odgi_b200.graph_from_arrays(a)
+    gfa = tmp_path / "g.gfa"
+    synth.write_gfa(g, str(gfa))
+    outs = []
+    for k in range(2):
+        arr = tmp_path / f"init{k}.arr"
+        subprocess.run([CLI, "init", "-i", str(gfa), "-N", "d", "--init-seed", "42", "-a", str(arr)], check=True)
+        outs.append(read_arrays(str(arr)))
+    cs = np.cumsum(a["node_len"].astype(np.float64))
+    assert np.array_equal(outs[0]["X"][1::2], cs) and np.array_equal(outs[0]["X"][2::2], cs[:-1]) and outs[0]["X"][0] == 0
+    assert np.array_equal(outs[0]["Y"], outs[1]["Y"]) and abs(outs[0]["Y"].std() / np.sqrt(2 * g.N) - 1) < 0.05
+    r = subprocess.run([CLI, "init", "-i", str(gfa), "-N", "z", "-a", str(tmp_path / "z.arr")], capture_output=True, text=True)
+    assert r.returncode == 1 and "unknown layout initialization" in r.stderr
