@@ -109,7 +109,7 @@ def make_workload(name: str):
     return g, desc
 
 
-def cpu_baseline(workload: str, threads: int, seconds_budget: float = 25.0):
+def cpu_baseline(workload: str, threads: int, iters: int = 2, warmup_iters: int = 0):
     """Reference CPU implementation on the host cores, on a bounded sample of the workload.
     kind 'reference' = the unmodified reference compiled into oracle/_ref (std::thread workers, -Ofast);
     falls back to kind 'port' (the oracle's C restatement, one core) when oracle/_ref was not built."""
@@ -121,25 +121,28 @@ def cpu_baseline(workload: str, threads: int, seconds_budget: float = 25.0):
         n_sites, n_paths = synth.PRESETS[workload]
         n_sites = min(n_sites, 30_000)  # bounded sample: same generator, same haplotype count, fewer sites
         g = synth.generate(n_sites, n_paths, seed=42)
-        sample = f"same generator, {n_paths} paths x {n_sites} sites (S={g.S}), 2 iterations of 10*S updates"
+        sample = f"same generator, {n_paths} paths x {n_sites} sites (S={g.S}), {iters} iterations of 10*S updates"
     else:
         import odgi_b200
         g = odgi_b200.load_graph_arrays(os.path.join(ROOT, "tests", "golden", f"{workload}.graph.arr.gz"))
-        sample = f"the whole graph (S={g.S}), 2 iterations of 10*S updates"
+        sample = f"the whole graph (S={g.S}), {iters} iterations of 10*S updates"
     if os.path.exists(ref):
         with tempfile.TemporaryDirectory() as tmp:
             gfa = os.path.join(tmp, "sample.gfa")
             synth.write_gfa(g, gfa)
             out = os.path.join(tmp, "o.arr")
-            r = subprocess.run([ref, "layout", gfa, "-", out, f"threads={threads}", "iter_max=2"], cwd=tmp, capture_output=True,
+            if warmup_iters:  # untimed: page cache, CPU clocks
+                subprocess.run([ref, "layout", gfa, "-", out, f"threads={threads}", f"iter_max={warmup_iters}"], cwd=tmp, capture_output=True,
                                text=True, timeout=600)
+            r = subprocess.run([ref, "layout", gfa, "-", out, f"threads={threads}", f"iter_max={iters}"], cwd=tmp, capture_output=True,
+                               text=True, timeout=1200)
             if r.returncode == 0:
                 info = json.loads(r.stdout.strip().splitlines()[-1])
                 return {"value": info["updates_per_sec"] / 1e6, "unit": "M updates/s", "cores": threads, "kind": "reference",
                         "sample": sample + f"; {os.path.basename(ref)} (reference sources, -Ofast)", "seconds": info["seconds"]}
     from oracle import oracle as orc
     go = orc.Graph(g.node_len, g.path_first_step, g.step_node, g.step_rev)
-    cfg = orc.default_layout_config(go, iter_max=2)
+    cfg = orc.default_layout_config(go, iter_max=iters)
     X, Y = orc.layout_init(go, 42)
     t0 = time.time()
     n, _, _ = orc.layout_2d(go, cfg, X, Y, n_streams=1)
@@ -153,11 +156,13 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # each step = one iteration over a bounded sample of the workload (same generator, same haplotype count)
+    # each step = one iteration (10*S updates) over a bounded sample of the workload (same generator, same haplotype count,
+    # fewer sites): W untimed iterations, then K timed ones; the reference times its own SGD loop (graph load excluded)
     t0 = time.time()
-    cb = cpu_baseline(args.workload, threads)
+    iters = max(2, args.steps)   # the reference's schedule divides by iter_max - 1
+    cb = cpu_baseline(args.workload, threads, iters=iters, warmup_iters=max(0, min(args.warmup, 3)))
     line = {"impl": "reference", "metric": "M node-pair SGD updates/sec", "value": cb["value"], "unit": "M updates/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds"] / iters * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "sample": cb["sample"]},
             "cpu_baseline": {"value": cb["value"], "unit": cb["unit"], "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
