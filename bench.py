@@ -326,7 +326,7 @@ def main():
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cb = cpu_baseline(args.workload, os.cpu_count() or 1)
+            cb = cpu_baseline(args.workload, os.cpu_count() or 1, iters=10)   # ~10-30 s of host CPU work
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
             cb = {"value": None, "unit": "M updates/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
     line = {
