@@ -42,6 +42,7 @@
 #include <fstream>
 
 #include "../../odgi_b200/host/pgsgd_arrays.hpp"
+#include "../../odgi_b200/host/pgsgd_flatten.hpp"
 
 using namespace odgi;
 
@@ -159,7 +160,14 @@ static int cmd_dump(int argc, char** argv) {
             xp_handle.push_back(as_integer(L.xp.get_handle_of_step(s)));
         }
     }
+    // the product's own walk over the reference's graph_t (the template the odgi shim instantiates): must equal both
+    const pgsgd::FlatGraph shim = pgsgd::flatten_handle_graph<graph_t, path_handle_t, step_handle_t>(L.graph);
     pgsgd::ArrayWriter w(argv[3]);
+    w.add("shim_node_len", shim.node_len);
+    w.add("shim_path_first_step", shim.path_first_step);
+    w.add("shim_step_node", shim.step_node);
+    w.add("shim_step_rev", shim.step_rev);
+    w.add("shim_step_pos", shim.step_pos);
     w.add("node_len", node_len);
     w.add("path_first_step", path_first);
     w.add("step_node", step_node);

@@ -180,6 +180,9 @@ def write_graph_fixture(name, arrs):
     assert np.array_equal(arrs["step_pos"], arrs["xp_position_of_step"])
     assert np.array_equal((arrs["step_node"].astype(np.uint64) << np.uint64(1)) | arrs["step_rev"], arrs["xp_handle_of_step"])
     assert np.array_equal(orc.positions_from_lengths(arrs["node_len"], arrs["path_first_step"], arrs["step_node"]), arrs["step_pos"])
+    # odgi_b200/host/pgsgd_flatten.hpp instantiated on the reference's graph_t (what odgi_shim.cpp does) gives the same arrays
+    for k in ("node_len", "path_first_step", "step_node", "step_rev", "step_pos"):
+        assert np.array_equal(arrs[k], arrs["shim_" + k]), k
     keep = {k: arrs[k] for k in ("node_len", "path_first_step", "step_node", "step_rev", "step_pos", "path_names")}
     keep["xp_nr_iv"] = arrs["xp_nr_iv"].astype(np.uint32)
     keep["xp_npi_iv"] = arrs["xp_npi_iv"].astype(np.uint32)

@@ -159,3 +159,22 @@ def test_default_initialisation_shape(golden_graphs, tmp_path):
     assert np.array_equal(outs[0]["Y"], outs[1]["Y"]) and abs(outs[0]["Y"].std() / np.sqrt(2 * g.N) - 1) < 0.05
     r = subprocess.run([CLI, "init", "-i", str(gfa), "-N", "z", "-a", str(tmp_path / "z.arr")], capture_output=True, text=True)
     assert r.returncode == 1 and "unknown layout initialization" in r.stderr
+
+
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DRIVER), reason="oracle/_ref/ref_driver not built (needs the reference tree at build time)")
+@pytest.mark.parametrize("name", ["note5", "overlap", "DRB1-3123", "LPA"])
+def test_shim_flatten_template_on_the_reference_graph_type(golden_graphs, tmp_path, name):
+    """pgsgd::flatten_handle_graph instantiated on the reference's own graph_t (exactly what odgi_shim.cpp does), run inside
+    the reference driver: equals the driver's walk, the XP accessors the CPU workers use, and the committed fixture."""
+    a = golden_graphs[name]
+    gfa, out = tmp_path / "g.gfa", tmp_path / "dump.arr"
+    synth.write_gfa(odgi_b200.graph_from_arrays(a), str(gfa))
+    subprocess.run([REF_DRIVER, "dump", str(gfa), str(out)], check=True, capture_output=True, cwd=str(tmp_path))
+    d = read_arrays(str(out))
+    for k in ("node_len", "path_first_step", "step_node", "step_rev", "step_pos"):
+        assert np.array_equal(d["shim_" + k], d[k]) and np.array_equal(d["shim_" + k], a[k]), k
+    assert np.array_equal(d["shim_step_pos"], d["xp_position_of_step"])
+    assert np.array_equal((d["shim_step_node"].astype(np.uint64) << np.uint64(1)) | d["shim_step_rev"], d["xp_handle_of_step"])
