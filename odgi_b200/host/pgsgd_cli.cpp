@@ -40,7 +40,8 @@ const Flag LAYOUT_FLAGS[] = {
     {"g", "path-sgd-eps", true}, {"v", "path-sgd-eta-max", true}, {"a", "path-sgd-zipf-theta", true}, {"x", "path-sgd-iter-max", true},
     {"K", "path-sgd-cooling", true}, {"F", "path-sgd-iteration-max-learning-rate", true}, {"k", "path-sgd-zipf-space", true},
     {"I", "path-sgd-zipf-space-max", true}, {"l", "path-sgd-zipf-space-quantization-step", true}, {"t", "threads", true},
-    {"", "gpu", false}, {"P", "progress", false}, {"h", "help", false}, {"", "seed", true}, {"", "init-seed", true}, {"", "sampling", true}};
+    {"", "gpu", false}, {"P", "progress", false}, {"h", "help", false}, {"", "seed", true}, {"", "init-seed", true}, {"", "sampling", true},
+    {"u", "path-sgd-snapshot", true}};
 const Flag SORT_FLAGS[] = {
     {"i", "idx", true}, {"o", "out", true}, {"Y", "path-sgd", false}, {"G", "path-sgd-min-term-updates-paths", true},
     {"U", "path-sgd-min-term-updates-nodes", true}, {"j", "path-sgd-delta", true}, {"g", "path-sgd-eps", true},
@@ -211,7 +212,7 @@ bool init_layout(const pgsgd::FlatGraph& fg, char mode, bool seeded, uint64_t se
 int main_layout(int argc, char** argv) {
     Args a;
     if (!parse(argc, argv, LAYOUT_FLAGS, a, "layout") || a.has("help") || argc == 2) {
-        std::cout << "pgsgd layout -i g.gfa (-o out.lay | -T out.tsv) --gpu [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-N d|r|u|g|h] [-t N] [-P]\n"
+        std::cout << "pgsgd layout -i g.gfa (-o out.lay | -T out.tsv) --gpu [-u snapshot_prefix] [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-N d|r|u|g|h] [-t N] [-P]\n"
                      "  the `odgi layout` PG-SGD flags with the same defaults; --seed N (worker streams), --init-seed N (layout initialisation)\n";
         return a.has("help") ? 0 : 1;
     }
@@ -228,7 +229,35 @@ int main_layout(int argc, char** argv) {
     if (!init_layout(fg, a.str("layout-initialization", "d")[0], a.has("init-seed"), a.u64("init-seed", 0), X, Y)) return 1;
     pgsgd_stats st;
     const pgsgd_graph_view v = fg.view();
-    if (pgsgd_layout_2d(&v, &c, X.data(), Y.data(), &st) != PGSGD_OK) { std::cerr << "[odgi::layout] error: " << pgsgd_last_error() << std::endl; return 1; }
+    if (!a.has("path-sgd-snapshot")) {
+        if (pgsgd_layout_2d(&v, &c, X.data(), Y.data(), &st) != PGSGD_OK) { std::cerr << "[odgi::layout] error: " << pgsgd_last_error() << std::endl; return 1; }
+    } else {
+        // -u PREFIX: after every iteration but the last, the current coordinates as a .lay in PREFIX<iteration>
+        // (snapshot_lambda, path_sgd_layout.cpp:379-409; the reference GPU path ignores the flag).  The graph stays
+        // resident in HBM; only the coordinates come back per snapshot.
+        pgsgd_engine* e = nullptr;
+        int rc = pgsgd_engine_create(&v, 0, &e);
+        if (!rc) rc = pgsgd_engine_set_coords_2d(e, X.data(), Y.data());
+        std::memset(&st, 0, sizeof(st));
+        for (uint64_t it = 0; !rc && it < c.iter_max; ++it) {
+            pgsgd_stats one;
+            rc = pgsgd_engine_run_range(e, &c, 2, it, it + 1, &one);
+            if (rc) break;
+            st.term_updates += one.term_updates;
+            st.seconds_iterations += one.seconds_iterations;
+            st.seconds_upload = one.seconds_upload;
+            if (one.iterations_run == 0) break;  // nothing to do (no path with more than one step)
+            rc = pgsgd_engine_get_coords_2d(e, X.data(), Y.data());
+            if (!rc && it + 1 < c.iter_max) {
+                if (a.has("progress")) std::cerr << "[odgi::path_linear_sgd_layout] snapshot thread: Taking snapshot!" << std::endl;
+                std::ofstream f(a.str("path-sgd-snapshot") + std::to_string(it + 1), std::ios::binary);
+                pgsgd::lay::write_lay(f, X, Y);
+            }
+            if (!rc && c.delta > 0 && one.last_delta_max <= c.delta) break;  // early stop, as the checker thread decides it
+        }
+        if (e) pgsgd_engine_destroy(e);
+        if (rc) { std::cerr << "[odgi::layout] error: " << pgsgd_last_error() << std::endl; return 1; }
+    }
     if (a.has("progress"))
         std::cerr << "[odgi::path_linear_sgd_layout] 2D path-guided SGD: " << st.term_updates << " term updates in " << st.seconds_iterations
                   << " s on the GPU (" << st.term_updates / st.seconds_iterations / 1e6 << " M updates/s), upload " << st.seconds_upload << " s" << std::endl;

@@ -107,3 +107,22 @@ def test_reference_call_chain_on_two_gpus(drb1, tmp_path):
     b1 = _band("DRB1-3123.sort1d")
     s1 = orc.path_stress_1d(go, x, b1["n_pairs"], b1["seed"])
     assert abs(s1 - b1["mean"]) <= 0.03 * b1["mean"] + 2 * b1["sd"], (s1, b1["mean"])
+
+
+def test_cli_layout_snapshots(drb1, tmp_path):
+    """-u PREFIX: one .lay per iteration but the last, named PREFIX<iteration> (path_sgd_layout.cpp:379-409)."""
+    gfa, go = drb1
+    prefix = str(tmp_path / "snap_")
+    tsv = tmp_path / "final.tsv"
+    subprocess.run([CLI, "layout", "-i", gfa, "-T", str(tsv), "--gpu", "--init-seed", "42", "-x", "5", "-u", prefix], check=True)
+    stress = []
+    for it in range(1, 5):
+        back = tmp_path / f"snap{it}.arr"
+        subprocess.run([CLI, "lay", "-i", f"{prefix}{it}", "-a", str(back)], check=True)
+        b = read_arrays(str(back))
+        assert b["X"].size == 2 * go.N and np.all(np.isfinite(b["X"])) and np.all(np.isfinite(b["Y"]))
+        stress.append(orc.path_stress_2d(go, b["X"], b["Y"], 200000, 1))
+    assert not os.path.exists(f"{prefix}5")
+    rows = np.loadtxt(str(tsv), skiprows=1)
+    final = orc.path_stress_2d(go, rows[:, 1], rows[:, 2], 200000, 1)   # component offsetting is a translation: stress unchanged
+    assert final < stress[0] and len(set(stress)) == 4, (stress, final)
