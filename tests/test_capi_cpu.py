@@ -77,3 +77,19 @@ def test_abi_version_is_one_number_everywhere():
     with open(os.path.join(ROOT, "include", "pgsgd.h")) as f:
         m = re.search(r"#define\s+PGSGD_VERSION\s+(\d+)", f.read())
     assert m and int(m.group(1)) == capi.ABI_VERSION == capi.lib().pgsgd_version()
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/pgsgd.h is the drop-in boundary for ANY FFI: it must compile as strict C99 and link against the library."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "pgsgd.h"\n#include <stdio.h>\n'
+                   'int main(void) { pgsgd_config c; pgsgd_graph_view v; pgsgd_stats s;\n'
+                   '  printf("%d %d %d\\n", (int) sizeof c, (int) sizeof v, (int) sizeof s);\n'
+                   '  return pgsgd_version() == PGSGD_VERSION && pgsgd_last_error() ? 0 : 1; }\n')
+    exe = tmp_path / "hdr"
+    libdir = os.path.join(ROOT, "odgi_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lpgsgd_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split() == ["120", "64", "80"]
