@@ -185,10 +185,11 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--flags", type=int, default=0)
-    ap.add_argument("--multi", default="hybrid", choices=["hybrid", "peer", "allreduce"],
+    ap.add_argument("--multi", default="hybrid", choices=["hybrid", "peer", "allreduce", "sharded"],
                     help="N>1: 'peer' = coordinates partitioned over the GPUs, updated through NVLink peer memory (one shared Hogwild); "
                          "'allreduce' = replicated + 1 all-reduce/step (fastest, costs layout quality); 'hybrid' = allreduce for the first "
-                         "third of the schedule, peer afterwards (single-GPU layout quality)")
+                         "third of the schedule, peer afterwards (single-GPU layout quality); 'sharded' = allreduce with the step records dealt out "
+                         "over the ranks by path (capacity mode for graphs whose records do not fit one GPU; quality readout covers rank 0's paths)")
     ap.add_argument("--sampling", type=int, default=0, help="0 auto, 1 stream (reference-exact worker streams), 2 tile")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -216,7 +217,13 @@ def main():
     g, desc = make_workload(args.workload)
     W, K = args.warmup, args.steps
     iter_max = max(30, W + K)
+    # the schedule's parameters (U, space, eta_max) are those of the WHOLE job, whatever a rank holds of it
     cfg = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags, sampling=args.sampling)
+    job_steps = g.S
+    sharded = world > 1 and args.multi == "sharded"
+    if sharded:
+        g = odgi_b200.shard_paths(g, world, rank)   # this rank's paths only; node table whole
+    multi_mode = {"peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE, "sharded": capi.MULTI_ALLREDUCE}[args.multi]
     sampling_name = {1: "stream", 2: "tile"}.get(args.sampling, "tile" if g.S >= (1 << 22) else "stream")
     X0, Y0 = odgi_b200.layout_init(g, seed=42)
     U = cfg.min_term_updates
@@ -243,7 +250,9 @@ def main():
     e = odgi_b200.Engine(g, device=local_rank)
     if uid is not None:
         e.attach_comm(uid, world, rank)
-        e.set_multi_mode({"peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE}[args.multi])
+        e.set_multi_mode(multi_mode)
+        if sharded:
+            e.set_shard(job_steps)
     e.set_coords_2d(X0, Y0)
     stress_initial = e.path_stress(2, 4_000_000, 12345)
     barrier()
@@ -291,7 +300,7 @@ def main():
         gp = capi.FlatGraph(pin(g.node_len), pin(g.path_first_step), pin(g.step_node), None if g.step_rev is None else pin(g.step_rev),
                             None if g.step_pos is None else pin(g.step_pos))
         Xp, Yp = pin(X0), pin(Y0)
-        cfg_e = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags, sampling=args.sampling)
+        cfg_e = cfg
         barrier()
         t0 = time.time()
         e2 = odgi_b200.Engine(gp, device=local_rank)        # flatten-to-device upload
@@ -299,14 +308,21 @@ def main():
             obj = [capi.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(obj, src=0)
             e2.attach_comm(obj[0], world, rank)
-            e2.set_multi_mode({"peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE}[args.multi])
+            e2.set_multi_mode(multi_mode)
+            if sharded:
+                e2.set_shard(job_steps)
         e2.set_coords_2d(Xp, Yp)                            # coordinate upload
         st2 = e2.run_range(cfg_e, 2, 0, K)                  # the same number of steps
         Xo, Yo = e2.get_coords_2d()                         # result download
         t_e2e = max_over_ranks(time.time() - t0)
         h2d = st2["h2d_bytes"]
         e2.close()
-        e2e = {"value": st2["term_updates"] * world / t_e2e / 1e6, "unit": "M updates/s", "h2d_bytes_per_step": h2d / K,
+        tot2 = float(st2["term_updates"])
+        if dist is not None:
+            t2 = torch.tensor([tot2], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+            tot2 = float(t2.item())
+        e2e = {"value": tot2 / t_e2e / 1e6, "unit": "M updates/s", "h2d_bytes_per_step": h2d / K,
                "d2h_bytes_per_step": 4 * g.N * 8 / K, "seconds": t_e2e, "steps_in_call": K,
                "note": "one engine lifetime: graph flatten+upload from pinned host memory, coords up, K steps, coords down; host wall clock"}
 
@@ -333,14 +349,16 @@ def main():
         "metric": "M node-pair SGD updates/sec", "value": value, "unit": "M updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic" if args.workload in ("c4", "mid", "small", "tiny") else "reference test graph (flattened fixture)",
-        "config": {"workload": args.workload, "description": desc, "nodes": g.N, "paths": g.P, "steps_in_graph": g.S,
+        "config": {"workload": args.workload, "description": desc, "nodes": g.N, "paths": g.P if not sharded else None, "steps_in_graph": job_steps,
                    "updates_per_step": U, "iter_max": iter_max, "timed_iterations": [W, W + K], "sampling": sampling_name, "batch": args.batch or "auto",
                    "l2_policy": "inputs larger than L2" if g.S * 16 > 126e6 else "L2-resident graph (plumbing config)",
                    "parallelism": ("1 GPU" if world == 1 else
                                    f"coords partitioned over {world} GPUs, updated through NVLink peer memory (one shared Hogwild), tiles owned by node range"
                                    if args.multi == "peer" else
                                    f"hybrid over {world} GPUs: iterations < {iter_max // 3} replicated + 1 NCCL all-reduce/step, then coords partitioned and updated through NVLink peer memory"
-                                   if args.multi == "hybrid" else f"replicated coords, term updates split over {world} GPU(s), 1 NCCL all-reduce/step"),
+                                   if args.multi == "hybrid" else
+                                   f"step records dealt out over {world} GPUs by path (rank 0 holds {g.P} paths, {g.S} steps), replicated coords, 1 NCCL all-reduce/step"
+                                   if sharded else f"replicated coords, term updates split over {world} GPU(s), 1 NCCL all-reduce/step"),
                    "device_bytes": dev_bytes, "coords_finite": finite},
         "gpu_launches": K * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -190,6 +190,14 @@ int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int 
 #define PGSGD_MULTI_HYBRID    2
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode);
 
+/* Path-sharded step records (graphs whose step records do not fit one GPU): a term always pairs two steps of
+ * the SAME path, so the paths of a job can be dealt out over the ranks and every rank's engine is created from a view that
+ * holds only ITS paths (node_len stays the whole node table).  global_step_count = the steps of the whole job: the rank
+ * then performs min_term_updates * S_local / S_global updates per iteration over its own steps, which keeps every step of
+ * the job equally likely to start a term (path_sgd_layout.cpp:175-182).  Coordinates stay replicated and are combined per
+ * iteration (PGSGD_MULTI_ALLREDUCE only).  0 switches the mode off. */
+int pgsgd_engine_set_shard(pgsgd_engine* e, uint64_t global_step_count);
+
 /* ---- verification hooks (used by tests; they exercise exactly the device code the runs use) ---- */
 /* The first n_terms draws of worker stream `stream`, produced by the device sampler.  dims = 2 or 1;
  * cooling / theta_zipf as the iteration would set them.  Outputs are [n_terms] each (any may be NULL);

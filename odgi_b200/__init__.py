@@ -6,4 +6,4 @@ keeps odgi's own function signatures lives in odgi_b200/host/.
 """
 from .capi import (Config, Engine, FlatGraph, PgsgdError, comm_unique_id, device_count, layout_2d, layout_2d_multi, layout_defaults,  # noqa: F401
                    schedule, sort_1d, sort_defaults, zetas)
-from .graphio import load_graph_arrays, graph_from_arrays, layout_init  # noqa: F401
+from .graphio import assign_paths, graph_from_arrays, layout_init, load_graph_arrays, shard_paths  # noqa: F401

@@ -60,7 +60,7 @@ EXPORTED_SYMBOLS = [
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
     "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
-    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_path_stress", "pgsgd_engine_order_1d", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
+    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_set_shard", "pgsgd_engine_path_stress", "pgsgd_engine_order_1d", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
 ]
 
 ABI_VERSION = 101  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
@@ -101,6 +101,7 @@ def lib():
         L.pgsgd_comm_unique_id.argtypes = [vp]
         L.pgsgd_engine_attach_comm.argtypes = [vp, vp, i32, i32]
         L.pgsgd_engine_set_multi_mode.argtypes = [vp, i32]
+        L.pgsgd_engine_set_shard.argtypes = [vp, u64]
         L.pgsgd_engine_path_stress.argtypes = [vp, i32, u64, u64, vp]
         L.pgsgd_engine_order_1d.argtypes = [vp, vp]
         L.pgsgd_engine_sample_terms.argtypes = [vp, C.POINTER(ConfigC), i32, i32, dbl, u64, u64] + [vp] * 11
@@ -352,6 +353,10 @@ class Engine:
     def set_multi_mode(self, mode: int):
         """0 = all-reduce of replicated coordinates, 1 = NVLink peer memory (partitioned coordinates)"""
         _check(lib().pgsgd_engine_set_multi_mode(self._h, mode))
+
+    def set_shard(self, global_step_count: int):
+        """this engine holds only some of the job's paths (graphio.partition_paths); 0 switches the mode off"""
+        _check(lib().pgsgd_engine_set_shard(self._h, int(global_step_count)))
 
     def sample_terms(self, cfg: Config, dims: int, cooling: bool, n_terms: int, stream: int = 0, theta_zipf=None):
         out = {"step_index": np.zeros(n_terms, np.uint64), "path": np.zeros(n_terms, np.uint32),

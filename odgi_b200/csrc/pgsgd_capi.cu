@@ -161,6 +161,8 @@ struct pgsgd_engine {
     std::vector<uint32_t> tile_mid_node;     // node of the middle step of every tile (tile -> owner rank)
     uint32_t* d_tile_list = nullptr;
     uint64_t my_tiles = 0, my_tile_steps = 0;
+    // ---- path-sharded step records (pgsgd_engine_set_shard): this engine holds only some of the job's paths ----
+    uint64_t shard_global_steps = 0;         // S of the whole job; 0 = the view is the whole graph
 };
 
 namespace {
@@ -385,7 +387,12 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
 
     // this rank's share of every iteration's term updates
     const uint64_t U = cfg->min_term_updates;
-    const uint64_t U_rank = U / e->n_ranks + ((uint64_t) e->rank < U % e->n_ranks ? 1 : 0);
+    // replicated step records: an equal share of U; path-sharded records: in proportion to the steps this rank holds, so
+    // that every step of the job stays equally likely to be a term's first step (path_sgd_layout.cpp:175-182)
+    const bool sharded = e->shard_global_steps != 0;
+    if (sharded && e->active_mode != PGSGD_MULTI_ALLREDUCE) return fail(PGSGD_ERR_STATE, "path-sharded step records need PGSGD_MULTI_ALLREDUCE (peer phases walk tiles by node range)");
+    const uint64_t U_rank = sharded ? (uint64_t) ((unsigned __int128) U * e->S / e->shard_global_steps)
+                                    : U / e->n_ranks + ((uint64_t) e->rank < U % e->n_ranks ? 1 : 0);
     const bool peer = e->active_mode == PGSGD_MULTI_PEER && e->comm;
     if (peer && !(dims == 2 ? e->peer_ready_2d : e->peer_ready_1d)) return fail(PGSGD_ERR_STATE, "peer mode: coordinates were not set after the mode was selected");
     // in peer mode all ranks update ONE coordinate array: the Hogwild in-flight cap is shared by the ranks
@@ -516,12 +523,14 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         // tile visits of the WHOLE job (all ranks); rank r takes visits v = r (mod n_ranks)
         const uint64_t W = TILE_STEPS;
         p.n_tiles = (e->S + W - 1) / W;
-        const uint64_t q = U / e->S, rU = U % e->S;
+        // (a path-sharded rank walks all visits of its own U_rank over its own steps)
+        const uint64_t U_job = sharded ? U_rank : U;
+        const uint64_t q = U_job / e->S, rU = U_job % e->S;
         const uint64_t extra = (rU + W - 1) / W;
         p.n_visits = q * p.n_tiles + extra;
         p.last_visit_terms = rU ? rU - (extra - 1) * W : W;
-        p.visit_rank = (uint32_t) e->rank;
-        p.visit_nranks = (uint32_t) e->n_ranks;
+        p.visit_rank = sharded ? 0u : (uint32_t) e->rank;
+        p.visit_nranks = sharded ? 1u : (uint32_t) e->n_ranks;
         if (peer) {
             // this rank walks ITS OWN tiles (those whose middle node it owns): U * my_steps / S terms per iteration
             p.tile_list = e->d_tile_list;
@@ -630,6 +639,8 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
 // NVLink peer memory.  Final stress equals the single-GPU one (oracle emulation + tests/test_gpu_multi.py), at most
 // of the all-reduce mode's throughput in the early phase.
 int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end, pgsgd_stats* stats) {
+    if (e->shard_global_steps && e->comm && e->multi_mode != PGSGD_MULTI_ALLREDUCE)
+        return fail(PGSGD_ERR_STATE, "path-sharded step records need PGSGD_MULTI_ALLREDUCE (peer phases walk tiles by node range)");
     if (!e->comm || e->multi_mode != PGSGD_MULTI_HYBRID) {
         e->active_mode = e->comm ? e->multi_mode : PGSGD_MULTI_ALLREDUCE;
         return run_phase(e, cfg, dims, iter_begin, iter_end, stats);
@@ -1075,6 +1086,14 @@ int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode) {
     if (mode != PGSGD_MULTI_ALLREDUCE && (!e->comm || e->n_ranks < 2)) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator (pgsgd_engine_attach_comm) with >= 2 ranks");
     if (e->have_2d || e->have_1d) return fail(PGSGD_ERR_STATE, "select the multi-GPU mode before uploading coordinates");
     e->multi_mode = mode;
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_set_shard(pgsgd_engine* e, uint64_t global_step_count) {
+    if (!e) return fail(PGSGD_ERR_ARG, "set_shard: NULL engine");
+    if (global_step_count != 0 && global_step_count < e->S) return fail(PGSGD_ERR_ARG, "set_shard: the job cannot have fewer steps (%llu) than this shard (%llu)",
+                                                                    (unsigned long long) global_step_count, (unsigned long long) e->S);
+    e->shard_global_steps = global_step_count;
     return PGSGD_OK;
 }
 

@@ -40,3 +40,30 @@ def layout_init(g: FlatGraph, seed: int = 42, noise: bool = True):
     else:
         Y = np.zeros(2 * N, dtype=np.float64)
     return X, Y
+
+
+def assign_paths(step_counts, n_ranks: int):
+    """Deal the paths of a job out over n_ranks: greedy bin packing on step count, longest path first, ties
+    to the lower rank.  Returns the owner rank of every path.  A term always pairs two steps of the same path, so whole
+    paths are the unit; the ranks' shares of an iteration's updates follow their step counts."""
+    step_counts = np.asarray(step_counts, dtype=np.uint64)
+    owner = np.zeros(step_counts.size, dtype=np.int64)
+    load = np.zeros(n_ranks, dtype=np.uint64)
+    for p in np.argsort(-step_counts.astype(np.int64), kind="stable"):
+        r = int(np.argmin(load))
+        owner[p] = r
+        load[r] += step_counts[p]
+    return owner
+
+
+def shard_paths(g: FlatGraph, n_ranks: int, rank: int) -> FlatGraph:
+    """The view rank `rank` creates its engine from: the whole node table, only the steps of ITS paths (in path order).
+    Use with Engine.set_shard(g.S)."""
+    first = g.path_first_step
+    owner = assign_paths(np.diff(first), n_ranks)
+    mine = np.nonzero(owner == rank)[0]
+    sel = np.concatenate([np.arange(first[p], first[p + 1], dtype=np.int64) for p in mine]) if mine.size else np.zeros(0, dtype=np.int64)
+    new_first = np.concatenate([[0], np.cumsum(np.diff(first)[mine])]).astype(np.uint64)
+    names = [g.path_names[p] for p in mine] if g.path_names else []
+    return FlatGraph(g.node_len, new_first, g.step_node[sel], None if g.step_rev is None else g.step_rev[sel],
+                     None if g.step_pos is None else g.step_pos[sel], names)

@@ -288,6 +288,26 @@ def run_range(g: Graph, cfg: Config, n_streams: int, seed_base: int, updates: in
                                    _ptr(X), _ptr(Y), _ptr(xy), _ptr(frozen), _ptr(rng_state)))
 
 
+def emulate_sharded_2d_f32(shards, global_steps: int, cfg: Config, xy0, n_streams: int):
+    """Single-process emulation of the PATH-SHARDED multi-GPU schedule (pgsgd_engine_set_shard): rank r holds only the
+    graph shards[r] (its paths), performs U * S_r / S updates per iteration on it with worker streams
+    seed + r*n_streams + t, then the replicas are averaged in fp32."""
+    n_ranks = len(shards)
+    reps = [np.ascontiguousarray(xy0, dtype=np.float32).copy() for _ in range(n_ranks)]
+    states = [np.zeros(4 * n_streams, dtype=np.uint64) for _ in range(n_ranks)]
+    for it in range(cfg.iter_max):
+        for r in range(n_ranks):
+            share = cfg.min_term_updates * shards[r].S // global_steps
+            run_range(shards[r], cfg, n_streams, cfg.seed + r * n_streams, share, it, it + 1, 1, xy=reps[r], rng_state=states[r])
+        acc = reps[0].copy()
+        for r in range(1, n_ranks):
+            acc = acc + reps[r]
+        merged = (acc / np.float32(n_ranks)).astype(np.float32)
+        for r in range(n_ranks):
+            reps[r][...] = merged
+    return reps[0]
+
+
 def emulate_multirank_2d_f32(g: Graph, cfg: Config, xy0, n_ranks: int, n_streams: int, sum_deltas: bool = False,
                              syncs_per_iter: int = 1):
     """Single-process emulation of the multi-GPU schedule of pgsgd_engine_run_2d with a communicator attached:
