@@ -304,6 +304,7 @@ def main():
         barrier()
         t0 = time.time()
         e2 = odgi_b200.Engine(gp, device=local_rank)        # flatten-to-device upload
+        t_create = time.time()
         if uid is not None:
             obj = [capi.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(obj, src=0)
@@ -311,9 +312,15 @@ def main():
             e2.set_multi_mode(multi_mode)
             if sharded:
                 e2.set_shard(job_steps)
+        t_comm = time.time()
         e2.set_coords_2d(Xp, Yp)                            # coordinate upload
+        t_up = time.time()
         st2 = e2.run_range(cfg_e, 2, 0, K)                  # the same number of steps
+        t_run = time.time()
         Xo, Yo = e2.get_coords_2d()                         # result download
+        t_down = time.time()
+        phases = {"engine_create_flatten_upload_s": t_create - t0, "comm_attach_s": t_comm - t_create, "coords_upload_s": t_up - t_comm,
+                  "run_call_s": t_run - t_up, "of_which_device_iterations_s": st2["seconds_iterations"], "coords_download_s": t_down - t_run}
         t_e2e = max_over_ranks(time.time() - t0)
         h2d = st2["h2d_bytes"]
         e2.close()
@@ -323,7 +330,7 @@ def main():
             dist.all_reduce(t2, op=dist.ReduceOp.SUM)
             tot2 = float(t2.item())
         e2e = {"value": tot2 / t_e2e / 1e6, "unit": "M updates/s", "h2d_bytes_per_step": h2d / K,
-               "d2h_bytes_per_step": 4 * g.N * 8 / K, "seconds": t_e2e, "steps_in_call": K,
+               "d2h_bytes_per_step": 4 * g.N * 8 / K, "seconds": t_e2e, "steps_in_call": K, "phases_rank0": phases,
                "note": "one engine lifetime: graph flatten+upload from pinned host memory, coords up, K steps, coords down; host wall clock"}
 
     if rank != 0:
