@@ -178,3 +178,62 @@ def test_shim_flatten_template_on_the_reference_graph_type(golden_graphs, tmp_pa
         assert np.array_equal(d["shim_" + k], d[k]) and np.array_equal(d["shim_" + k], a[k]), k
     assert np.array_equal(d["shim_step_pos"], d["xp_position_of_step"])
     assert np.array_equal((d["shim_step_node"].astype(np.uint64) << np.uint64(1)) | d["shim_step_rev"], d["xp_handle_of_step"])
+
+
+def test_bench_line_assembles_with_a_stand_in_engine(monkeypatch, capfd):
+    """bench.py's own arm needs a GPU; this runs its whole control flow on the CPU with the engine replaced by a stand-in that
+    returns plausible statistics, so that the JSON contract (keys, units, one line on stdout) is guarded without a device."""
+    import importlib
+    import json
+    import sys
+    import types
+    import torch
+    from odgi_b200 import capi
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+
+    class StandIn:
+        device_bytes = 123
+
+        def __init__(self, g, device=0):
+            self.g, self.it = g, 0
+
+        def set_coords_2d(self, X, Y):
+            self.X, self.Y = np.array(X, dtype=np.float64), np.array(Y, dtype=np.float64)
+
+        def path_stress(self, dims, pairs, seed):
+            return 1.0 / (1 + self.it)
+
+        def run_range(self, cfg, dims, lo, hi):
+            n = max(0, min(hi, cfg.iter_max) - lo)
+            self.it += n
+            return {"iterations_run": n, "kernel_launches": n, "term_updates": n * cfg.min_term_updates, "seconds_iterations": 1e-3 * n,
+                    "h2d_bytes": 1000, "seconds_upload": 0.0}
+
+        def get_coords_2d(self):
+            return self.X, self.Y
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(bench, "pinned_like", lambda a: (np.array(a), None))
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda i: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(odgi_b200, "device_count", lambda: 1)
+    monkeypatch.setattr(odgi_b200, "Engine", StandIn)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "tiny", "--steps", "4", "--warmup", "3", "--no-cpu-baseline"])
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    bench.main()
+    out = capfd.readouterr().out.strip().splitlines()
+    assert len(out) == 1, out
+    line = json.loads(out[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "gpu_launches", "clocks", "e2e", "roofline"):
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["steps"] == 4 and line["warmup"] == 3 and line["gpu_launches"] == 4 and line["vs_baseline"] is None
+    assert line["config"]["workload"] == "tiny" and "model" not in line["config"]
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "phases_rank0"}
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["bound"] == "hbm"
+    assert abs(line["value"] - 4 * line["config"]["updates_per_step"] / 4e-3 / 1e6) < 1e-6 * line["value"]
