@@ -67,11 +67,32 @@ ABI_VERSION = 101  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs m
 _lib = None
 
 
+def _prefer_environment_nccl():
+    """libpgsgd_b200.so depends on libnccl.so.2 by soname, and a process holds ONE library per soname.  If this Python
+    environment ships a (newer) NCCL next to PyTorch, load that one first: otherwise the system NCCL loaded for us would also
+    be handed to a later `import torch`, which needs symbols of the version it was built against.  Plumbing only: the
+    library itself runs with either."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise PgsgdError(-2, f"{LIB_PATH} is missing: build it with `python -m odgi_b200.build` (no CPU fallback exists)")
+        _prefer_environment_nccl()
         L = C.CDLL(LIB_PATH)
         vp, u64, i32, dbl = C.c_void_p, C.c_uint64, C.c_int, C.c_double
         L.pgsgd_last_error.restype = C.c_char_p
