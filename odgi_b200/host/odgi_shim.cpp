@@ -38,9 +38,10 @@ void check_abi() {
     }
 }
 
-pgsgd::FlatGraph flatten_or_exit(const odgi::graph_t& graph) {
+pgsgd::FlatGraph flatten_or_exit(const odgi::graph_t& graph, uint64_t nthreads) {
     try {
-        return pgsgd::flatten_handle_graph<odgi::graph_t, handlegraph::path_handle_t, handlegraph::step_handle_t>(graph);
+        // config.nthreads is used for exactly this in the reference too (OpenMP path walk, layout.cu:371)
+        return pgsgd::flatten_handle_graph<odgi::graph_t, handlegraph::path_handle_t, handlegraph::step_handle_t>(graph, (unsigned) (nthreads ? nthreads : 1));
     } catch (const std::exception& e) {
         std::fprintf(stderr, "%s\n", e.what());   // same message and exit code as layout.cu:320-323
         std::exit(1);
@@ -54,7 +55,7 @@ namespace cuda {
 void gpu_layout(layout_config_t config, const odgi::graph_t& graph, std::vector<std::atomic<double>>& X,
                 std::vector<std::atomic<double>>& Y) {
     std::cout << "===== Use GPU to compute odgi-layout =====" << std::endl;  // layout.cu:293
-    const pgsgd::FlatGraph fg = flatten_or_exit(graph);
+    const pgsgd::FlatGraph fg = flatten_or_exit(graph, (uint64_t) (config.nthreads > 0 ? config.nthreads : 1));
     check_abi();
     pgsgd_config c{};
     c.iter_max = config.iter_max;
@@ -93,10 +94,10 @@ std::vector<double> path_linear_sgd_gpu(const graph_t& graph, const xp::XP& /*pa
                                         const uint64_t& iter_with_max_learning_rate, const uint64_t& min_term_updates,
                                         const double& delta, const double& eps, const double& eta_max, const double& theta,
                                         const uint64_t& space, const uint64_t& space_max, const uint64_t& space_quantization_step,
-                                        const double& cooling_start, const uint64_t& /*nthreads*/, const bool& /*progress*/,
+                                        const double& cooling_start, const uint64_t& nthreads, const bool& /*progress*/,
                                         const bool& /*snapshot*/, std::vector<std::string>& /*snapshots*/,
                                         const bool& target_sorting, std::vector<bool>& target_nodes) {
-    const pgsgd::FlatGraph fg = flatten_or_exit(graph);
+    const pgsgd::FlatGraph fg = flatten_or_exit(graph, nthreads);
     check_abi();
     pgsgd_config c{};
     c.iter_max = iter_max;

@@ -6,9 +6,11 @@
 // get_node_count, for_each_path_handle, for_each_step_in_path, get_handle_of_step, get_id, get_is_reverse, get_length)
 // without this header including any odgi header.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pgsgd.h"
@@ -60,8 +62,11 @@ private:
 // (layout_main.cpp:148, layout.cu:320-323); throws std::runtime_error with the reference's message otherwise.
 // PathHandle / StepHandle are the graph's handle types (handlegraph::path_handle_t, handlegraph::step_handle_t):
 // libhandlegraph's iteratee wrappers need concrete lambda parameter types.
+// nthreads > 1 walks the paths concurrently (graph reads are thread-safe in odgi; the reference's GPU host code walks them
+// under OpenMP for the same reason, layout.cu:371): step counts give every path its slice up front, then worker threads
+// take whole paths from a shared counter.  The result does not depend on nthreads.
 template <typename Graph, typename PathHandle, typename StepHandle>
-FlatGraph flatten_handle_graph(const Graph& graph) {
+FlatGraph flatten_handle_graph(const Graph& graph, unsigned nthreads = 1) {
     FlatGraph fg;
     const uint64_t N = graph.get_node_count();
     if ((uint64_t) graph.min_node_id() != 1 || (uint64_t) graph.max_node_id() != N) {
@@ -69,14 +74,51 @@ FlatGraph flatten_handle_graph(const Graph& graph) {
     }
     fg.node_len.resize(N);
     for (uint64_t r = 0; r < N; ++r) fg.node_len[r] = (uint32_t) graph.get_length(graph.get_handle(r + 1, false));
-    graph.for_each_path_handle([&](const PathHandle& path) {
-        fg.begin_path(graph.get_path_name(path));
-        graph.for_each_step_in_path(path, [&](const StepHandle& step) {
-            const auto h = graph.get_handle_of_step(step);
-            fg.add_step((uint32_t) (graph.get_id(h) - 1), graph.get_is_reverse(h));
-        });
-        fg.end_path();
-    });
+    std::vector<PathHandle> paths;
+    graph.for_each_path_handle([&](const PathHandle& path) { paths.push_back(path); });
+    fg.path_first_step.assign(1, 0);
+    for (const PathHandle& path : paths) {
+        fg.path_names.push_back(graph.get_path_name(path));
+        fg.path_first_step.push_back(fg.path_first_step.back() + (uint64_t) graph.get_step_count(path));
+    }
+    const uint64_t S = fg.path_first_step.back();
+    fg.step_node.resize(S);
+    fg.step_rev.resize(S);
+    fg.step_pos.resize(S);
+    std::vector<uint64_t> path_bp(paths.size(), 0);
+    std::atomic<uint64_t> next{0};
+    std::atomic<bool> count_mismatch{false};
+    auto work = [&]() {
+        for (uint64_t p = next.fetch_add(1); p < paths.size(); p = next.fetch_add(1)) {
+            uint64_t i = fg.path_first_step[p], bp = 0;
+            const uint64_t end = fg.path_first_step[p + 1];
+            graph.for_each_step_in_path(paths[p], [&](const StepHandle& step) {
+                if (i >= end) { count_mismatch.store(true); return; }
+                const auto h = graph.get_handle_of_step(step);
+                const uint32_t rank = (uint32_t) (graph.get_id(h) - 1);
+                fg.step_node[i] = rank;
+                fg.step_rev[i] = graph.get_is_reverse(h) ? 1 : 0;
+                fg.step_pos[i] = bp;   // == XP positions[rank] (xp.cpp:607-616)
+                bp += fg.node_len[rank];
+                ++i;
+            });
+            if (i != end) count_mismatch.store(true);
+            path_bp[p] = bp;
+        }
+    };
+    if (nthreads <= 1 || paths.size() <= 1) {
+        work();
+    } else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nthreads && t < paths.size(); ++t) pool.emplace_back(work);
+        for (auto& th : pool) th.join();
+    }
+    if (count_mismatch.load()) throw std::runtime_error("[pgsgd::flatten] a path's walk disagrees with its step count");
+    for (uint64_t p = 0; p < paths.size(); ++p) {
+        const uint64_t c = fg.path_first_step[p + 1] - fg.path_first_step[p];
+        if (c > fg.max_path_steps) fg.max_path_steps = c;
+        if (path_bp[p] > fg.max_path_bp) fg.max_path_bp = path_bp[p];
+    }
     return fg;
 }
 

@@ -162,6 +162,12 @@ static int cmd_dump(int argc, char** argv) {
     }
     // the product's own walk over the reference's graph_t (the template the odgi shim instantiates): must equal both
     const pgsgd::FlatGraph shim = pgsgd::flatten_handle_graph<graph_t, path_handle_t, step_handle_t>(L.graph);
+    // ... and does not depend on the number of walker threads
+    const pgsgd::FlatGraph shim4 = pgsgd::flatten_handle_graph<graph_t, path_handle_t, step_handle_t>(L.graph, 4);
+    if (shim4.step_node != shim.step_node || shim4.step_rev != shim.step_rev || shim4.step_pos != shim.step_pos ||
+        shim4.path_first_step != shim.path_first_step || shim4.node_len != shim.node_len || shim4.path_names != shim.path_names ||
+        shim4.max_path_steps != shim.max_path_steps || shim4.max_path_bp != shim.max_path_bp)
+        throw std::runtime_error("flatten_handle_graph: the 4-thread walk differs from the 1-thread walk");
     pgsgd::ArrayWriter w(argv[3]);
     w.add("shim_node_len", shim.node_len);
     w.add("shim_path_first_step", shim.path_first_step);
