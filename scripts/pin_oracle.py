@@ -232,6 +232,8 @@ def main():
             arrs = dump_graph(name, tmp)
             pin_1d(name, arrs, tmp, updates=8000)
         pin_1d("DRB1-3123", dump_graph("DRB1-3123", tmp), tmp, updates=8000, freeze_mod=3)
+        pin_1d("chr6.C4", dump_graph("chr6.C4", tmp), tmp, updates=8000)
+        pin_1d("LPA", dump_graph("LPA", tmp), tmp, updates=6000, freeze_mod=2)
         pin_2d("LPA", dump_graph("LPA", tmp), tmp, cooling_start=0.5, updates=8000, tag="cool")
 
 

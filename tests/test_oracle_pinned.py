@@ -71,7 +71,7 @@ def test_2d_trace_and_coords_bit_exact(golden_dir, golden_graphs, name, tag):
     assert np.array_equal(X, pin["X"]) and np.array_equal(Y, pin["Y"])
 
 
-@pytest.mark.parametrize("name", ["DRB1-3123", "LPA", "overlap", "k", "note5"])
+@pytest.mark.parametrize("name", ["DRB1-3123", "LPA", "chr6.C4", "overlap", "k", "note5"])
 def test_1d_trace_and_coords_bit_exact(golden_dir, golden_graphs, name):
     pin = _load(golden_dir, f"{name}.pin1d.arr.gz")
     g = orc.Graph.from_arrays(golden_graphs[name], use_xp_perm=True)
@@ -85,11 +85,12 @@ def test_1d_trace_and_coords_bit_exact(golden_dir, golden_graphs, name):
     assert np.array_equal(X, pin["X"])
 
 
-def test_1d_frozen_nodes_bit_exact(golden_dir, golden_graphs):
+@pytest.mark.parametrize("name,mod", [("DRB1-3123", 3), ("LPA", 2)])
+def test_1d_frozen_nodes_bit_exact(golden_dir, golden_graphs, name, mod):
     """`odgi sort -H` semantics (target nodes stay put, path_sgd.cpp:290-302,387-392): reference run with every third
-    node frozen, replayed by the oracle — trace and final coordinates bit-exact; frozen nodes never moved."""
-    pin = _load(golden_dir, "DRB1-3123.pin1d_frozen3.arr.gz")
-    g = orc.Graph.from_arrays(golden_graphs["DRB1-3123"], use_xp_perm=True)
+    (second) node frozen, replayed by the oracle — trace and final coordinates bit-exact; frozen nodes never moved."""
+    pin = _load(golden_dir, f"{name}.pin1d_frozen{mod}.arr.gz")
+    g = orc.Graph.from_arrays(golden_graphs[name], use_xp_perm=True)
     mod = int(pin["freeze_mod"][0])
     frozen = (np.arange(g.N) % mod == 0).astype(np.uint8)
     eta = float(pin["eta"][0])
