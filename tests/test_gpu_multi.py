@@ -169,62 +169,3 @@ def test_single_process_two_gpus(tmp_path):
         r = res[tag]
         assert abs(r["updates"] - 30 * 10 * 35059) <= 30 * 2048, res
         assert abs(r["stress"] - b2["mean"]) <= 0.03 * b2["mean"], (tag, r["stress"], b2["mean"])
-
-
-SHARDED = r'''
-import os, sys, json
-import numpy as np
-sys.path.insert(0, os.environ["PGSGD_ROOT"])
-import torch, torch.distributed as dist
-import odgi_b200
-from odgi_b200 import capi
-from odgi_b200.arrays import read_arrays
-from oracle import oracle as orc
-rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(rank)
-dist.init_process_group("gloo")
-a = read_arrays(os.path.join(os.environ["PGSGD_ROOT"], "tests/golden/chr6.C4.graph.arr.gz"))
-gd, go = odgi_b200.graph_from_arrays(a), orc.Graph.from_arrays(a)
-obj = [capi.comm_unique_id() if rank == 0 else None]
-dist.broadcast_object_list(obj, src=0)
-X0, Y0 = orc.layout_init(go, 42)
-kw = dict(iter_max=4, min_term_updates=6001, eta_max=2000.0)
-cd = capi.layout_defaults(gd, n_streams=1, batch=1, sampling=capi.SAMPLING_STREAM, **kw)   # the WHOLE job's config
-mine = odgi_b200.shard_paths(gd, world, rank)
-with odgi_b200.Engine(mine, device=rank) as e:
-    e.attach_comm(obj[0], world, rank)
-    e.set_multi_mode(capi.MULTI_ALLREDUCE)
-    e.set_shard(gd.S)
-    e.set_coords_2d_f32(orc.XY_to_xy(X0, Y0))
-    st = e.run_2d(cd)
-    xy = e.get_coords_2d_f32()
-    e.set_multi_mode(capi.MULTI_HYBRID)
-    try:
-        e.run_2d(cd); refused = False
-    except odgi_b200.PgsgdError:
-        refused = True
-shards = []
-for r in range(world):
-    s = odgi_b200.shard_paths(gd, world, r)
-    shards.append(orc.Graph(s.node_len, s.path_first_step, s.step_node, s.step_rev))
-ref = orc.emulate_sharded_2d_f32(shards, gd.S, orc.default_layout_config(go, **kw), orc.XY_to_xy(X0, Y0), 1)
-cnt = torch.tensor([int(st["term_updates"])]); dist.all_reduce(cnt)
-if rank == 0:
-    print("RESULT " + json.dumps({"equal": bool(np.array_equal(xy, ref)), "updates": int(cnt.item()), "refused": refused,
-                                  "expected": int(sum(6001 * s.S // gd.S for s in shards) * 4)}))
-dist.destroy_process_group()
-'''
-
-
-@pytest.mark.skipif(odgi_b200.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_path_sharded_matches_emulation(tmp_path):
-    """Step records dealt out over the ranks by path (pgsgd_engine_set_shard): the 2-GPU run equals the oracle's emulation of
-    that schedule bit for bit; modes that walk tiles by node range refuse a sharded engine."""
-    import json
-    script = tmp_path / "sharded.py"
-    script.write_text(SHARDED)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29519", str(script)], capture_output=True, text=True, env=dict(os.environ, PGSGD_ROOT=ROOT), timeout=600)
-    assert r.returncode == 0, r.stderr[-3000:]
-    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
-    assert res["equal"] and res["updates"] == res["expected"] and res["refused"], res

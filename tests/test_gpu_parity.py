@@ -93,37 +93,6 @@ def test_2d_single_stream_bit_exact(graphs, name, flags):
 
 
 @pytest.mark.parametrize("flags", [0, capi.PGSGD_FLAG_EXCH_WRITE])
-@pytest.mark.parametrize("name", ["overlap", "k", "note5"])
-def test_odd_shaped_graphs_single_stream_bit_exact(graphs, name, flags):
-    """The reference's small test graphs with the corners of the path: a 1-step path and a node repeated back to back
-    (overlap.gfa: terms whose two ends are the SAME coordinate), two short paths (k.gfa), a reverse-strand step (note5.gfa).
-    The oracle is pinned on exactly these against the reference (tests/golden/{overlap,k,note5}.pin*)."""
-    gd, go = graphs[name]
-    kw = dict(iter_max=3, min_term_updates=2000, eta_max=50.0)
-    cd, co = _cfgs(gd, go, 2, **kw)
-    cd.n_streams, cd.batch, cd.flags = 1, 1, flags
-    X0, Y0 = orc.layout_init(go, seed=5)
-    xy0 = orc.XY_to_xy(X0, Y0)
-    n_ref, xy_ref = orc.layout_2d_f32(go, co, xy0.copy(), n_streams=1)
-    with odgi_b200.Engine(gd) as e:
-        e.set_coords_2d_f32(xy0)
-        st = e.run_2d(cd)
-        xy_dev = e.get_coords_2d_f32()
-    assert st["term_updates"] == n_ref == 3 * 2000
-    assert np.array_equal(xy_dev, xy_ref)
-    kw = dict(iter_max=2, min_term_updates=2000, eta_max=50.0)
-    cd, co = _cfgs(gd, go, 1, **kw)
-    cd.n_streams, cd.batch, cd.flags = 1, 1, flags
-    n_ref, x_ref = orc.sort_1d(go, co, orc.sort_init(go), n_streams=1)
-    with odgi_b200.Engine(gd) as e:
-        e.set_coords_1d(None)
-        st = e.run_1d(cd)
-        x_dev = e.get_coords_1d()
-    assert st["term_updates"] == n_ref == 3 * 2000
-    assert np.array_equal(x_dev, x_ref)
-
-
-@pytest.mark.parametrize("flags", [0, capi.PGSGD_FLAG_EXCH_WRITE])
 @pytest.mark.parametrize("name", ["LPA", "DRB1-3123"])
 def test_1d_single_stream_bit_exact(graphs, name, flags):
     gd, go = graphs[name]
@@ -548,32 +517,3 @@ def test_degenerate_graphs_do_nothing_like_the_reference():
     empty = odgi_b200.FlatGraph(node_len, np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.uint8))
     X, Y, st = odgi_b200.layout_2d(empty, capi.Config(iter_max=3, min_term_updates=10, eta_max=4.0, space=1), X0, Y0)
     assert st["term_updates"] == 0 and np.array_equal(X, X0)
-
-
-def test_path_sharded_engine_runs_its_share(graphs):
-    """pgsgd_engine_set_shard: an engine created from a subset of the job's paths performs U * S_shard / S updates per
-    iteration on them (single stream: bit-identical to the oracle on the same shard; tile sampling: the same count)."""
-    gd, go = graphs["chr6.C4"]
-    shard = odgi_b200.shard_paths(gd, 2, 1)
-    g_shard = orc.Graph(shard.node_len, shard.path_first_step, shard.step_node, shard.step_rev)
-    kw = dict(iter_max=3, min_term_updates=9001, eta_max=2000.0)
-    cd, co = _cfgs(gd, go, 2, **kw)          # the config of the WHOLE job (space, eta_max from the longest path of the job)
-    cd.n_streams, cd.batch = 1, 1
-    share = 9001 * shard.S // gd.S
-    X0, Y0 = orc.layout_init(go, seed=9)
-    xy_ref = orc.XY_to_xy(X0, Y0)
-    n_ref = orc.run_range(g_shard, co, 1, co.seed, share, 0, 3, 1, xy=xy_ref)
-    with odgi_b200.Engine(shard) as e:
-        e.set_shard(gd.S)
-        e.set_coords_2d_f32(orc.XY_to_xy(X0, Y0))
-        st = e.run_2d(cd)
-        xy_dev = e.get_coords_2d_f32()
-        assert st["term_updates"] == n_ref == 3 * share
-        assert np.array_equal(xy_dev, xy_ref)
-        # tile sampling on the shard: whole passes over the shard's steps + a truncated one
-        ct = capi.layout_defaults(gd, iter_max=2, sampling=capi.SAMPLING_TILE)
-        e.set_coords_2d(X0, Y0)
-        st = e.run_2d(ct)
-        assert abs(int(st["term_updates"]) - 2 * (ct.min_term_updates * shard.S // gd.S)) <= 2 * 2048
-        with pytest.raises(odgi_b200.PgsgdError):
-            e.set_shard(shard.S - 1)          # a job cannot be smaller than one of its shards

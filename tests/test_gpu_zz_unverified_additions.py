@@ -1,0 +1,200 @@
+"""GPU tests written AFTER round 1's GPU budget was spent: none of them has run on a device yet.  They live in
+their own file, last in collection order, so that `pytest -x` reaches every test that HAS been verified before any of these."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import odgi_b200
+from odgi_b200 import capi, synth
+from odgi_b200.arrays import read_arrays
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "odgi_b200", "host", "pgsgd")
+
+
+@pytest.fixture(scope="module")
+def graphs(golden_graphs):
+    return {k: (odgi_b200.graph_from_arrays(a), orc.Graph.from_arrays(a)) for k, a in golden_graphs.items()}
+
+
+def _cfgs(gd, go, dims, **kw):
+    if dims == 2:
+        return capi.layout_defaults(gd, **kw), orc.default_layout_config(go, **kw)
+    return capi.sort_defaults(gd, **kw), orc.default_sort_config(go, **kw)
+
+
+@pytest.fixture(scope="module")
+def drb1(golden_graphs, tmp_path_factory):
+    a = golden_graphs["DRB1-3123"]
+    g = odgi_b200.graph_from_arrays(a)
+    gfa = tmp_path_factory.mktemp("gfa") / "DRB1-3123.gfa"
+    synth.write_gfa(g, str(gfa))
+    return str(gfa), orc.Graph.from_arrays(a)
+
+
+@pytest.mark.parametrize("flags", [0, capi.PGSGD_FLAG_EXCH_WRITE])
+@pytest.mark.parametrize("name", ["overlap", "k", "note5"])
+def test_odd_shaped_graphs_single_stream_bit_exact(graphs, name, flags):
+    """The reference's small test graphs with the corners of the path: a 1-step path and a node repeated back to back
+    (overlap.gfa: terms whose two ends are the SAME coordinate), two short paths (k.gfa), a reverse-strand step (note5.gfa).
+    The oracle is pinned on exactly these against the reference (tests/golden/{overlap,k,note5}.pin*)."""
+    gd, go = graphs[name]
+    kw = dict(iter_max=3, min_term_updates=2000, eta_max=50.0)
+    cd, co = _cfgs(gd, go, 2, **kw)
+    cd.n_streams, cd.batch, cd.flags = 1, 1, flags
+    X0, Y0 = orc.layout_init(go, seed=5)
+    xy0 = orc.XY_to_xy(X0, Y0)
+    n_ref, xy_ref = orc.layout_2d_f32(go, co, xy0.copy(), n_streams=1)
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_2d_f32(xy0)
+        st = e.run_2d(cd)
+        xy_dev = e.get_coords_2d_f32()
+    assert st["term_updates"] == n_ref == 3 * 2000
+    assert np.array_equal(xy_dev, xy_ref)
+    kw = dict(iter_max=2, min_term_updates=2000, eta_max=50.0)
+    cd, co = _cfgs(gd, go, 1, **kw)
+    cd.n_streams, cd.batch, cd.flags = 1, 1, flags
+    n_ref, x_ref = orc.sort_1d(go, co, orc.sort_init(go), n_streams=1)
+    with odgi_b200.Engine(gd) as e:
+        e.set_coords_1d(None)
+        st = e.run_1d(cd)
+        x_dev = e.get_coords_1d()
+    assert st["term_updates"] == n_ref == 3 * 2000
+    assert np.array_equal(x_dev, x_ref)
+
+
+def test_path_sharded_engine_runs_its_share(graphs):
+    """pgsgd_engine_set_shard: an engine created from a subset of the job's paths performs U * S_shard / S updates per
+    iteration on them (single stream: bit-identical to the oracle on the same shard; tile sampling: the same count)."""
+    gd, go = graphs["chr6.C4"]
+    shard = odgi_b200.shard_paths(gd, 2, 1)
+    g_shard = orc.Graph(shard.node_len, shard.path_first_step, shard.step_node, shard.step_rev)
+    kw = dict(iter_max=3, min_term_updates=9001, eta_max=2000.0)
+    cd, co = _cfgs(gd, go, 2, **kw)          # the config of the WHOLE job (space, eta_max from the longest path of the job)
+    cd.n_streams, cd.batch = 1, 1
+    share = 9001 * shard.S // gd.S
+    X0, Y0 = orc.layout_init(go, seed=9)
+    xy_ref = orc.XY_to_xy(X0, Y0)
+    n_ref = orc.run_range(g_shard, co, 1, co.seed, share, 0, 3, 1, xy=xy_ref)
+    with odgi_b200.Engine(shard) as e:
+        e.set_shard(gd.S)
+        e.set_coords_2d_f32(orc.XY_to_xy(X0, Y0))
+        st = e.run_2d(cd)
+        xy_dev = e.get_coords_2d_f32()
+        assert st["term_updates"] == n_ref == 3 * share
+        assert np.array_equal(xy_dev, xy_ref)
+        # tile sampling on the shard: whole passes over the shard's steps + a truncated one
+        ct = capi.layout_defaults(gd, iter_max=2, sampling=capi.SAMPLING_TILE)
+        e.set_coords_2d(X0, Y0)
+        st = e.run_2d(ct)
+        assert abs(int(st["term_updates"]) - 2 * (ct.min_term_updates * shard.S // gd.S)) <= 2 * 2048
+        with pytest.raises(odgi_b200.PgsgdError):
+            e.set_shard(shard.S - 1)          # a job cannot be smaller than one of its shards
+
+
+def test_cli_layout_writes_the_lay_container(drb1, tmp_path):
+    """`pgsgd layout -o`: the binary container holds the coordinates of the TSV (the writer itself is byte-identical to
+    odgi's: tests/test_host_cpu.py)."""
+    gfa, go = drb1
+    tsv, lay, back = tmp_path / "lay.tsv", tmp_path / "lay.lay", tmp_path / "back.arr"
+    subprocess.run([CLI, "layout", "-i", gfa, "-T", str(tsv), "-o", str(lay), "--gpu", "--init-seed", "42"], check=True)
+    rows = np.loadtxt(str(tsv), skiprows=1)
+    subprocess.run([CLI, "lay", "-i", str(lay), "-a", str(back)], check=True)
+    b = read_arrays(str(back))
+    assert np.allclose(b["X"], rows[:, 1], rtol=1e-12, atol=1e-6) and np.allclose(b["Y"], rows[:, 2], rtol=1e-12, atol=1e-6)
+
+
+def test_cli_sort_writes_the_1d_lay(drb1, tmp_path):
+    """`pgsgd sort -e`: (start, start + length) per sorted node on X and zeros on Y (path_sgd.cpp:659-677)."""
+    gfa, go = drb1
+    out, lay, lay_bin, back = tmp_path / "order.txt", tmp_path / "lay1d.tsv", tmp_path / "sorted.lay", tmp_path / "sorted.arr"
+    subprocess.run([CLI, "sort", "-i", gfa, "-o", str(out), "-Y", "--gpu", "--layout-out", str(lay), "-e", str(lay_bin)], check=True)
+    rows = np.loadtxt(str(lay), skiprows=1)
+    subprocess.run([CLI, "lay", "-i", str(lay_bin), "-a", str(back)], check=True)
+    b = read_arrays(str(back))
+    assert b["X"].size == 2 * go.N and not b["Y"].any()
+    assert np.allclose(b["X"][0::2], rows[:, 1], rtol=1e-12, atol=1e-6) and np.allclose(b["X"][1::2], rows[:, 2], rtol=1e-12, atol=1e-6)
+
+
+def test_cli_layout_snapshots(drb1, tmp_path):
+    """-u PREFIX: one .lay per iteration but the last, named PREFIX<iteration> (path_sgd_layout.cpp:379-409)."""
+    gfa, go = drb1
+    prefix = str(tmp_path / "snap_")
+    tsv = tmp_path / "final.tsv"
+    subprocess.run([CLI, "layout", "-i", gfa, "-T", str(tsv), "--gpu", "--init-seed", "42", "-x", "5", "-u", prefix], check=True)
+    stress = []
+    for it in range(1, 5):
+        back = tmp_path / f"snap{it}.arr"
+        subprocess.run([CLI, "lay", "-i", f"{prefix}{it}", "-a", str(back)], check=True)
+        b = read_arrays(str(back))
+        assert b["X"].size == 2 * go.N and np.all(np.isfinite(b["X"])) and np.all(np.isfinite(b["Y"]))
+        stress.append(orc.path_stress_2d(go, b["X"], b["Y"], 200000, 1))
+    assert not os.path.exists(f"{prefix}5")
+    rows = np.loadtxt(str(tsv), skiprows=1)
+    final = orc.path_stress_2d(go, rows[:, 1], rows[:, 2], 200000, 1)   # component offsetting is a translation: stress unchanged
+    assert final < stress[0] and len(set(stress)) == 4, (stress, final)
+
+
+SHARDED = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.environ["PGSGD_ROOT"])
+import torch, torch.distributed as dist
+import odgi_b200
+from odgi_b200 import capi
+from odgi_b200.arrays import read_arrays
+from oracle import oracle as orc
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo")
+a = read_arrays(os.path.join(os.environ["PGSGD_ROOT"], "tests/golden/chr6.C4.graph.arr.gz"))
+gd, go = odgi_b200.graph_from_arrays(a), orc.Graph.from_arrays(a)
+obj = [capi.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(obj, src=0)
+X0, Y0 = orc.layout_init(go, 42)
+kw = dict(iter_max=4, min_term_updates=6001, eta_max=2000.0)
+cd = capi.layout_defaults(gd, n_streams=1, batch=1, sampling=capi.SAMPLING_STREAM, **kw)   # the WHOLE job's config
+mine = odgi_b200.shard_paths(gd, world, rank)
+with odgi_b200.Engine(mine, device=rank) as e:
+    e.attach_comm(obj[0], world, rank)
+    e.set_multi_mode(capi.MULTI_ALLREDUCE)
+    e.set_shard(gd.S)
+    e.set_coords_2d_f32(orc.XY_to_xy(X0, Y0))
+    st = e.run_2d(cd)
+    xy = e.get_coords_2d_f32()
+    e.set_multi_mode(capi.MULTI_HYBRID)
+    try:
+        e.run_2d(cd); refused = False
+    except odgi_b200.PgsgdError:
+        refused = True
+shards = []
+for r in range(world):
+    s = odgi_b200.shard_paths(gd, world, r)
+    shards.append(orc.Graph(s.node_len, s.path_first_step, s.step_node, s.step_rev))
+ref = orc.emulate_sharded_2d_f32(shards, gd.S, orc.default_layout_config(go, **kw), orc.XY_to_xy(X0, Y0), 1)
+cnt = torch.tensor([int(st["term_updates"])]); dist.all_reduce(cnt)
+if rank == 0:
+    print("RESULT " + json.dumps({"equal": bool(np.array_equal(xy, ref)), "updates": int(cnt.item()), "refused": refused,
+                                  "expected": int(sum(6001 * s.S // gd.S for s in shards) * 4)}))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(odgi_b200.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_path_sharded_matches_emulation(tmp_path):
+    """Step records dealt out over the ranks by path (pgsgd_engine_set_shard): the 2-GPU run equals the oracle's emulation of
+    that schedule bit for bit; modes that walk tiles by node range refuse a sharded engine."""
+    import json
+    script = tmp_path / "sharded.py"
+    script.write_text(SHARDED)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29519", str(script)], capture_output=True, text=True, env=dict(os.environ, PGSGD_ROOT=ROOT), timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
+    assert res["equal"] and res["updates"] == res["expected"] and res["refused"], res
