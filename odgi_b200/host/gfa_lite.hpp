@@ -15,7 +15,11 @@
 namespace pgsgd {
 
 inline FlatGraph read_gfa_flat(const std::string& path) {
-    std::ifstream in(path);
+    // P lines of a chromosome-scale graph are tens of MB each: read through a large buffer (libstdc++ takes it only before open)
+    std::vector<char> iobuf(8u << 20);
+    std::ifstream in;
+    in.rdbuf()->pubsetbuf(iobuf.data(), (std::streamsize) iobuf.size());
+    in.open(path);
     if (!in) throw std::runtime_error("cannot open " + path);
     FlatGraph fg;
     std::string line;
@@ -23,7 +27,19 @@ inline FlatGraph read_gfa_flat(const std::string& path) {
     std::vector<std::pair<uint64_t, uint32_t>> segs;
     uint64_t max_id = 0;
     bool numeric = true;
+    uint64_t steps_total = 0;   // counted here so that pass 2 fills exactly-sized arrays (no regrowth of multi-GB vectors)
     while (std::getline(in, line)) {
+        if (line.size() >= 2 && line[0] == 'P' && line[1] == '\t') {
+            const size_t b = line.find('\t', 2);
+            if (b == std::string::npos) continue;   // reported in pass 2
+            size_t c = line.find('\t', b + 1);
+            if (c == std::string::npos) c = line.size();
+            if (c > b + 1) {
+                ++steps_total;
+                for (const char* q = line.data() + b + 1, * const e = line.data() + c; (q = (const char*) std::memchr(q, ',', (size_t) (e - q))) != nullptr; ++q) ++steps_total;
+            }
+            continue;
+        }
         if (line.size() < 2 || line[0] != 'S' || line[1] != '\t') continue;
         const size_t a = 2, b = line.find('\t', a);
         if (b == std::string::npos) throw std::runtime_error("malformed S line");
@@ -47,6 +63,9 @@ inline FlatGraph read_gfa_flat(const std::string& path) {
     }
     fg.node_len.assign(max_id, 0);
     for (auto& s : segs) fg.node_len[s.first - 1] = s.second;
+    fg.step_node.reserve(steps_total);
+    fg.step_rev.reserve(steps_total);
+    fg.step_pos.reserve(steps_total);
     // pass 2: paths, in file order (path handles are assigned in file order, gfa_to_handle.cpp:193-199)
     in.clear();
     in.seekg(0);
@@ -60,11 +79,11 @@ inline FlatGraph read_gfa_flat(const std::string& path) {
         const char* p = line.c_str() + b + 1;
         const char* end = line.c_str() + c;
         while (p < end) {
-            char* q = nullptr;
-            const uint64_t id = std::strtoull(p, &q, 10);
-            if (q == p || q >= end + 1 || id == 0 || id > max_id) throw std::runtime_error("bad step in path " + fg.path_names.back());
-            const bool rev = *q == '-';
-            fg.add_step((uint32_t) (id - 1), rev);
+            uint64_t id = 0;
+            const char* q = p;
+            while (q < end && (unsigned) (*q - '0') <= 9u) id = id * 10 + (uint64_t) (*q++ - '0');
+            if (q == p || q >= end || (*q != '+' && *q != '-') || id == 0 || id > max_id) throw std::runtime_error("bad step in path " + fg.path_names.back());
+            fg.add_step((uint32_t) (id - 1), *q == '-');
             p = q + 1;
             if (p < end && *p == ',') ++p;
         }
