@@ -87,6 +87,8 @@ def lib():
         L.orc_run_range.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_run_range.restype = C.c_uint64
+        L.orc_run_inflight.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_run_inflight.restype = C.c_uint64
         L.orc_peer_stale_2d_f32.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_peer_stale_2d_f32.restype = C.c_uint64
         L.orc_replay_single.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_int, C.c_uint64, C.c_uint64, C.c_double,
@@ -286,6 +288,13 @@ def run_range(g: Graph, cfg: Config, n_streams: int, seed_base: int, updates: in
     gc, cc = g.c(), cfg.c()
     return int(lib().orc_run_range(C.byref(gc), C.byref(cc), n_streams, seed_base, updates, iter_begin, iter_end, mode,
                                    _ptr(X), _ptr(Y), _ptr(xy), _ptr(frozen), _ptr(rng_state)))
+
+
+def run_inflight(g: Graph, cfg: Config, n_streams: int, dims: int, exch: bool, xy=None, X=None) -> int:
+    """Hogwild staleness model (orc_run_inflight): waves of n_streams terms that all read before any of them writes;
+    exch=False sums the displacements (red.add), True is last-writer-wins.  In place on xy (2D fp32) or X (1D)."""
+    gc, cc = g.c(), cfg.c()
+    return int(lib().orc_run_inflight(C.byref(gc), C.byref(cc), n_streams, 1 if dims == 2 else 2, 1 if exch else 0, _ptr(xy), _ptr(X)))
 
 
 def emulate_sharded_2d_f32(shards, global_steps: int, cfg: Config, xy0, n_streams: int):

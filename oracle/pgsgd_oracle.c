@@ -399,6 +399,85 @@ static uint64_t run_streams_range(const orc_graph* g, const orc_config* c, uint6
     return counted;
 }
 
+/* Hogwild staleness model (a planning tool for the launch-shape caps, DESIGN.md 3.4 — NOT a model of the reference): the
+ * n_streams worker streams advance in waves; within a wave every stream reads the coordinates as they were when the wave
+ * began, and the writes land together at its end — either summed (write = 0: the device's red.add) or last-writer-wins on
+ * top of the stale value (write = 1: atomicExch / plain store).  n_streams terms in flight with the longest possible
+ * read-to-write distance: an upper bound on what that many GPU threads in flight do.  mode 1 = 2D fp32, mode 2 = 1D. */
+uint64_t orc_run_inflight(const orc_graph* g, const orc_config* c, uint64_t n_streams, int mode, int write, float* xy, double* X) {
+    if (!any_path_with_more_than_one_step(g)) return 0;
+    run_tables rt;
+    tables_init(&rt, c);
+    orc_rng* rngs = (orc_rng*) malloc(sizeof(orc_rng) * n_streams);
+    for (uint64_t t = 0; t < n_streams; ++t) orc_rng_seed(&rngs[t], c->seed + t);
+    uint64_t* ia = (uint64_t*) malloc(sizeof(uint64_t) * n_streams * 2);
+    double* dv = (double*) malloc(sizeof(double) * n_streams * 4);   /* per term: rx, ry, stale a.x.., used per mode */
+    double* stale = (double*) malloc(sizeof(double) * n_streams * 4);
+    const int dims = mode == 2 ? 1 : 2;
+    const uint64_t n_iters = mode == 2 ? c->iter_max + 1 : c->iter_max;
+    uint64_t counted = 0;
+    for (uint64_t iter = 0; iter < n_iters; ++iter) {
+        const double eta = rt.etas[iter];
+        int cooling;
+        double theta_zipf = c->theta;
+        if (mode == 2) { cooling = iter > rt.first_cooling_iteration; if (cooling) theta_zipf = 0.001; }
+        else cooling = iter >= rt.first_cooling_iteration;
+        uint64_t done = 0;
+        while (done < c->min_term_updates) {
+            uint64_t n = 0;
+            for (uint64_t t = 0; t < n_streams && done + n < c->min_term_updates; ++t) {   /* reads of the wave */
+                orc_term term;
+                if (!orc_sample_term(g, c, rt.zetas, dims, cooling, theta_zipf, &rngs[t], &term)) continue;
+                if (mode == 2) {
+                    double d = fabs((double) term.pos_a - (double) term.pos_b);
+                    if (d == 0) continue;
+                    double mu = eta / d; if (mu > 1) mu = 1;
+                    double xa = X[term.node_a], xb = X[term.node_b];
+                    double dx = xa - xb; if (dx == 0) dx = 1e-9;
+                    double mag = fabs(dx);
+                    double r_x = mu * (mag - d) / 2 / mag * dx;
+                    ia[2 * n] = term.node_a; ia[2 * n + 1] = term.node_b;
+                    dv[4 * n] = r_x; stale[4 * n] = xa; stale[4 * n + 1] = xb;
+                } else {
+                    uint64_t dpos = term.pos_a > term.pos_b ? term.pos_a - term.pos_b : term.pos_b - term.pos_a;
+                    float d = dpos ? (float) dpos : 1e-9f;
+                    float mu = (float) eta / d; if (mu > 1.0f) mu = 1.0f;
+                    uint64_t pa = 4 * (uint64_t) term.node_a + 2 * (term.end_a ? 1 : 0), pb = 4 * (uint64_t) term.node_b + 2 * (term.end_b ? 1 : 0);
+                    float dx = xy[pa] - xy[pb], dy = xy[pa + 1] - xy[pb + 1];
+                    if (dx == 0.0f) dx = 1e-9f;
+                    float mag = sqrtf(dx * dx + dy * dy);
+                    float r = mu * (mag - d) * 0.5f / mag;
+                    ia[2 * n] = pa; ia[2 * n + 1] = pb;
+                    dv[4 * n] = r * dx; dv[4 * n + 1] = r * dy;
+                    stale[4 * n] = xy[pa]; stale[4 * n + 1] = xy[pa + 1]; stale[4 * n + 2] = xy[pb]; stale[4 * n + 3] = xy[pb + 1];
+                }
+                ++n;
+            }
+            for (uint64_t k = 0; k < n; ++k) {   /* writes of the wave */
+                if (mode == 2) {
+                    if (write == 0) { X[ia[2 * k]] -= dv[4 * k]; X[ia[2 * k + 1]] += dv[4 * k]; }
+                    else { X[ia[2 * k]] = stale[4 * k] - dv[4 * k]; X[ia[2 * k + 1]] = stale[4 * k + 1] + dv[4 * k]; }
+                } else {
+                    const uint64_t pa = ia[2 * k], pb = ia[2 * k + 1];
+                    if (write == 0) {
+                        xy[pa] -= (float) dv[4 * k]; xy[pa + 1] -= (float) dv[4 * k + 1];
+                        xy[pb] += (float) dv[4 * k]; xy[pb + 1] += (float) dv[4 * k + 1];
+                    } else {
+                        xy[pa] = (float) (stale[4 * k] - dv[4 * k]); xy[pa + 1] = (float) (stale[4 * k + 1] - dv[4 * k + 1]);
+                        xy[pb] = (float) (stale[4 * k + 2] + dv[4 * k]); xy[pb + 1] = (float) (stale[4 * k + 3] + dv[4 * k + 1]);
+                    }
+                }
+            }
+            done += n;
+            counted += n;
+            if (n == 0) break;
+        }
+    }
+    free(rngs); free(ia); free(dv); free(stale);
+    tables_free(&rt);
+    return counted;
+}
+
 static uint64_t run_streams(const orc_graph* g, const orc_config* c, uint64_t n_streams, int mode, double* X, double* Y,
                             float* xy, const uint8_t* frozen) {
     return run_streams_range(g, c, n_streams, c->seed, c->min_term_updates, 0, UINT64_MAX, mode, X, Y, xy, frozen, NULL);

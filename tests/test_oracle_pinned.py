@@ -126,3 +126,20 @@ def test_runs_are_deterministic_and_count_updates(golden_graphs):
     cfg1 = orc.default_sort_config(g, iter_max=3, min_term_updates=5000)
     n3, _ = orc.sort_1d(g, cfg1, orc.sort_init(g), n_streams=3)
     assert n3 == 4 * 5000  # 1D runs iter_max + 1 iterations (path_sgd.cpp:181)
+
+
+def test_staleness_model_reduces_to_the_sequential_run(golden_graphs):
+    """orc_run_inflight (planning tool for the launch caps): one term in flight is the sequential single-stream run up to
+    fp32 rounding of the intermediate products; a few hundred in flight stay in the reference's stress band."""
+    g = orc.Graph.from_arrays(golden_graphs["DRB1-3123"])
+    cfg = orc.default_layout_config(g, iter_max=6, min_term_updates=20000)
+    X0, Y0 = orc.layout_init(g, 42)
+    _, seq = orc.layout_2d_f32(g, cfg, orc.XY_to_xy(X0, Y0), n_streams=1)
+    xy = orc.XY_to_xy(X0, Y0)
+    assert orc.run_inflight(g, cfg, 1, 2, False, xy=xy) == 6 * 20000
+    s_seq = orc.path_stress_2d(g, *orc.xy_to_XY(seq), 200000, 1)
+    s_one = orc.path_stress_2d(g, *orc.xy_to_XY(xy), 200000, 1)
+    assert abs(s_one - s_seq) <= 0.02 * s_seq, (s_one, s_seq)
+    x = orc.sort_init(g)
+    c1 = orc.default_sort_config(g, iter_max=10)
+    assert orc.run_inflight(g, c1, 256, 1, True, X=x) == 11 * c1.min_term_updates and np.all(np.isfinite(x))
