@@ -89,6 +89,8 @@ def lib():
         L.orc_run_range.restype = C.c_uint64
         L.orc_run_inflight.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_run_inflight.restype = C.c_uint64
+        L.orc_run_tile_order.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_run_tile_order.restype = C.c_uint64
         L.orc_peer_stale_2d_f32.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.orc_peer_stale_2d_f32.restype = C.c_uint64
         L.orc_replay_single.argtypes = [C.POINTER(_Graph), C.POINTER(_Config), C.c_int, C.c_uint64, C.c_uint64, C.c_double,
@@ -288,6 +290,12 @@ def run_range(g: Graph, cfg: Config, n_streams: int, seed_base: int, updates: in
     gc, cc = g.c(), cfg.c()
     return int(lib().orc_run_range(C.byref(gc), C.byref(cc), n_streams, seed_base, updates, iter_begin, iter_end, mode,
                                    _ptr(X), _ptr(Y), _ptr(xy), _ptr(frozen), _ptr(rng_state)))
+
+
+def run_tile_order(g: Graph, cfg: Config, tile_steps: int, dims: int, xy=None, X=None) -> int:
+    """Sequential tile-ORDER model of the device's tile sampling (orc_run_tile_order), exact partner law.  In place."""
+    gc, cc = g.c(), cfg.c()
+    return int(lib().orc_run_tile_order(C.byref(gc), C.byref(cc), tile_steps, 1 if dims == 2 else 2, _ptr(xy), _ptr(X)))
 
 
 def run_inflight(g: Graph, cfg: Config, n_streams: int, dims: int, exch: bool, xy=None, X=None) -> int:

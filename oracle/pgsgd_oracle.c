@@ -159,11 +159,20 @@ static uint64_t find_path(const orc_graph* g, uint64_t idx) {
     return lo;
 }
 
+static int sample_term_at(const orc_graph* g, const orc_config* c, const double* zetas, int dims, int cooling,
+                          double theta_zipf, orc_rng* rng, uint64_t step_index, orc_term* t);
+
 int orc_sample_term(const orc_graph* g, const orc_config* c, const double* zetas, int dims, int cooling,
                     double theta_zipf, orc_rng* rng, orc_term* t) {
-    memset(t, 0, sizeof(*t));
     /* path_sgd_layout.cpp:175,182: dis_step(0, np_bv.size()-1) */
     uint64_t step_index = orc_uniform(rng, g->step_count);
+    return sample_term_at(g, c, zetas, dims, cooling, theta_zipf, rng, step_index, t);
+}
+
+/* everything after the first pick: the partner and the node ends, given the first step */
+static int sample_term_at(const orc_graph* g, const orc_config* c, const double* zetas, int dims, int cooling,
+                          double theta_zipf, orc_rng* rng, uint64_t step_index, orc_term* t) {
+    memset(t, 0, sizeof(*t));
     uint64_t idx = g->step_perm ? g->step_perm[step_index] : step_index;
     /* :186,199: path_i = npi_iv[step_index]; s_rank = nr_iv[step_index] - 1 */
     uint64_t p = find_path(g, idx);
@@ -395,6 +404,51 @@ static uint64_t run_streams_range(const orc_graph* g, const orc_config* c, uint6
     if (rng_state) memcpy(rng_state, rngs, sizeof(orc_rng) * n_streams);
     free(rngs);
     free(remaining);
+    tables_free(&rt);
+    return counted;
+}
+
+/* Tile-ORDER model of the device's tile sampling (pgsgd_tile_kernel), sequential and with the exact partner law: per
+ * iteration every step is the first step of floor(U/S) terms (+1 for the steps of the leading tiles of a last, partial
+ * pass); tiles of tile_steps consecutive steps are visited in a fresh pseudo-random bijection per pass, the steps of a tile
+ * in order.  Isolates what the blocked ORDER of terms does to the result (no concurrency, no fp32 sampler).
+ * mode 1 = 2D fp32, mode 2 = 1D. */
+uint64_t orc_run_tile_order(const orc_graph* g, const orc_config* c, uint64_t tile_steps, int mode, float* xy, double* X) {
+    if (!any_path_with_more_than_one_step(g) || tile_steps == 0) return 0;
+    run_tables rt;
+    tables_init(&rt, c);
+    orc_rng rng, perm_rng;
+    orc_rng_seed(&rng, c->seed);
+    orc_rng_seed(&perm_rng, c->seed ^ 0x9e3779b97f4a7c15ULL);
+    const int dims = mode == 2 ? 1 : 2;
+    const uint64_t n_iters = mode == 2 ? c->iter_max + 1 : c->iter_max;
+    const uint64_t S = g->step_count, n_tiles = (S + tile_steps - 1) / tile_steps;
+    uint64_t* order = (uint64_t*) malloc(sizeof(uint64_t) * n_tiles);
+    uint64_t counted = 0;
+    for (uint64_t iter = 0; iter < n_iters; ++iter) {
+        const double eta = rt.etas[iter];
+        int cooling;
+        double theta_zipf = c->theta;
+        if (mode == 2) { cooling = iter > rt.first_cooling_iteration; if (cooling) theta_zipf = 0.001; }
+        else cooling = iter >= rt.first_cooling_iteration;
+        uint64_t left = c->min_term_updates;
+        while (left) {
+            for (uint64_t i = 0; i < n_tiles; ++i) order[i] = i;                       /* Fisher-Yates: one bijection per pass */
+            for (uint64_t i = n_tiles - 1; i > 0; --i) { uint64_t j = orc_uniform(&perm_rng, i + 1), tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+            for (uint64_t k = 0; k < n_tiles && left; ++k) {
+                const uint64_t lo = order[k] * tile_steps, hi = lo + tile_steps < S ? lo + tile_steps : S;
+                for (uint64_t s = lo; s < hi && left; ++s) {
+                    orc_term term;
+                    --left;                                                            /* a visit slot is used whether or not it counts */
+                    if (!sample_term_at(g, c, rt.zetas, dims, cooling, theta_zipf, &rng, s, &term)) continue;
+                    if (mode == 1) orc_apply_2d_f32(&term, eta, xy);
+                    else if (orc_apply_1d(&term, eta, X, NULL) < 0) continue;
+                    ++counted;
+                }
+            }
+        }
+    }
+    free(order);
     tables_free(&rt);
     return counted;
 }

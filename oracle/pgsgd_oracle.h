@@ -141,6 +141,9 @@ double orc_path_stress_1d(const orc_graph* g, const double* X, uint64_t n_pairs,
 #ifdef __cplusplus
 }
 #endif
+/* tile-ORDER model of the device's tile sampling, sequential, exact partner law (isolates the effect of the blocked order) */
+uint64_t orc_run_tile_order(const orc_graph* g, const orc_config* c, uint64_t tile_steps, int mode, float* xy, double* X);
+
 /* Hogwild staleness model: waves of n_streams terms that all read before any of them writes (planning tool) */
 uint64_t orc_run_inflight(const orc_graph* g, const orc_config* c, uint64_t n_streams, int mode, int write, float* xy, double* X);
 
