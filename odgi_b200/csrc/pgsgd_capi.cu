@@ -508,7 +508,9 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         const double hub_terms = e->S ? in_flight * 2.0 * (double) e->max_node_depth / (double) e->S : 0.0;
         // Over NVLink a term stays in flight several times longer than on one GPU, and the LPA 1D run on 2 GPUs at 3.7 left
         // the reference band (round 1, tests/test_gpu_multi.py), so peer phases switch earlier.
-        const double hub_margin = peer ? 2.0 : 4.0;
+        // One GPU: measured in band up to ~2.3 and diverging from ~9; the staleness model (oracle/pgsgd_oracle.c
+        // orc_run_inflight, the worst-case read-to-write distance) turns unstable at ~2.5, so nothing in between is trusted.
+        const double hub_margin = peer ? 2.0 : 2.5;
         if (hub_terms > hub_margin && !(p.flags & (PGSGD_FLAG_EXCH_WRITE | PGSGD_FLAG_PLAIN_STORE))) {
             p.flags |= PGSGD_FLAG_EXCH_WRITE;
             st.flags_used |= PGSGD_FLAG_EXCH_WRITE;
