@@ -103,6 +103,8 @@ typedef struct pgsgd_config {
 #define PGSGD_FLAG_PLAIN_STORE  4u  /* st.global of the new (x,y) (slower on B200: 14 vs 21 G updates/s, profiles/) */
 #define PGSGD_FLAG_TMA_STAGING  8u  /* tile kernel: stage tiles with double-buffered TMA bulk copies (cp.async.bulk + mbarrier) instead of
                                        coalesced LDG/STS into one buffer; measured slower on B200, kept for comparison */
+#define PGSGD_FLAG_KEEP_ADD    16u  /* experiments only: keep the red.add write even where the hub safeguard would switch to the
+                                       exchange write — used to measure where the summed write really turns unstable */
 #define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
 
 typedef struct pgsgd_stats {

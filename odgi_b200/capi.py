@@ -19,6 +19,7 @@ PGSGD_FLAG_EXCH_WRITE = 1
 PGSGD_FLAG_SUM_DELTAS = 2
 PGSGD_FLAG_PLAIN_STORE = 4
 PGSGD_FLAG_TMA_STAGING = 8
+PGSGD_FLAG_KEEP_ADD = 16
 SAMPLING_AUTO, SAMPLING_STREAM, SAMPLING_TILE = 0, 1, 2
 MULTI_ALLREDUCE, MULTI_PEER, MULTI_HYBRID = 0, 1, 2
 

@@ -511,7 +511,7 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         // One GPU: measured in band up to ~2.3 and diverging from ~9; the staleness model (oracle/pgsgd_oracle.c
         // orc_run_inflight, the worst-case read-to-write distance) turns unstable at ~2.5, so nothing in between is trusted.
         const double hub_margin = peer ? 2.0 : 2.5;
-        if (hub_terms > hub_margin && !(p.flags & (PGSGD_FLAG_EXCH_WRITE | PGSGD_FLAG_PLAIN_STORE))) {
+        if (hub_terms > hub_margin && !(p.flags & (PGSGD_FLAG_EXCH_WRITE | PGSGD_FLAG_PLAIN_STORE | PGSGD_FLAG_KEEP_ADD))) {
             p.flags |= PGSGD_FLAG_EXCH_WRITE;
             st.flags_used |= PGSGD_FLAG_EXCH_WRITE;
         }
