@@ -34,7 +34,9 @@ def _stale() -> bool:
 def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+    # experiments: PGSGD_TILE_STEPS=4096 python -m odgi_b200.build  (the default build takes the header's 2048)
+    tile = ["-DPGSGD_TILE_STEPS=" + os.environ["PGSGD_TILE_STEPS"]] if os.environ.get("PGSGD_TILE_STEPS") else []
+    cmd = [_nvcc()] + NVCC_FLAGS + tile + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-lnccl"]
     env = dict(os.environ)
     # nvcc must drive the system g++ (an alternative g++ on PATH lacks the OpenMP spec files and is untested with nvcc)

@@ -45,7 +45,11 @@ struct IterParams {
 };
 
 constexpr int STRESS_STREAMS = 4096;   // generators of the sampled path stress (== ORC_STRESS_STREAMS of the oracle)
-constexpr int TILE_STEPS = 2048;   // steps staged in shared memory per tile visit (32 KB of 16-byte records)
+#ifndef PGSGD_TILE_STEPS
+#define PGSGD_TILE_STEPS 2048      // experiments: PGSGD_TILE_STEPS=4096 python -m odgi_b200.build (1024, 2048 or 4096)
+#endif
+constexpr int TILE_STEPS = PGSGD_TILE_STEPS;   // steps staged in shared memory per tile visit (2048: 32 KB of 16-byte records)
+static_assert(TILE_STEPS == 1024 || TILE_STEPS == 2048 || TILE_STEPS == 4096, "tile size: 1024, 2048 or 4096 steps");
 
 struct LaunchShape {
     int block;           // threads per block
