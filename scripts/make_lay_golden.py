@@ -35,7 +35,40 @@ def cases():
     }
 
 
+def fuzz(n_cases: int):
+    """random coordinate sets of six kinds (wide dynamic range, many equal values, sorted, subnormals, all equal, integers):
+    writer bytes == reference bytes and reader == (X - min) + min, for every case"""
+    tmp = tempfile.mkdtemp()
+    rng = np.random.default_rng(123)
+    for case in range(n_cases):
+        n, kind = int(rng.integers(1, 700)), case % 6
+        if kind == 0:
+            X, Y = rng.normal(0, 10 ** rng.uniform(-5, 12), n), rng.normal(0, 10 ** rng.uniform(-5, 12), n)
+        elif kind == 1:
+            X, Y = np.round(rng.normal(0, 100, n)), np.round(rng.normal(0, 3, n))
+        elif kind == 2:
+            X, Y = np.sort(rng.uniform(0, 1e9, n)), np.zeros(n)
+        elif kind == 3:
+            X, Y = rng.uniform(-1, 1, n) * 1e-310, rng.uniform(-1, 1, n) * 1e-308
+        elif kind == 4:
+            X, Y = np.full(n, 7.25), np.full(n, 7.25)
+        else:
+            X, Y = rng.integers(-2 ** 40, 2 ** 40, n).astype(np.float64), rng.integers(0, 3, n).astype(np.float64)
+        a, r, m, back = (os.path.join(tmp, f) for f in ("a.arr", "r.lay", "m.lay", "b.arr"))
+        write_arrays(a, {"X": X.astype(np.float64), "Y": Y.astype(np.float64)})
+        subprocess.run([REF, "lay_write", a, r], check=True)
+        subprocess.run([CLI, "lay", "-c", a, "-o", m], check=True)
+        assert open(r, "rb").read() == open(m, "rb").read(), (case, kind, n)
+        subprocess.run([CLI, "lay", "-i", r, "-a", back], check=True)
+        b, mv = read_arrays(back), min(X.min(), Y.min())
+        assert np.array_equal(b["X"], (X - mv) + mv) and np.array_equal(b["Y"], (Y - mv) + mv), (case, kind, n)
+    shutil.rmtree(tmp)
+    print(f"[lay] fuzz: {n_cases} random coordinate sets, writer byte-identical to the reference and reader exact in every case")
+
+
 def main():
+    if "--fuzz" in sys.argv[1:]:
+        return fuzz(int(sys.argv[sys.argv.index("--fuzz") + 1]))
     tmp = tempfile.mkdtemp()
     for name, (X, Y) in cases().items():
         arr = os.path.join(GOLD, f"lay_{name}.arr.gz")
