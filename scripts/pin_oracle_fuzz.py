@@ -39,6 +39,8 @@ def main():
             arrs = po.dump_graph(name, tmp)
             po.pin_2d(name, arrs, tmp, cooling_start=0.5, updates=2500, tag="cool")
             po.pin_1d(name, arrs, tmp, updates=2500)
+            if k % 4 == 1:
+                po.pin_1d(name, arrs, tmp, updates=2500, freeze_mod=2)    # `sort -H`: every second node stays put
     print(f"[fuzz] {n_graphs} random graphs: 2D and 1D traces and final coordinates bit-exact vs the reference")
 
 
