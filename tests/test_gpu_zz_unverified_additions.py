@@ -198,3 +198,36 @@ def test_two_rank_path_sharded_matches_emulation(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1][7:])
     assert res["equal"] and res["updates"] == res["expected"] and res["refused"], res
+
+
+def test_random_graphs_single_stream_bit_exact():
+    """Device vs oracle on random small graphs (random node lengths, random walks with reverse-strand steps, 1-step paths,
+    revisited nodes) — the population the oracle itself is fuzz-pinned on against the reference (scripts/pin_oracle_fuzz.py)."""
+    rng = np.random.default_rng(2024)
+    for k in range(12):
+        N, P = int(rng.integers(2, 80)), int(rng.integers(1, 7))
+        node_len = rng.integers(1, 60, size=N).astype(np.uint32)
+        counts = rng.integers(2, 120, size=P)
+        if P > 1 and k % 3 == 0:
+            counts[rng.integers(0, P)] = 1
+        first = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64)
+        S = int(first[-1])
+        step_node = rng.integers(0, N, size=S).astype(np.uint32)
+        step_rev = (rng.random(S) < 0.3).astype(np.uint8)
+        gd = odgi_b200.FlatGraph(node_len, first, step_node, step_rev)
+        go = orc.Graph(node_len, first, step_node, step_rev)
+        kw = dict(iter_max=3, min_term_updates=1500, eta_max=100.0)
+        cd, co = _cfgs(gd, go, 2, **kw)
+        cd.n_streams, cd.batch = 1, 1
+        X0, Y0 = orc.layout_init(go, seed=k)
+        n_ref, xy_ref = orc.layout_2d_f32(go, co, orc.XY_to_xy(X0, Y0), n_streams=1)
+        cd1, co1 = _cfgs(gd, go, 1, iter_max=2, min_term_updates=1500, eta_max=100.0)
+        cd1.n_streams, cd1.batch = 1, 1
+        n1_ref, x_ref = orc.sort_1d(go, co1, orc.sort_init(go), n_streams=1)
+        with odgi_b200.Engine(gd) as e:
+            e.set_coords_2d_f32(orc.XY_to_xy(X0, Y0))
+            st = e.run_2d(cd)
+            assert st["term_updates"] == n_ref and np.array_equal(e.get_coords_2d_f32(), xy_ref), k
+            e.set_coords_1d(None)
+            st = e.run_1d(cd1)
+            assert st["term_updates"] == n1_ref and np.array_equal(e.get_coords_1d(), x_ref), k
