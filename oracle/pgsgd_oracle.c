@@ -576,7 +576,7 @@ uint64_t orc_peer_stale_2d_f32(const orc_graph* g, const orc_config* c, uint64_t
             uint64_t left = slice;
             while (left) {
                 for (uint64_t t = 0; t < T && left; ++t) {
-                    const uint64_t r = t / streams_per_rank;
+                    const uint64_t r = t % n_ranks;   /* ranks interleaved: concurrent ranks have no order among themselves */
                     orc_term term;
                     if (!orc_sample_term(g, c, rt.zetas, 2, cooling, c->theta, &rngs[t], &term)) continue;
                     uint64_t oa = term.node_a / chunk, ob = term.node_b / chunk;
