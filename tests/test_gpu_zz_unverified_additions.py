@@ -231,3 +231,29 @@ def test_random_graphs_single_stream_bit_exact():
             e.set_coords_1d(None)
             st = e.run_1d(cd1)
             assert st["term_updates"] == n1_ref and np.array_equal(e.get_coords_1d(), x_ref), k
+
+
+def _band(name):
+    with open(os.path.join(ROOT, "tests", "golden", "stress_reference.json")) as f:
+        return json.load(f)[name]
+
+
+def test_lpa_2d_default_run_in_reference_band(graphs):
+    """LPA in 2D: a hub-heavy graph (the default launch switches to the exchange write by itself) against the band of six
+    reference CPU runs (0.68477 +- 0.00002; the staleness model predicts +0.01 % for this launch shape)."""
+    gd, go = graphs["LPA"]
+    band = _band("LPA.layout2d")
+    X0, Y0 = orc.layout_init(go, seed=42)
+    X, Y, st = odgi_b200.layout_2d(gd, capi.layout_defaults(gd), X0, Y0)
+    s = orc.path_stress_2d(go, X, Y, band["n_pairs"], band["seed"])
+    assert st["flags_used"] & capi.PGSGD_FLAG_EXCH_WRITE
+    assert abs(s - band["mean"]) <= 0.01 * band["mean"] + 2 * band["sd"], (s, band["mean"])
+
+
+def test_c4_1d_default_run_in_reference_band(graphs):
+    """chr6.C4 in 1D (90 paths over 1748 nodes) against the band of six reference CPU runs (10.74 +- 0.36)."""
+    gd, go = graphs["chr6.C4"]
+    band = _band("chr6.C4.sort1d")
+    x, st = odgi_b200.sort_1d(gd, capi.sort_defaults(gd))
+    s = orc.path_stress_1d(go, x, band["n_pairs"], band["seed"])
+    assert abs(s - band["mean"]) <= 0.025 * band["mean"] + 2 * band["sd"], (s, band["mean"])
