@@ -48,7 +48,8 @@ const Flag SORT_FLAGS[] = {
     {"v", "path-sgd-eta-max", true}, {"a", "path-sgd-zipf-theta", true}, {"x", "path-sgd-iter-max", true}, {"K", "path-sgd-cooling", true},
     {"F", "path-sgd-iteration-max-learning-rate", true}, {"k", "path-sgd-zipf-space", true}, {"I", "path-sgd-zipf-space-max", true},
     {"l", "path-sgd-zipf-space-quantization-step", true}, {"t", "threads", true}, {"", "gpu", false}, {"P", "progress", false},
-    {"h", "help", false}, {"", "seed", true}, {"", "sampling", true}, {"", "layout-out", true}, {"e", "path-sgd-layout", true}};
+    {"h", "help", false}, {"", "seed", true}, {"", "sampling", true}, {"", "layout-out", true}, {"e", "path-sgd-layout", true},
+    {"f", "path-sgd-use-paths", true}, {"H", "target-paths", true}, {"", "prepared-out", true}};
 
 template <size_t NF>
 bool parse(int argc, char** argv, const Flag (&flags)[NF], Args& a, const char* sub) {
@@ -111,9 +112,28 @@ std::vector<uint32_t> components_of(const pgsgd::FlatGraph& fg, const std::strin
     return comp;
 }
 
-void common_config(const Args& a, const pgsgd::FlatGraph& fg, bool is_sort, pgsgd_config& c) {
+// what the default schedule parameters are derived from: all paths, or the ones named by -f (sort_main.cpp:355-387; the
+// sampler itself always draws from every path, path_sgd.cpp:82)
+struct PathStats { uint64_t sum_steps = 0, max_steps = 0, max_bp = 0; };
+
+PathStats path_stats(const pgsgd::FlatGraph& fg, const std::vector<uint64_t>* only = nullptr) {
+    PathStats ps;
+    auto add = [&](uint64_t p) {
+        const uint64_t lo = fg.path_first_step[p], hi = fg.path_first_step[p + 1], cnt = hi - lo;
+        const uint64_t bp = cnt ? fg.step_pos[hi - 1] + fg.node_len[fg.step_node[hi - 1]] : 0;
+        ps.sum_steps += cnt;
+        ps.max_steps = std::max(ps.max_steps, cnt);
+        ps.max_bp = std::max(ps.max_bp, bp);
+    };
+    if (only) for (uint64_t p : *only) add(p);
+    else for (uint64_t p = 0; p + 1 < fg.path_first_step.size(); ++p) add(p);
+    return ps;
+}
+
+void common_config(const Args& a, const pgsgd::FlatGraph& fg, bool is_sort, pgsgd_config& c, const PathStats* use = nullptr) {
     std::memset(&c, 0, sizeof(c));
-    const uint64_t S = fg.steps(), N = fg.node_len.size();
+    const PathStats all = use ? *use : path_stats(fg);
+    const uint64_t S = all.sum_steps, N = fg.node_len.size();
     c.iter_max = a.u64("path-sgd-iter-max", is_sort ? 100 : 30);
     c.iter_with_max_learning_rate = a.u64("path-sgd-iteration-max-learning-rate", 0);
     c.theta = a.num("path-sgd-zipf-theta", 0.99);
@@ -123,9 +143,9 @@ void common_config(const Args& a, const pgsgd::FlatGraph& fg, bool is_sort, pgsg
     if (a.has("path-sgd-min-term-updates-paths")) c.min_term_updates = (uint64_t) (a.num("path-sgd-min-term-updates-paths", 0) * (double) S);
     else if (a.has("path-sgd-min-term-updates-nodes")) c.min_term_updates = (uint64_t) (a.num("path-sgd-min-term-updates-nodes", 0) * (double) N);
     else c.min_term_updates = (uint64_t) ((is_sort ? 1.0 : 10.0) * (double) S);
-    c.eta_max = a.has("path-sgd-eta-max") ? a.num("path-sgd-eta-max", 0) : (double) fg.max_path_steps * (double) fg.max_path_steps;
+    c.eta_max = a.has("path-sgd-eta-max") ? a.num("path-sgd-eta-max", 0) : (double) all.max_steps * (double) all.max_steps;
     if (is_sort) {  // sort_main.cpp:387-412
-        const uint64_t max_len = fg.max_path_bp;
+        const uint64_t max_len = all.max_bp;
         c.space = a.has("path-sgd-zipf-space") ? std::min(a.u64("path-sgd-zipf-space", 0), max_len) : max_len;
         c.space_max = a.has("path-sgd-zipf-space-max") ? std::min(c.space, a.u64("path-sgd-zipf-space-max", 0)) : 100;
         if (a.has("path-sgd-zipf-space-quantization-step")) {
@@ -135,7 +155,7 @@ void common_config(const Args& a, const pgsgd::FlatGraph& fg, bool is_sort, pgsg
             c.space_quantization_step = std::max<uint64_t>(2, (uint64_t) std::ceil((double) (c.space - c.space_max) / (double) (max_dists - c.space_max)));
         }
     } else {  // layout_main.cpp:261-266
-        c.space = a.has("path-sgd-zipf-space") ? std::min(a.u64("path-sgd-zipf-space", 0), fg.max_path_steps) : fg.max_path_steps;
+        c.space = a.has("path-sgd-zipf-space") ? std::min(a.u64("path-sgd-zipf-space", 0), all.max_steps) : all.max_steps;
         c.space_max = a.has("path-sgd-zipf-space-max") ? std::min(c.space, a.u64("path-sgd-zipf-space-max", 0)) : 1000;
         c.space_quantization_step = a.has("path-sgd-zipf-space-quantization-step") ? std::max<uint64_t>(2, a.u64("path-sgd-zipf-space-quantization-step", 0)) : 100;
     }
@@ -303,10 +323,60 @@ int main_layout(int argc, char** argv) {
     return 0;
 }
 
+// a line-separated list of path names -> path ranks (file order)
+bool read_path_list(const std::string& file, const pgsgd::FlatGraph& fg, bool reject_duplicates, bool unknown_is_error, std::vector<uint64_t>& out) {
+    std::ifstream in(file);
+    if (!in) { std::cerr << "[odgi::sort] error: cannot open " << file << std::endl; return false; }
+    std::map<std::string, uint64_t> rank;
+    for (uint64_t p = 0; p < fg.path_names.size(); ++p) rank.emplace(fg.path_names[p], p);
+    std::vector<bool> seen(fg.path_names.size(), false);
+    std::string line;
+    uint64_t in_file = 0;
+    while (std::getline(in, line)) {
+        if (line.empty()) continue;
+        ++in_file;
+        auto it = rank.find(line);
+        if (it == rank.end()) {
+            if (unknown_is_error) std::cerr << "[odgi::sort] error: path '" << line << "' as was given by -f=[FILE], --path-sgd-use-paths=[FILE] is not present in the graph." << std::endl;
+            continue;   // sort_main.cpp:241,361-367: unknown names are skipped (with a message for -f)
+        }
+        if (seen[it->second] && reject_duplicates) { std::cerr << "[odgi::sort] error: in the path list there are duplicated path names." << std::endl; return false; }
+        seen[it->second] = true;
+        out.push_back(it->second);
+    }
+    if (reject_duplicates) std::cerr << "[odgi::sort] found " << out.size() << "/" << in_file << " paths to consider." << std::endl;
+    if (out.empty()) { std::cerr << "[odgi::sort] error: no path to consider." << std::endl; return false; }
+    return true;
+}
+
+// `odgi sort -H` (sort_graph_by_target_paths, sort_main.cpp:266-311): the nodes of the target paths come first, in the order
+// the paths first visit them (paths in file order), all other nodes follow in id order; the first `ref_nodes` ranks of the
+// reordered graph are the ones PG-SGD keeps fixed.  Returns old rank of every new rank.
+std::vector<uint32_t> reorder_by_target_paths(pgsgd::FlatGraph& fg, const std::vector<uint64_t>& targets, uint64_t& ref_nodes) {
+    const uint64_t N = fg.node_len.size();
+    std::vector<uint32_t> old_of_new;
+    old_of_new.reserve(N);
+    std::vector<bool> is_ref(N, false);
+    for (uint64_t p : targets)
+        for (uint64_t s = fg.path_first_step[p]; s < fg.path_first_step[p + 1]; ++s) {
+            const uint32_t r = fg.step_node[s];
+            if (!is_ref[r]) { is_ref[r] = true; old_of_new.push_back(r); }
+        }
+    ref_nodes = old_of_new.size();
+    for (uint32_t r = 0; r < N; ++r) if (!is_ref[r]) old_of_new.push_back(r);
+    std::vector<uint32_t> new_of_old(N);
+    for (uint32_t n = 0; n < N; ++n) new_of_old[old_of_new[n]] = n;
+    std::vector<uint32_t> len(N);
+    for (uint32_t n = 0; n < N; ++n) len[n] = fg.node_len[old_of_new[n]];
+    fg.node_len.swap(len);
+    for (auto& r : fg.step_node) r = new_of_old[r];   // positions along the paths do not change
+    return old_of_new;
+}
+
 int main_sort(int argc, char** argv) {
     Args a;
     if (!parse(argc, argv, SORT_FLAGS, a, "sort") || a.has("help") || argc == 2) {
-        std::cout << "pgsgd sort -i g.gfa -o order.txt [-e sorted.lay] -Y --gpu [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-t N] [-P]\n"
+        std::cout << "pgsgd sort -i g.gfa -o order.txt [-e sorted.lay] [-f use_paths.txt] [-H target_paths.txt] -Y --gpu [-x N] [-G N|-U N] [-j N] [-g N] [-v N] [-a N] [-K N] [-F N] [-k N] [-I N] [-l N] [-t N] [-P]\n"
                      "  the `odgi sort -Y` PG-SGD flags with the same defaults; writes the node order (one node id per line) that\n"
                      "  path_linear_sgd_order derives (sorted by position, then handle); odgi applies it with apply_ordering.\n";
         return a.has("help") ? 0 : 1;
@@ -314,16 +384,52 @@ int main_sort(int argc, char** argv) {
     if (!a.has("idx")) { std::cerr << "[odgi::sort] error: please specify an input file from where to load the graph via -i=[FILE], --idx=[FILE]." << std::endl; return 1; }
     if (!a.has("out")) { std::cerr << "[odgi::sort] error: please specify an output file to where to store the node order via -o=[FILE], --out=[FILE]." << std::endl; return 1; }
     if (!a.has("path-sgd")) { std::cerr << "[odgi::sort] error: only the path-guided SGD sort (-Y, --path-sgd) is provided by this build." << std::endl; return 1; }
-    if (int rc = need_gpu(a, "sort")) return rc;
+    if (!a.has("prepared-out")) { if (int rc = need_gpu(a, "sort")) return rc; }
     pgsgd::FlatGraph fg;
     try { fg = pgsgd::read_gfa_flat(a.str("idx")); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
-    pgsgd_config c;
-    common_config(a, fg, true, c);
     const uint64_t N = fg.node_len.size();
+    // -H: target (reference) paths stay put
+    std::vector<uint32_t> old_of_new;
+    std::vector<uint8_t> frozen;
+    if (a.has("target-paths")) {
+        std::vector<uint64_t> targets;
+        if (!read_path_list(a.str("target-paths"), fg, true, false, targets)) return 1;
+        uint64_t ref_nodes = 0;
+        old_of_new = reorder_by_target_paths(fg, targets, ref_nodes);
+        frozen.assign(N, 0);
+        std::fill_n(frozen.begin(), ref_nodes, (uint8_t) 1);
+    }
+    // -f: the paths the default parameters are derived from
+    pgsgd_config c;
+    if (a.has("path-sgd-use-paths")) {
+        std::vector<uint64_t> use;
+        if (!read_path_list(a.str("path-sgd-use-paths"), fg, false, true, use)) return 1;
+        const PathStats ps = path_stats(fg, &use);
+        common_config(a, fg, true, c, &ps);
+    } else {
+        common_config(a, fg, true, c);
+    }
+    if (a.has("prepared-out")) {   // what goes to the GPU, for inspection and tests: no device needed
+        pgsgd::ArrayWriter w(a.str("prepared-out"));
+        w.add("node_len", fg.node_len);
+        w.add("path_first_step", fg.path_first_step);
+        w.add("step_node", fg.step_node);
+        w.add("step_rev", fg.step_rev);
+        w.add("step_pos", fg.step_pos);
+        w.add("frozen", frozen);
+        w.add("old_of_new", old_of_new);
+        w.add_scalar<uint64_t>("min_term_updates", c.min_term_updates);
+        w.add_scalar<uint64_t>("space", c.space);
+        w.add_scalar<uint64_t>("space_max", c.space_max);
+        w.add_scalar<uint64_t>("space_quantization_step", c.space_quantization_step);
+        w.add_scalar<double>("eta_max", c.eta_max);
+        w.close();
+        if (!a.has("gpu")) return 0;
+    }
     std::vector<double> X(N);
     pgsgd_stats st;
     const pgsgd_graph_view v = fg.view();
-    if (pgsgd_sort_1d(&v, &c, nullptr, 0, X.data(), &st) != PGSGD_OK) { std::cerr << "[odgi::sort] error: " << pgsgd_last_error() << std::endl; return 1; }
+    if (pgsgd_sort_1d(&v, &c, frozen.empty() ? nullptr : frozen.data(), 0, X.data(), &st) != PGSGD_OK) { std::cerr << "[odgi::sort] error: " << pgsgd_last_error() << std::endl; return 1; }
     if (a.has("progress"))
         std::cerr << "[odgi::path_linear_sgd] 1D path-guided SGD: " << st.term_updates << " term updates in " << st.seconds_iterations << " s on the GPU" << std::endl;
     // path_linear_sgd_order (path_sgd.cpp:638-683): sort by (weak component, pos, handle).  The reference clears its
@@ -331,12 +437,14 @@ int main_sort(int argc, char** argv) {
     std::vector<uint64_t> order(N);
     std::iota(order.begin(), order.end(), 0);
     std::sort(order.begin(), order.end(), [&](uint64_t i, uint64_t j) { return X[i] < X[j] || (X[i] == X[j] && i < j); });
+    // node ids of the INPUT graph, in sorted order (with -H the run worked on the reordered graph)
+    auto input_id = [&](uint64_t r) { return (uint64_t) (old_of_new.empty() ? r : old_of_new[r]) + 1; };
     std::ofstream f(a.str("out"));
-    for (uint64_t r : order) f << r + 1 << '\n';
+    for (uint64_t r : order) f << input_id(r) << '\n';
     if (a.has("layout-out")) {  // -L in odgi sort: the 1D layout (start, start + node length) per sorted node
         std::ofstream l(a.str("layout-out"));
         l << std::setprecision(std::numeric_limits<double>::digits10 + 1) << "node\tstart\tend\n";
-        for (uint64_t r : order) l << r + 1 << "\t" << X[r] << "\t" << X[r] + (double) fg.node_len[r] << '\n';
+        for (uint64_t r : order) l << input_id(r) << "\t" << X[r] << "\t" << X[r] + (double) fg.node_len[r] << '\n';
     }
     if (a.has("path-sgd-layout")) {  // -e in odgi sort: the same as a .lay, X = (start, start + length) per sorted node, Y = 0 (path_sgd.cpp:659-677)
         std::vector<double> sorted_layout(2 * N), dummy(2 * N, 0.0);

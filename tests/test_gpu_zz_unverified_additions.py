@@ -257,3 +257,27 @@ def test_c4_1d_default_run_in_reference_band(graphs):
     x, st = odgi_b200.sort_1d(gd, capi.sort_defaults(gd))
     s = orc.path_stress_1d(go, x, band["n_pairs"], band["seed"])
     assert abs(s - band["mean"]) <= 0.025 * band["mean"] + 2 * band["sd"], (s, band["mean"])
+
+
+def test_cli_sort_keeps_target_paths_fixed(drb1, golden_graphs, tmp_path):
+    """`pgsgd sort -H targets`: the nodes of the target paths keep the positions the reordered graph starts from
+    (path_sgd.cpp:63-69 cumulative bp, frozen by path_sgd.cpp:290-302,387-392); every other node moves."""
+    gfa, go = drb1
+    a = golden_graphs["DRB1-3123"]
+    names = bytes(a["path_names"]).decode().split("\n")[:-1]
+    (tmp_path / "targets.txt").write_text(names[0] + "\n")
+    out, lay, prep = tmp_path / "order.txt", tmp_path / "lay1d.tsv", tmp_path / "prep.arr"
+    subprocess.run([CLI, "sort", "-i", gfa, "-o", str(out), "-Y", "--gpu", "-H", str(tmp_path / "targets.txt"), "--layout-out", str(lay),
+                    "--prepared-out", str(prep)], check=True)
+    p = read_arrays(str(prep))
+    start = np.concatenate([[0], np.cumsum(p["node_len"].astype(np.float64))[:-1]])     # initial X of the reordered graph, by new rank
+    rows = np.loadtxt(str(lay), skiprows=1)
+    new_of_old = np.empty(go.N, dtype=np.int64)
+    new_of_old[p["old_of_new"].astype(np.int64)] = np.arange(go.N)
+    x_new = np.empty(go.N)
+    x_new[new_of_old[rows[:, 0].astype(np.int64) - 1]] = rows[:, 1]
+    fz = p["frozen"].astype(bool)
+    assert fz.sum() > 100 and np.array_equal(x_new[fz], start[fz])
+    assert np.mean(x_new[~fz] != start[~fz]) > 0.95
+    order = np.loadtxt(str(out), dtype=np.int64)
+    assert np.array_equal(np.sort(order), np.arange(1, go.N + 1))

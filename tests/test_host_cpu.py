@@ -241,3 +241,48 @@ def test_bench_line_assembles_with_a_stand_in_engine(monkeypatch, capfd):
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "phases_rank0"}
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["roofline"]["bound"] == "hbm"
     assert abs(line["value"] - 4 * line["config"]["updates_per_step"] / 4e-3 / 1e6) < 1e-6 * line["value"]
+
+
+def test_sort_target_paths_and_use_paths_preparation(golden_graphs, tmp_path):
+    """`pgsgd sort -H targets -f use`: what reaches the GPU (--prepared-out, no device needed) against an independent restatement
+    of sort_graph_by_target_paths (sort_main.cpp:266-311: nodes of the target paths first, in first-visit order; the rest in
+    id order; the first ref_nodes ranks frozen) and of the -f parameter derivation (sort_main.cpp:355-412)."""
+    a = golden_graphs["DRB1-3123"]
+    g = odgi_b200.graph_from_arrays(a)
+    names = bytes(a["path_names"]).decode().split("\n")[:-1]
+    gfa, prep = tmp_path / "g.gfa", tmp_path / "prep.arr"
+    synth.write_gfa(g, str(gfa))
+    targets, use = [names[5], names[2], "not-in-the-graph"], [names[1], names[7], names[3]]
+    (tmp_path / "targets.txt").write_text("\n".join(targets) + "\n")
+    (tmp_path / "use.txt").write_text("\n".join(use) + "\n")
+    r = subprocess.run([CLI, "sort", "-i", str(gfa), "-o", str(tmp_path / "order.txt"), "-Y", "-H", str(tmp_path / "targets.txt"),
+                        "-f", str(tmp_path / "use.txt"), "--prepared-out", str(prep)], capture_output=True, text=True)
+    assert r.returncode == 0 and "found 2/3 paths to consider" in r.stderr, r.stderr
+    p = read_arrays(str(prep))
+    first, node = a["path_first_step"].astype(np.int64), a["step_node"].astype(np.int64)
+    order, seen = [], np.zeros(g.N, dtype=bool)
+    for name in targets[:2]:
+        k = names.index(name)
+        for n in node[first[k]:first[k + 1]]:
+            if not seen[n]:
+                seen[n] = True
+                order.append(n)
+    ref_nodes = len(order)
+    order += [n for n in range(g.N) if not seen[n]]
+    order = np.array(order)
+    new_of_old = np.empty(g.N, dtype=np.int64)
+    new_of_old[order] = np.arange(g.N)
+    assert np.array_equal(p["old_of_new"], order)
+    assert np.array_equal(p["frozen"], (np.arange(g.N) < ref_nodes).astype(np.uint8)) and 0 < ref_nodes < g.N
+    assert np.array_equal(p["node_len"], a["node_len"][order]) and np.array_equal(p["step_node"], new_of_old[node])
+    assert np.array_equal(p["step_pos"], a["step_pos"]) and np.array_equal(p["step_rev"], a["step_rev"])
+    ks = [names.index(n) for n in use]
+    steps = [int(first[k + 1] - first[k]) for k in ks]
+    bps = [int(a["step_pos"][first[k + 1] - 1]) + int(a["node_len"][node[first[k + 1] - 1]]) for k in ks]
+    assert p["min_term_updates"][0] == sum(steps) and p["space"][0] == max(bps) and p["eta_max"][0] == float(max(steps)) ** 2
+    assert p["space_max"][0] == 100 and p["space_quantization_step"][0] == max(2, -(-(max(bps) - 100) // 1))
+    # duplicates in the target list are an error, as in the reference
+    (tmp_path / "dup.txt").write_text(names[0] + "\n" + names[0] + "\n")
+    r = subprocess.run([CLI, "sort", "-i", str(gfa), "-o", str(tmp_path / "o.txt"), "-Y", "-H", str(tmp_path / "dup.txt"), "--prepared-out", str(prep)],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "duplicated path names" in r.stderr
