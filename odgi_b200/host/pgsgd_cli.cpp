@@ -41,7 +41,7 @@ const Flag LAYOUT_FLAGS[] = {
     {"K", "path-sgd-cooling", true}, {"F", "path-sgd-iteration-max-learning-rate", true}, {"k", "path-sgd-zipf-space", true},
     {"I", "path-sgd-zipf-space-max", true}, {"l", "path-sgd-zipf-space-quantization-step", true}, {"t", "threads", true},
     {"", "gpu", false}, {"P", "progress", false}, {"h", "help", false}, {"", "seed", true}, {"", "init-seed", true}, {"", "sampling", true},
-    {"u", "path-sgd-snapshot", true}};
+    {"u", "path-sgd-snapshot", true}, {"f", "path-sgd-use-paths", true}};
 const Flag SORT_FLAGS[] = {
     {"i", "idx", true}, {"o", "out", true}, {"Y", "path-sgd", false}, {"G", "path-sgd-min-term-updates-paths", true},
     {"U", "path-sgd-min-term-updates-nodes", true}, {"j", "path-sgd-delta", true}, {"g", "path-sgd-eps", true},
@@ -229,6 +229,8 @@ bool init_layout(const pgsgd::FlatGraph& fg, char mode, bool seeded, uint64_t se
     return true;
 }
 
+bool read_path_list(const std::string& file, const pgsgd::FlatGraph& fg, bool reject_duplicates, bool unknown_is_error, std::vector<uint64_t>& out);
+
 int main_layout(int argc, char** argv) {
     Args a;
     if (!parse(argc, argv, LAYOUT_FLAGS, a, "layout") || a.has("help") || argc == 2) {
@@ -243,7 +245,14 @@ int main_layout(int argc, char** argv) {
     pgsgd::FlatGraph fg;
     try { fg = pgsgd::read_gfa_flat(a.str("idx")); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
     pgsgd_config c;
-    common_config(a, fg, false, c);
+    if (a.has("path-sgd-use-paths")) {   // layout_main.cpp:230-263: the default parameters come from these paths only
+        std::vector<uint64_t> use;
+        if (!read_path_list(a.str("path-sgd-use-paths"), fg, false, true, use)) return 1;
+        const PathStats ps = path_stats(fg, &use);
+        common_config(a, fg, false, c, &ps);
+    } else {
+        common_config(a, fg, false, c);
+    }
     const uint64_t N = fg.node_len.size();
     std::vector<double> X, Y;
     if (!init_layout(fg, a.str("layout-initialization", "d")[0], a.has("init-seed"), a.u64("init-seed", 0), X, Y)) return 1;
