@@ -101,10 +101,15 @@ typedef struct pgsgd_config {
  * The other two reproduce the reference's racy last-writer-wins write (path_sgd_layout.cpp:360-363, layout.cu:184-187). */
 #define PGSGD_FLAG_EXCH_WRITE   1u  /* 64-bit atom.exch of the new (x,y) — the reference CUDA kernel's atomicExch semantics */
 #define PGSGD_FLAG_PLAIN_STORE  4u  /* st.global of the new (x,y) (slower on B200: 14 vs 21 G updates/s, profiles/) */
-#define PGSGD_FLAG_TMA_STAGING  8u  /* tile kernel: stage tiles with double-buffered TMA bulk copies (cp.async.bulk + mbarrier) instead of
-                                       coalesced LDG/STS into one buffer; measured slower on B200, kept for comparison */
+#define PGSGD_FLAG_TMA_STAGING  8u  /* tile kernels: stage tiles with double-buffered TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP)
+                                       instead of coalesced LDG.128/STS.128 into one buffer (DESIGN.md 3.2 has the measurements) */
 #define PGSGD_FLAG_KEEP_ADD    16u  /* experiments only: keep the red.add write even where the hub safeguard would switch to the
                                        exchange write — used to measure where the summed write really turns unstable */
+#define PGSGD_FLAG_LEGACY_TILE 32u  /* tile sampling with round 1's unpipelined kernel (pgsgd_tile_kernel) instead of the pipelined one
+                                       (pgsgd_tile2_kernel, pgsgd_tile2.cu); NVLink peer phases always use the legacy kernel */
+#define PGSGD_FLAG_HALF_TILE   64u  /* pipelined tile kernel: 1024-step tiles (with TMA_STAGING: two 1024-step buffers = the footprint of
+                                       one 2048-step buffer) */
+#define PGSGD_FLAG_BIG_TILE   128u  /* pipelined tile kernel: 4096-step tiles (experiments: occupancy vs in-tile partner rate) */
 #define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
 
 typedef struct pgsgd_stats {

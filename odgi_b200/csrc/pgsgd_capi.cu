@@ -129,6 +129,9 @@ struct pgsgd_engine {
     uint8_t* d_frozen = nullptr;
     double* d_zetas = nullptr;
     uint64_t zetas_cap = 0;
+    float2* d_ztab[2] = {nullptr, nullptr};  // pipelined tile kernel: fp32 {zeta_n, 1/(1 - zeta_2/zeta_n)} for theta / for the 1D cooling theta
+    uint64_t ztab_cap = 0;
+    uint64_t max_path_bp = 0;                // largest end-adjusted position (pos + len) of any step: < 2^32 selects 32-bit distances
     uint64_t* d_rng = nullptr;
     uint64_t rng_stride = 0;
     uint64_t rng_streams = 0;     // streams seeded by the run in progress
@@ -185,6 +188,27 @@ int ensure_zetas(pgsgd_engine* e, const std::vector<double>& z) {
         e->zetas_cap = z.size();
     }
     CU(cudaMemcpyAsync(e->d_zetas, z.data(), z.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    return PGSGD_OK;
+}
+
+// fp32 companion of the zeta table for the pipelined tile kernel: {zeta_n, 1 / (1 - zeta_2 / zeta_n)} per table entry, so
+// that the per-term eta of the dirty Zipf (dirty_zipfian_int_distribution.h:126-133) costs one multiply instead of two
+// divisions; zeta_2 is recomputed from the theta handed to the draw exactly as the reference does (:126-128)
+int upload_ztab(pgsgd_engine* e, int which, const std::vector<double>& z, double theta_draw) {
+    if (z.size() > e->ztab_cap) {
+        for (int k = 0; k < 2; ++k) { if (e->d_ztab[k]) cudaFree(e->d_ztab[k]); e->d_ztab[k] = nullptr; }
+        for (int k = 0; k < 2; ++k) { int rc = dev_alloc(e, &e->d_ztab[k], z.size()); if (rc) return rc; }
+        e->ztab_cap = z.size();
+    }
+    const float zeta2 = (float) make_zipf_const(theta_draw).zeta2;
+    std::vector<float2> t(z.size());
+    for (size_t i = 0; i < z.size(); ++i) {
+        const float zn = (float) z[i];
+        t[i].x = zn;
+        t[i].y = 1.0f / (1.0f - zeta2 / zn);
+    }
+    CU(cudaMemcpyAsync(e->d_ztab[which], t.data(), t.size() * sizeof(float2), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));   // t is a local
     return PGSGD_OK;
 }
 
@@ -410,12 +434,25 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     int blocks_per_sm = 0;
     uint64_t n_streams = 0;
     LaunchShape shape;
+    // the pipelined tile kernel (pgsgd_tile2.cu) unless the legacy one is asked for or needed (NVLink peer-partitioned
+    // coordinates, paths with >= 2^31 steps)
+    bool tile2 = false;
+    int tile_steps = TILE_STEPS;
     if (tile_mode) {
         const bool tma = (cfg->flags & PGSGD_FLAG_TMA_STAGING) != 0;
-        const size_t tile_bytes = (tma ? 2 : 1) * (size_t) TILE_STEPS * sizeof(StepRec);  // TMA staging is double-buffered
-        smem_paths = tile_bytes + smem_first <= 200 * 1024;
-        smem = tile_bytes + (smem_paths ? smem_first : 0);
-        CU(tile_occupancy(dims, batch, smem, smem_paths, tma, &blocks_per_sm));
+        tile2 = !peer && !(cfg->flags & PGSGD_FLAG_LEGACY_TILE) && e->max_path_steps < (1ull << 31) && e->N < (1ull << 30);
+        if (tile2) {
+            if (cfg->flags & PGSGD_FLAG_HALF_TILE) tile_steps = 1024;
+            else if ((cfg->flags & PGSGD_FLAG_BIG_TILE) && !tma) tile_steps = 4096;
+            batch = 1;
+            smem = tile2_smem_bytes(tile_steps, tma, (uint32_t) e->P, &smem_paths);
+            CU(tile2_occupancy(dims, tile_steps, tma, smem, &blocks_per_sm));
+        } else {
+            const size_t tile_bytes = (tma ? 2 : 1) * (size_t) TILE_STEPS * sizeof(StepRec);  // TMA staging is double-buffered
+            smem_paths = tile_bytes + smem_first <= 200 * 1024;
+            smem = tile_bytes + (smem_paths ? smem_first : 0);
+            CU(tile_occupancy(dims, batch, smem, smem_paths, tma, &blocks_per_sm));
+        }
         if (blocks_per_sm < 1) return fail(PGSGD_ERR_CUDA, "tile kernel does not fit on an SM (smem %zu)", smem);
         uint64_t grid = (uint64_t) e->sm_count * blocks_per_sm;
         if (cfg->n_streams) grid = (cfg->n_streams + block - 1) / block;
@@ -546,6 +583,36 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
             if (p.n_tiles == 0) p.n_tiles = 1;
         }
     }
+    Tile2Params t2;
+    memset(&t2, 0, sizeof(t2));
+    if (tile_mode && tile2) {
+        // same visit arithmetic with this kernel's tile size
+        const uint64_t W = (uint64_t) tile_steps;
+        const uint64_t U_job = sharded ? U_rank : U;
+        const uint64_t q = U_job / e->S, rU = U_job % e->S;
+        const uint64_t extra = (rU + W - 1) / W;
+        t2.n_tiles = (e->S + W - 1) / W;
+        t2.n_visits = q * t2.n_tiles + extra;
+        t2.last_visit_terms = rU ? rU - (extra - 1) * W : W;
+        t2.visit_rank = p.visit_rank;
+        t2.visit_nranks = p.visit_nranks;
+        t2.steps = e->d_steps; t2.xy = e->d_xy; t2.x1d = e->d_x1d; t2.frozen = p.frozen;
+        t2.rng = e->d_rng; t2.rng_stride = e->rng_stride;
+        t2.path_first = e->d_path_first; t2.step_count = e->S; t2.path_count = (uint32_t) e->P;
+        t2.smem_paths = smem_paths ? 1u : 0u;
+        t2.space = (uint32_t) (cfg->space < 0xFFFFFFFFull ? cfg->space : 0xFFFFFFFFull);   // jump spaces never exceed the longest path (< 2^31 steps)
+        t2.space_max = (uint32_t) (cfg->space_max < 0xFFFFFFFFull ? cfg->space_max : 0xFFFFFFFFull);
+        t2.space_q = (uint32_t) (cfg->space_quantization_step < 0xFFFFFFFFull ? cfg->space_quantization_step : 0xFFFFFFFFull);
+        t2.space_q_rcp = (cfg->space < (1ull << 24) && cfg->space_quantization_step >= 16) ? 1.0f / (float) t2.space_q : 0.0f;
+        t2.pos32 = e->max_path_bp < (1ull << 32) ? 1u : 0u;
+        t2.flags = p.flags;
+        t2.delta_max_bits = p.delta_max_bits;
+        t2.counted = p.counted;
+        t2.trace = p.trace; t2.trace_count = p.trace_count; t2.trace_cap = p.trace_cap;
+        rc = upload_ztab(e, 0, zetas, cfg->theta);
+        if (!rc && dims == 1) rc = upload_ztab(e, 1, zetas, 0.001);   // 1D cooling: adj_theta with the zetas of the original theta (path_sgd.cpp:195,246)
+        if (rc) return rc;
+    }
     if (peer) {
         p.n_parts = (uint32_t) e->n_ranks;
         for (int q = 0; q < 9; ++q) p.part_lo[q] = e->part_lo[q];
@@ -569,13 +636,24 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         p.sp.zipf_f = make_zipf_const_f(p.sp.zipf);
         if (tile_mode) {
             // one bijection of the tile index per pass: i -> (i * mul + add) mod n_tiles with gcd(mul, n_tiles) = 1
+            const uint64_t nt = tile2 ? t2.n_tiles : p.n_tiles;
             uint64_t sm = cfg->seed ^ (0x9e3779b97f4a7c15ULL * (iter + 1));
             for (int k = 0; k < 16; ++k) {
                 uint64_t mul;
-                do { mul = splitmix64_next(sm) % p.n_tiles; } while (p.n_tiles > 1 && (mul == 0 || std::gcd(mul, p.n_tiles) != 1));
-                if (p.n_tiles == 1) mul = 1;
-                p.perm_mul[k] = mul;
-                p.perm_add[k] = splitmix64_next(sm) % p.n_tiles;
+                do { mul = splitmix64_next(sm) % nt; } while (nt > 1 && (mul == 0 || std::gcd(mul, nt) != 1));
+                if (nt == 1) mul = 1;
+                p.perm_mul[k] = t2.perm_mul[k] = mul;
+                p.perm_add[k] = t2.perm_add[k] = splitmix64_next(sm) % nt;
+            }
+            if (tile2) {
+                t2.eta = p.eta;
+                t2.eta_f = (float) p.eta;
+                t2.cooling = p.sp.cooling;
+                t2.one_minus_theta = p.sp.zipf_f.one_minus_theta;
+                t2.alpha_frac = p.sp.zipf_f.alpha_frac;
+                t2.alpha_int = p.sp.zipf_f.alpha_int;
+                t2.thresh2 = p.sp.zipf_f.thresh2;
+                t2.ztab = e->d_ztab[(dims == 1 && p.sp.cooling) ? 1 : 0];
             }
         }
         if (track_delta) CU(cudaMemsetAsync(e->d_delta, 0, sizeof(unsigned int), e->stream));
@@ -583,7 +661,8 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
             if (dims == 2) CU(cudaMemcpyAsync(e->d_xy_prev, e->d_xy, 4 * e->N * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
             else CU(cudaMemcpyAsync(e->d_x1d_prev, e->d_x1d, e->N * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
         }
-        if (tile_mode) CU(launch_tile_iteration(dims, batch, p, shape, e->stream));
+        if (tile_mode && tile2) CU(launch_tile2_iteration(dims, tile_steps, (cfg->flags & PGSGD_FLAG_TMA_STAGING) != 0, t2, shape, e->stream));
+        else if (tile_mode) CU(launch_tile_iteration(dims, batch, p, shape, e->stream));
         else CU(launch_iteration(dims, batch, p, shape, e->stream));
         ++st.kernel_launches;
         if (peer) {
@@ -851,6 +930,14 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
         if (err == cudaSuccess) err = cudaMemcpy(&md, d_maxdup, sizeof(md), cudaMemcpyDeviceToHost);
         e->tile_repeats = md;
     }
+    if (err == cudaSuccess) {   // largest end-adjusted bp position (the 32-bit distance path of the pipelined tile kernel needs < 2^32)
+        err = cudaMemsetAsync(d_maxdup, 0, sizeof(unsigned long long), e->stream);
+        if (err == cudaSuccess) err = launch_max_path_bp(e->d_steps, e->d_path_first, (uint32_t) e->P, d_maxdup, e->stream);
+        unsigned long long mb = 0;
+        if (err == cudaSuccess) err = cudaMemcpyAsync(&mb, d_maxdup, sizeof(mb), cudaMemcpyDeviceToHost, e->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        e->max_path_bp = mb;
+    }
     cudaFree(d_maxdup);
     cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
     if (err != cudaSuccess) return cu_bail(err, "flatten-to-device");
@@ -868,6 +955,7 @@ void pgsgd_engine_destroy(pgsgd_engine* e) {
     if (e->comm) ncclCommDestroy(e->comm);
     cudaFree(e->d_steps); cudaFree(e->d_path_first); cudaFree(e->d_xy); cudaFree(e->d_xy_prev); cudaFree(e->d_x1d);
     cudaFree(e->d_trace); cudaFree(e->d_trace_count);
+    cudaFree(e->d_ztab[0]); cudaFree(e->d_ztab[1]);
     cudaFree(e->d_x1d_prev); cudaFree(e->d_frozen); cudaFree(e->d_zetas); cudaFree(e->d_rng); cudaFree(e->d_delta); cudaFree(e->d_counted);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);

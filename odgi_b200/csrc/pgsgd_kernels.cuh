@@ -44,6 +44,38 @@ struct IterParams {
     uint64_t trace_cap;
 };
 
+// Parameters of one launch of the pipelined tile kernel (pgsgd_tile2.cu): everything the host can fold is folded.
+struct Tile2Params {
+    const StepRec* steps;
+    float* xy;                  // 2D: [4N]
+    double* x1d;                // 1D: [N]
+    const uint8_t* frozen;      // 1D: [N] or nullptr
+    uint64_t* rng;
+    uint64_t rng_stride;
+    const uint64_t* path_first; // [P+1]
+    uint64_t step_count;
+    const float2* ztab;         // [zeta table size] {zeta_n, 1 / (1 - zeta_2 / zeta_n)} in fp32 for this iteration's theta
+    uint32_t path_count;
+    uint32_t smem_paths;        // 1: path_first staged in shared memory
+    uint32_t space, space_max, space_q;
+    float space_q_rcp;          // 1 / space_q when the reciprocal quotient is exact after one correction step, else 0 (integer division)
+    uint32_t cooling;
+    uint32_t pos32;             // every end-adjusted bp position fits 32 bits
+    float one_minus_theta, alpha_frac, thresh2;
+    int alpha_int;
+    double eta;
+    float eta_f;
+    uint32_t flags;
+    unsigned int* delta_max_bits;
+    unsigned long long* counted;
+    uint64_t n_visits, n_tiles, last_visit_terms;
+    uint64_t perm_mul[16], perm_add[16];
+    uint32_t visit_rank, visit_nranks;
+    unsigned long long* trace;
+    unsigned long long* trace_count;
+    uint64_t trace_cap;
+};
+
 constexpr int STRESS_STREAMS = 4096;   // generators of the sampled path stress (== ORC_STRESS_STREAMS of the oracle)
 #ifndef PGSGD_TILE_STEPS
 #define PGSGD_TILE_STEPS 2048      // experiments: PGSGD_TILE_STEPS=4096 python -m odgi_b200.build (1024, 2048 or 4096)
@@ -67,6 +99,14 @@ cudaError_t launch_tile_iteration(int dims, int batch, const IterParams& p, cons
 cudaError_t tile_occupancy(int dims, int batch, size_t smem, bool smem_paths, bool tma, int* blocks_per_sm);
 // occupancy query for the kernel variant (resident blocks per SM for the given block size / smem)
 cudaError_t iteration_occupancy(int dims, int batch, int block, size_t smem, bool smem_paths, int* blocks_per_sm);
+
+// the pipelined tile kernel (pgsgd_tile2.cu): tile_steps 1024 | 2048 | 4096, tma = double-buffered TMA bulk staging
+struct Tile2Params;
+size_t tile2_smem_bytes(int tile_steps, bool tma, uint32_t path_count, bool* smem_paths);
+cudaError_t launch_tile2_iteration(int dims, int tile_steps, bool tma, const Tile2Params& p, const LaunchShape& shape, cudaStream_t stream);
+cudaError_t tile2_occupancy(int dims, int tile_steps, bool tma, size_t smem, int* blocks_per_sm);
+// largest end-adjusted bp position over all paths (pos + len of every path's last step), for the 32-bit position path
+cudaError_t launch_max_path_bp(const StepRec* steps, const uint64_t* first, uint32_t P, unsigned long long* out, cudaStream_t stream);
 
 // packs SoA step arrays into StepRec records on the device
 cudaError_t launch_pack_steps(StepRec* out, const uint32_t* step_node, const uint8_t* step_rev, const uint64_t* step_pos,

@@ -102,6 +102,10 @@ def lib():
         L.orc_path_stress_2d.restype = C.c_double
         L.orc_path_stress_1d.argtypes = [C.POINTER(_Graph), C.c_void_p, C.c_uint64, C.c_uint64]
         L.orc_path_stress_1d.restype = C.c_double
+        L.orc_local_stress_2d.argtypes = [C.POINTER(_Graph), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
+        L.orc_local_stress_2d.restype = C.c_double
+        L.orc_local_stress_1d.argtypes = [C.POINTER(_Graph), C.c_void_p, C.c_uint64, C.c_uint64]
+        L.orc_local_stress_1d.restype = C.c_double
         assert C.sizeof(_Config) == 96
     return _lib
 
@@ -400,6 +404,20 @@ def path_stress_1d(g: Graph, X, n_pairs: int = 1_000_000, seed: int = 12345) -> 
     X = np.ascontiguousarray(X, dtype=np.float64)
     gc = g.c()
     return float(lib().orc_path_stress_1d(C.byref(gc), _ptr(X), n_pairs, seed))
+
+
+def local_stress_2d(g: Graph, X, Y, n_pairs: int = 1_000_000, seed: int = 12345) -> float:
+    """near-pair stress: partner 1..64 ranks away along the path, d <= 1000 bp (orc_local_stress_2d)"""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    gc = g.c()
+    return float(lib().orc_local_stress_2d(C.byref(gc), _ptr(X), _ptr(Y), n_pairs, seed))
+
+
+def local_stress_1d(g: Graph, X, n_pairs: int = 1_000_000, seed: int = 12345) -> float:
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    gc = g.c()
+    return float(lib().orc_local_stress_1d(C.byref(gc), _ptr(X), n_pairs, seed))
 
 
 def xy_to_XY(xy: np.ndarray):

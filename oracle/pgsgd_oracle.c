@@ -711,3 +711,77 @@ double orc_path_stress_1d(const orc_graph* g, const double* X, uint64_t n_pairs,
     }
     return used ? acc / (double) used : 0.0;
 }
+
+/* Local path stress: the same estimator restricted to NEAR pairs — partner = the step `j` ranks away along the
+ * path, j uniform in [1, ORC_LOCAL_WINDOW], random direction, pairs further apart than ORC_LOCAL_MAX_BP skipped.  The
+ * far-pair stress above is dominated by pairs megabases apart and is blind to the fine structure of the layout (where
+ * limited coordinate precision would show first); this one measures exactly that.  Same stream structure. */
+#define ORC_LOCAL_WINDOW 64
+#define ORC_LOCAL_MAX_BP 1000
+
+double orc_local_stress_2d(const orc_graph* g, const double* X, const double* Y, uint64_t n_pairs, uint64_t seed) {
+    const uint64_t per = (n_pairs + ORC_STRESS_STREAMS - 1) / ORC_STRESS_STREAMS;
+    double acc = 0;
+    uint64_t used = 0;
+    for (uint64_t t = 0; t < ORC_STRESS_STREAMS; ++t) {
+        orc_rng rng;
+        orc_rng_seed(&rng, seed + t);
+        double a = 0;
+        for (uint64_t k = 0; k < per; ++k) {
+            uint64_t ia = orc_uniform(&rng, g->step_count);
+            uint64_t p = find_path(g, ia);
+            uint64_t first = g->path_first_step[p], cnt = g->path_first_step[p + 1] - first;
+            uint64_t j = 1 + orc_uniform(&rng, ORC_LOCAL_WINDOW);
+            uint64_t back = orc_uniform(&rng, 2);
+            uint64_t fa = orc_uniform(&rng, 2), fb = orc_uniform(&rng, 2);
+            uint64_t ra = ia - first;
+            if (back ? ra < j : ra + j >= cnt) continue;
+            uint64_t ib = back ? ia - j : ia + j;
+            uint32_t na = g->step_node[ia], nb = g->step_node[ib];
+            uint64_t pa = g->step_pos[ia] + (fa ? g->node_len[na] : 0);
+            uint64_t pb = g->step_pos[ib] + (fb ? g->node_len[nb] : 0);
+            uint64_t ea = fa ? !g->step_rev[ia] : g->step_rev[ia];
+            uint64_t eb = fb ? !g->step_rev[ib] : g->step_rev[ib];
+            if (pa == pb) continue;
+            double d = fabs((double) pa - (double) pb);
+            if (d > (double) ORC_LOCAL_MAX_BP) continue;
+            double dx = X[2 * (uint64_t) na + ea] - X[2 * (uint64_t) nb + eb];
+            double dy = Y[2 * (uint64_t) na + ea] - Y[2 * (uint64_t) nb + eb];
+            double e = (sqrt(dx * dx + dy * dy) - d) / d;
+            a += e * e;
+            ++used;
+        }
+        acc += a;
+    }
+    return used ? acc / (double) used : 0.0;
+}
+
+double orc_local_stress_1d(const orc_graph* g, const double* X, uint64_t n_pairs, uint64_t seed) {
+    const uint64_t per = (n_pairs + ORC_STRESS_STREAMS - 1) / ORC_STRESS_STREAMS;
+    double acc = 0;
+    uint64_t used = 0;
+    for (uint64_t t = 0; t < ORC_STRESS_STREAMS; ++t) {
+        orc_rng rng;
+        orc_rng_seed(&rng, seed + t);
+        double a = 0;
+        for (uint64_t k = 0; k < per; ++k) {
+            uint64_t ia = orc_uniform(&rng, g->step_count);
+            uint64_t p = find_path(g, ia);
+            uint64_t first = g->path_first_step[p], cnt = g->path_first_step[p + 1] - first;
+            uint64_t j = 1 + orc_uniform(&rng, ORC_LOCAL_WINDOW);
+            uint64_t back = orc_uniform(&rng, 2);
+            uint64_t ra = ia - first;
+            if (back ? ra < j : ra + j >= cnt) continue;
+            uint64_t ib = back ? ia - j : ia + j;
+            uint64_t pa = g->step_pos[ia], pb = g->step_pos[ib];
+            if (pa == pb) continue;
+            double d = fabs((double) pa - (double) pb);
+            if (d > (double) ORC_LOCAL_MAX_BP) continue;
+            double e = (fabs(X[g->step_node[ia]] - X[g->step_node[ib]]) - d) / d;
+            a += e * e;
+            ++used;
+        }
+        acc += a;
+    }
+    return used ? acc / (double) used : 0.0;
+}

@@ -137,6 +137,9 @@ uint64_t orc_replay_single_frozen(const orc_graph* g, const orc_config* c, int d
  * stress = mean(((|p_a - p_b| - d)/d)^2).  2D coords: X/Y indexed 2*node+end; 1D: X by node. */
 double orc_path_stress_2d(const orc_graph* g, const double* X, const double* Y, uint64_t n_pairs, uint64_t seed);
 double orc_path_stress_1d(const orc_graph* g, const double* X, uint64_t n_pairs, uint64_t seed);
+/* Local variant: partner 1..64 ranks away along the path, pairs further apart than 1000 bp skipped (fine structure). */
+double orc_local_stress_2d(const orc_graph* g, const double* X, const double* Y, uint64_t n_pairs, uint64_t seed);
+double orc_local_stress_1d(const orc_graph* g, const double* X, uint64_t n_pairs, uint64_t seed);
 
 #ifdef __cplusplus
 }

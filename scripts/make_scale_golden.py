@@ -1,0 +1,138 @@
+#!/usr/bin/env python
+"""Reference stress bands AT SCALE: full default runs of the UNMODIFIED reference CPU implementation
+(oracle/_ref/ref_driver_fast = the reference's own -Ofast Release flags) on synthetic graphs large enough that the
+device's AUTO sampling picks the TILE kernel (S >= 2^22), one of them long and thin so that its layout coordinates
+exceed 2^24 bp (where fp32 coordinates stop resolving single base pairs):
+
+  mid       odgi_b200.synth preset: 500 000 sites x 90 paths (S ~ 4.6e7, N ~ 6e5; 2D coordinates ~7e6 bp)
+  longthin  3 000 000 sites x 6 paths (S ~ 1.8e7, N ~ 3.6e6; path length ~4e7 bp > 2^24)
+
+Stage 1 (`run`): write GFA + injected initialisation (seed 42), run the reference R times per graph and dimension,
+keep every result's coordinates under SCRATCH (not committed: tens of MB each).
+Stage 2 (`bands`): evaluate the oracle's far-pair stress AND local stress of every stored result and write
+tests/golden/stress_reference_scale.json {mean, sd, values} per graph / dimension / metric.
+
+Authoring container only (needs /root/reference via oracle/_ref).  Usage:
+  python scripts/make_scale_golden.py run  [graph ...] [--runs R] [--threads T] [--dims 2,1]
+  python scripts/make_scale_golden.py bands
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from odgi_b200 import synth  # noqa: E402
+from odgi_b200.arrays import read_arrays, write_arrays  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_driver_fast")
+SCRATCH = os.environ.get("PGSGD_SCALE_SCRATCH", os.path.join(ROOT, ".scratch", "scale_golden"))
+GOLD = os.path.join(ROOT, "tests", "golden")
+GRAPHS = {"mid": (500_000, 90), "longthin": (3_000_000, 6)}
+N_PAIRS, SEED = 4_000_000, 12345
+
+
+def graph_of(name):
+    n_sites, n_paths = GRAPHS[name]
+    return synth.generate(n_sites, n_paths, seed=42)
+
+
+def stage_run(names, runs, threads, dims):
+    from oracle import oracle as orc
+    os.makedirs(SCRATCH, exist_ok=True)
+    for name in names:
+        g = graph_of(name)
+        gfa = os.path.join(SCRATCH, f"{name}.gfa")
+        if not os.path.exists(gfa):
+            synth.write_gfa(g, gfa)
+        go = orc.Graph(g.node_len, g.path_first_step, g.step_node, g.step_rev)
+        init = os.path.join(SCRATCH, f"{name}.init.arr")
+        if not os.path.exists(init):
+            X0, Y0 = orc.layout_init(go, seed=42)
+            write_arrays(init, {"X": X0, "Y": Y0})
+        for d in dims:
+            for r in range(runs):
+                out = os.path.join(SCRATCH, f"{name}.{'layout2d' if d == 2 else 'sort1d'}.run{r}.arr")
+                if os.path.exists(out):
+                    continue
+                t0 = time.time()
+                cmd = [REF, "layout", gfa, init, out + ".tmp", f"threads={threads}"] if d == 2 else [REF, "sort", gfa, out + ".tmp", f"threads={threads}"]
+                p = subprocess.run(cmd, cwd=SCRATCH, capture_output=True, text=True)
+                if p.returncode != 0:
+                    print("FAILED", cmd, p.stderr[-2000:], flush=True)
+                    continue
+                os.replace(out + ".tmp", out)
+                info = p.stdout.strip().splitlines()[-1]
+                print(f"{name} dims={d} run{r}: {time.time() - t0:.0f} s  {info}", flush=True)
+
+
+def stage_bands():
+    from oracle import oracle as orc
+    path = os.path.join(GOLD, "stress_reference_scale.json")
+    out = {}
+    if os.path.exists(path):
+        with open(path) as f:
+            out = json.load(f)
+    for name in GRAPHS:
+        g = None
+        for kind in ("layout2d", "sort1d"):
+            files = sorted(f for f in os.listdir(SCRATCH) if f.startswith(f"{name}.{kind}.run") and f.endswith(".arr"))
+            if not files:
+                continue
+            if g is None:
+                gg = graph_of(name)
+                g = orc.Graph(gg.node_len, gg.path_first_step, gg.step_node, gg.step_rev)
+            far, loc = [], []
+            for fn in files:
+                r = read_arrays(os.path.join(SCRATCH, fn))
+                if kind == "layout2d":
+                    far.append(orc.path_stress_2d(g, r["X"], r["Y"], N_PAIRS, SEED))
+                    loc.append(orc.local_stress_2d(g, r["X"], r["Y"], N_PAIRS, SEED))
+                else:
+                    far.append(orc.path_stress_1d(g, r["X"], N_PAIRS, SEED))
+                    loc.append(orc.local_stress_1d(g, r["X"], N_PAIRS, SEED))
+            ent = {"runs": len(files), "n_pairs": N_PAIRS, "seed": SEED, "init_seed": 42, "generator": list(GRAPHS[name]),
+                   "nodes": int(g.N), "steps": int(g.S),
+                   "far": {"mean": float(np.mean(far)), "sd": float(np.std(far, ddof=1)) if len(far) > 1 else 0.0, "values": far},
+                   "local": {"mean": float(np.mean(loc)), "sd": float(np.std(loc, ddof=1)) if len(loc) > 1 else 0.0, "values": loc}}
+            if kind == "layout2d":
+                init = read_arrays(os.path.join(SCRATCH, f"{name}.init.arr"))
+                ent["initial_far"] = orc.path_stress_2d(g, init["X"], init["Y"], N_PAIRS, SEED)
+                ent["initial_local"] = orc.local_stress_2d(g, init["X"], init["Y"], N_PAIRS, SEED)
+                ent["coord_max"] = float(max(np.max(np.abs(r["X"])), np.max(np.abs(r["Y"]))))
+            else:
+                x0 = orc.sort_init(g)
+                ent["initial_far"] = orc.path_stress_1d(g, x0, N_PAIRS, SEED)
+                ent["initial_local"] = orc.local_stress_1d(g, x0, N_PAIRS, SEED)
+            out[f"{name}.{kind}"] = ent
+            print(name, kind, json.dumps(ent)[:400], flush=True)
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+
+
+def main():
+    a = sys.argv[1:]
+    if not a or a[0] not in ("run", "bands"):
+        raise SystemExit(__doc__)
+    if a[0] == "bands":
+        return stage_bands()
+    runs, threads, dims, names = 5, 6, [2, 1], []
+    i = 1
+    while i < len(a):
+        if a[i] == "--runs":
+            runs = int(a[i + 1]); i += 2
+        elif a[i] == "--threads":
+            threads = int(a[i + 1]); i += 2
+        elif a[i] == "--dims":
+            dims = [int(x) for x in a[i + 1].split(",")]; i += 2
+        else:
+            names.append(a[i]); i += 1
+    stage_run(names or list(GRAPHS), runs, threads, dims)
+
+
+if __name__ == "__main__":
+    main()
