@@ -23,7 +23,7 @@ extern "C" {
 
 /* Bumped whenever a struct below changes size or meaning.  Callers compare PGSGD_VERSION (what they were compiled against)
  * with pgsgd_version() (what they loaded) before the first call: a stale binary would otherwise pass short structs. */
-#define PGSGD_VERSION 101 /* 0.1.1 */
+#define PGSGD_VERSION 102 /* 0.1.2 */
 
 typedef enum pgsgd_status {
     PGSGD_OK = 0,
@@ -220,11 +220,20 @@ int pgsgd_engine_sample_terms(pgsgd_engine* e, const pgsgd_config* cfg, int dims
  * reference has no layout-quality readout on this path; this is the one the parity tests use. */
 int pgsgd_engine_path_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64_t seed, double* stress_out);
 
+/* The near-pair variant of the same estimator: partner 1..64 ranks away along the path, pairs further apart than 1000 bp
+ * skipped (oracle: orc_local_stress_2d / _1d).  The far-pair stress is dominated by pairs megabases apart; this one reads
+ * the fine structure of the layout, where limited coordinate precision would show first. */
+int pgsgd_engine_local_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64_t seed, double* stress_out);
+
 /* The node order `odgi sort -Y` derives from the 1D layout (path_linear_sgd_order, src/algorithms/path_sgd.cpp:638-683):
- * node ranks sorted by position, ties by handle, computed on the device (stable radix sort).  order_out: [N] node ranks.
- * (The reference also keys on the weak component, but clears that map before reading it, path_sgd.cpp:588 — the key is
- * constant there and here.) */
-int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out);
+ * node ranks sorted by (weak component, position, handle), computed on the device (stable radix sorts).  order_out: [N]
+ * node ranks.  node_component: [N] the component key of every node rank — components numbered by their average node id as
+ * path_sgd.cpp:557-573 does — or NULL for a single-component graph.  (The reference clear()s its component map before
+ * reading it, path_sgd.cpp:588; the storage stays in place and the unchecked reads still see the ids, so the running
+ * reference does sort by component: tests/golden/order_multi3.json.)  The weak components themselves come from the caller:
+ * the view (pgsgd_graph_view) carries no edges; odgi has algorithms::weakly_connected_components for this. */
+int pgsgd_engine_order_1d_components(pgsgd_engine* e, const uint32_t* node_component, uint64_t* order_out);
+int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out);   /* == node_component NULL */
 
 /* Tile-sampling verification: with a trace buffer set, every term the tile kernel draws is recorded (first step,
  * partner step as global step indices, flips = flip_a | flip_b << 1) until the buffer is full. */

@@ -61,10 +61,10 @@ EXPORTED_SYMBOLS = [
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
     "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
-    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_set_shard", "pgsgd_engine_path_stress", "pgsgd_engine_order_1d", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
+    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_set_shard", "pgsgd_engine_path_stress", "pgsgd_engine_local_stress", "pgsgd_engine_order_1d", "pgsgd_engine_order_1d_components", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
 ]
 
-ABI_VERSION = 101  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
+ABI_VERSION = 102  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
 _lib = None
 
 
@@ -126,6 +126,8 @@ def lib():
         L.pgsgd_engine_set_shard.argtypes = [vp, u64]
         L.pgsgd_engine_path_stress.argtypes = [vp, i32, u64, u64, vp]
         L.pgsgd_engine_order_1d.argtypes = [vp, vp]
+        L.pgsgd_engine_order_1d_components.argtypes = [vp, vp, vp]
+        L.pgsgd_engine_local_stress.argtypes = [vp, i32, u64, u64, vp]
         L.pgsgd_engine_sample_terms.argtypes = [vp, C.POINTER(ConfigC), i32, i32, dbl, u64, u64] + [vp] * 11
         L.pgsgd_engine_set_trace.argtypes = [vp, u64]
         L.pgsgd_engine_get_trace.argtypes = [vp, vp, vp, vp, vp]
@@ -367,9 +369,11 @@ class Engine:
         _check(lib().pgsgd_engine_path_stress(self._h, dims, n_pairs, seed, C.byref(out)))
         return float(out.value)
 
-    def order_1d(self) -> np.ndarray:
+    def order_1d(self, component: Optional[np.ndarray] = None) -> np.ndarray:
+        """node ranks sorted by ([component key,] position, handle) on the device (path_sgd.cpp:650-658)"""
         order = np.empty(self.g.N, dtype=np.uint64)
-        _check(lib().pgsgd_engine_order_1d(self._h, _ptr(order)))
+        comp = None if component is None else np.ascontiguousarray(component, dtype=np.uint32)
+        _check(lib().pgsgd_engine_order_1d_components(self._h, _ptr(comp), _ptr(order)))
         return order
 
     def set_multi_mode(self, mode: int):

@@ -230,8 +230,12 @@ std::vector<double> build_zetas(const pgsgd_config& c) {
     for (uint64_t i = 1; i < c.space + 1; i++) {
         zeta_tmp += host_fast_precise_pow(1.0 / i, c.theta);
         if (i <= c.space_max) zetas[i] = zeta_tmp;
+        // The reference writes zetas[space_max + 1] when i == space == space_max, one element past its vector
+        // (path_sgd_layout.cpp:92-95 with a table of space + 1 entries); that entry is never read (jump spaces above
+        // space_max do not exist then), so it is simply not stored here.
         if (i >= c.space_max && (i - c.space_max) % c.space_quantization_step == 0) {
-            zetas[c.space_max + 1 + (i - c.space_max) / c.space_quantization_step] = zeta_tmp;
+            const uint64_t slot = c.space_max + 1 + (i - c.space_max) / c.space_quantization_step;
+            if (slot < zetas.size()) zetas[slot] = zeta_tmp;
         }
     }
     return zetas;
@@ -1130,7 +1134,7 @@ int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int 
     return PGSGD_OK;
 }
 
-int pgsgd_engine_path_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64_t seed, double* stress_out) {
+static int stress_impl(pgsgd_engine* e, int dims, int local, uint64_t n_pairs, uint64_t seed, double* stress_out) {
     if (!e || !stress_out) return fail(PGSGD_ERR_ARG, "path_stress: NULL argument");
     if (dims != 1 && dims != 2) return fail(PGSGD_ERR_ARG, "dims must be 1 or 2");
     if (dims == 2 ? !e->have_2d : !e->have_1d) return fail(PGSGD_ERR_STATE, "no coordinates on the device");
@@ -1141,7 +1145,7 @@ int pgsgd_engine_path_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64
     CU(cudaMalloc(&d_acc, STRESS_STREAMS * sizeof(double)));
     if (cudaMalloc(&d_used, STRESS_STREAMS * sizeof(unsigned long long)) != cudaSuccess) { cudaFree(d_acc); return fail(PGSGD_ERR_NOMEM, "cudaMalloc failed"); }
     const uint64_t per = (n_pairs + STRESS_STREAMS - 1) / STRESS_STREAMS;
-    cudaError_t err = launch_stress(dims, e->d_path_first, (uint32_t) e->P, e->S, e->d_steps, e->d_xy, e->d_x1d, per, seed, d_acc, d_used, e->stream);
+    cudaError_t err = launch_stress(dims, local, e->d_path_first, (uint32_t) e->P, e->S, e->d_steps, e->d_xy, e->d_x1d, per, seed, d_acc, d_used, e->stream);
     std::vector<double> acc(STRESS_STREAMS);
     std::vector<unsigned long long> used(STRESS_STREAMS);
     if (err == cudaSuccess) err = cudaMemcpyAsync(acc.data(), d_acc, STRESS_STREAMS * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
@@ -1156,19 +1160,34 @@ int pgsgd_engine_path_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64
     return PGSGD_OK;
 }
 
-int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out) {
+int pgsgd_engine_path_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64_t seed, double* stress_out) {
+    return stress_impl(e, dims, 0, n_pairs, seed, stress_out);
+}
+int pgsgd_engine_local_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint64_t seed, double* stress_out) {
+    return stress_impl(e, dims, 1, n_pairs, seed, stress_out);
+}
+
+int pgsgd_engine_order_1d_components(pgsgd_engine* e, const uint32_t* node_component, uint64_t* order_out) {
     if (!e || !order_out) return fail(PGSGD_ERR_ARG, "order_1d: NULL argument");
     if (!e->have_1d) return fail(PGSGD_ERR_STATE, "no 1D coordinates on the device");
     CU(cudaSetDevice(e->device));
     if (e->coords_in_slices) { int rc = peer_gather(e, 1); if (rc) return rc; }
     uint64_t* d_order = nullptr;
+    uint32_t* d_comp = nullptr;
     CU(cudaMalloc(&d_order, e->N * sizeof(uint64_t)));
-    cudaError_t err = launch_order_1d(e->d_x1d, d_order, e->N, e->stream);
+    cudaError_t err = cudaSuccess;
+    if (node_component) {
+        err = cudaMalloc(&d_comp, e->N * sizeof(uint32_t));
+        if (err == cudaSuccess) err = cudaMemcpy(d_comp, node_component, e->N * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    }
+    if (err == cudaSuccess) err = launch_order_1d(e->d_x1d, d_comp, d_order, e->N, e->stream);
     if (err == cudaSuccess) err = cudaMemcpy(order_out, d_order, e->N * sizeof(uint64_t), cudaMemcpyDeviceToHost);
-    cudaFree(d_order);
+    cudaFree(d_order); cudaFree(d_comp);
     if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "order_1d: %s", cudaGetErrorString(err));
     return PGSGD_OK;
 }
+
+int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out) { return pgsgd_engine_order_1d_components(e, nullptr, order_out); }
 
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode) {
     if (!e) return fail(PGSGD_ERR_ARG, "set_multi_mode: NULL engine");

@@ -640,7 +640,7 @@ __global__ void sample_terms_kernel(SamplerParams sp, const StepRec* steps, uint
 // STRESS_STREAMS generators (stream t seeded seed + t) draw `per` pairs each — step uniform over all steps, partner
 // uniform in the same path, ends uniform (2D) — and accumulate ((|p_a - p_b| - d) / d)^2 in fp64 with IEEE operations, so
 // the per-stream sums are bit-identical to the oracle's; the host adds them in stream order.
-template <int DIMS>
+template <int DIMS, bool LOCAL>
 __global__ void stress_kernel(const uint64_t* first, uint32_t P, uint64_t S, const StepRec* steps, const float* xy, const double* x1d,
                               uint64_t per, uint64_t seed, double* acc_out, unsigned long long* used_out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -653,16 +653,29 @@ __global__ void stress_kernel(const uint64_t* first, uint32_t P, uint64_t S, con
         const uint64_t ia = draw_uniform(g, S);
         const uint32_t p = find_path(first, P, ia);
         const uint64_t f = first[p], cnt = first[p + 1] - f;
-        const uint64_t ib = f + draw_uniform(g, cnt);
+        uint64_t ib;
+        bool skip = false;
+        if (LOCAL) {   // orc_local_stress_*: partner 1..64 ranks away along the path, pairs beyond 1000 bp skipped
+            const uint64_t j = 1 + draw_uniform(g, 64);
+            const uint32_t back = draw_flip(g);
+            const uint64_t ra = ia - f;
+            skip = back ? ra < j : ra + j >= cnt;
+            ib = skip ? ia : (back ? ia - j : ia + j);
+        } else {
+            ib = f + draw_uniform(g, cnt);
+        }
+        uint32_t fa = 0, fb = 0;
+        if (DIMS == 2) { fa = draw_flip(g); fb = draw_flip(g); }   // drawn before any skip, as the oracle does
+        if (skip) continue;
         const uint4 ra = load_step(steps, ia), rb = load_step(steps, ib);
         uint64_t pa = step_pos(ra), pb = step_pos(rb);
         if (DIMS == 2) {
-            const uint32_t fa = draw_flip(g), fb = draw_flip(g);
             uint32_t ea = ra.x & 1u, eb = rb.x & 1u;
             if (fa) { pa += ra.y; ea ^= 1u; }
             if (fb) { pb += rb.y; eb ^= 1u; }
             if (pa == pb) continue;
             const double d = fabs(__dsub_rn(__ull2double_rn(pa), __ull2double_rn(pb)));
+            if (LOCAL && d > 1000.0) continue;
             const float2 ca = __ldcg(reinterpret_cast<const float2*>(xy) + ((uint64_t) (ra.x >> 1) * 2 + ea));
             const float2 cb = __ldcg(reinterpret_cast<const float2*>(xy) + ((uint64_t) (rb.x >> 1) * 2 + eb));
             const double dx = __dsub_rn((double) ca.x, (double) cb.x), dy = __dsub_rn((double) ca.y, (double) cb.y);
@@ -671,6 +684,7 @@ __global__ void stress_kernel(const uint64_t* first, uint32_t P, uint64_t S, con
         } else {
             if (pa == pb) continue;
             const double d = fabs(__dsub_rn(__ull2double_rn(pa), __ull2double_rn(pb)));
+            if (LOCAL && d > 1000.0) continue;
             const double xa = __ldcg(x1d + (ra.x >> 1)), xb = __ldcg(x1d + (rb.x >> 1));
             const double e = __ddiv_rn(__dsub_rn(fabs(__dsub_rn(xa, xb)), d), d);
             acc = __dadd_rn(acc, __dmul_rn(e, e));
@@ -840,22 +854,46 @@ __global__ void iota_kernel(uint64_t* v, uint64_t n) {
     if (i < n) v[i] = i;
 }
 
-// 1D node order (path_linear_sgd_order's sort, path_sgd.cpp:650-658, with its constant component key): node ranks sorted
-// by position, ties by handle — a STABLE radix sort of (x, rank) pairs that start in rank order gives exactly that.
-cudaError_t launch_order_1d(const double* x, uint64_t* order_out, uint64_t n, cudaStream_t stream) {
+__global__ void gather_u32_kernel(uint32_t* out, const uint32_t* table, const uint64_t* idx, uint64_t n) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = table[idx[i]];
+}
+
+// 1D node order (path_linear_sgd_order's sort, path_sgd.cpp:650-658): node ranks sorted by (weak component, position,
+// handle).  A STABLE radix sort of (x, rank) pairs that start in rank order gives (position, handle); a second stable sort
+// of the result by the component key (when the caller supplies one; device pointer, [n]) makes the component the major key.
+cudaError_t launch_order_1d(const double* x, const uint32_t* d_component, uint64_t* order_out, uint64_t n, cudaStream_t stream) {
     if (!n) return cudaSuccess;
     double* keys_out = nullptr;
     uint64_t* vals_in = nullptr;
+    uint64_t* vals_mid = nullptr;
+    uint32_t *ck_in = nullptr, *ck_out = nullptr;
     void* tmp = nullptr;
-    size_t tmp_bytes = 0;
+    size_t tmp_bytes = 0, tmp2 = 0;
+    uint64_t* first_out = d_component ? nullptr : order_out;
     cudaError_t e = cudaMalloc(&keys_out, n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&vals_in, n * sizeof(uint64_t));
+    if (e == cudaSuccess && d_component) {
+        e = cudaMalloc(&vals_mid, n * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaMalloc(&ck_in, n * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&ck_out, n * sizeof(uint32_t));
+        first_out = vals_mid;
+    }
     if (e == cudaSuccess) { iota_kernel<<<grid_for(n, 256), 256, 0, stream>>>(vals_in, n); e = cudaGetLastError(); }
-    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, x, keys_out, vals_in, order_out, n, 0, 64, stream);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, x, keys_out, vals_in, first_out, n, 0, 64, stream);
+    if (e == cudaSuccess && d_component) {
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmp2, ck_in, ck_out, vals_mid, order_out, n, 0, 32, stream);
+        if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+    }
     if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
-    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, x, keys_out, vals_in, order_out, n, 0, 64, stream);
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, x, keys_out, vals_in, first_out, n, 0, 64, stream);
+    if (e == cudaSuccess && d_component) {
+        gather_u32_kernel<<<grid_for(n, 256), 256, 0, stream>>>(ck_in, d_component, vals_mid, n);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, ck_in, ck_out, vals_mid, order_out, n, 0, 32, stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    cudaFree(tmp); cudaFree(vals_in); cudaFree(keys_out);
+    cudaFree(tmp); cudaFree(vals_in); cudaFree(keys_out); cudaFree(vals_mid); cudaFree(ck_in); cudaFree(ck_out);
     return e;
 }
 
@@ -907,10 +945,13 @@ cudaError_t launch_add_f64(double* out, const double* a, const double* b, uint64
     return cudaGetLastError();
 }
 
-cudaError_t launch_stress(int dims, const uint64_t* first, uint32_t P, uint64_t S, const StepRec* steps, const float* xy,
+cudaError_t launch_stress(int dims, int local, const uint64_t* first, uint32_t P, uint64_t S, const StepRec* steps, const float* xy,
                           const double* x1d, uint64_t per, uint64_t seed, double* acc_out, unsigned long long* used_out, cudaStream_t stream) {
-    if (dims == 2) stress_kernel<2><<<STRESS_STREAMS / 128, 128, 0, stream>>>(first, P, S, steps, xy, x1d, per, seed, acc_out, used_out);
-    else if (dims == 1) stress_kernel<1><<<STRESS_STREAMS / 128, 128, 0, stream>>>(first, P, S, steps, xy, x1d, per, seed, acc_out, used_out);
+    const dim3 grid(STRESS_STREAMS / 128), block(128);
+    if (dims == 2 && !local) stress_kernel<2, false><<<grid, block, 0, stream>>>(first, P, S, steps, xy, x1d, per, seed, acc_out, used_out);
+    else if (dims == 2) stress_kernel<2, true><<<grid, block, 0, stream>>>(first, P, S, steps, xy, x1d, per, seed, acc_out, used_out);
+    else if (dims == 1 && !local) stress_kernel<1, false><<<grid, block, 0, stream>>>(first, P, S, steps, xy, x1d, per, seed, acc_out, used_out);
+    else if (dims == 1) stress_kernel<1, true><<<grid, block, 0, stream>>>(first, P, S, steps, xy, x1d, per, seed, acc_out, used_out);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

@@ -121,8 +121,8 @@ cudaError_t launch_flatten_on_device(StepRec* out, const uint32_t* step_node, co
 // repeated node visits inside tiles of TILE_STEPS consecutive steps, summed over all tiles (n must start on a tile boundary)
 cudaError_t launch_tile_repeats(const uint32_t* step_node, uint64_t n, unsigned long long* total_dups, cudaStream_t stream);
 
-// 1D node order on the device: node ranks sorted by (x, rank), stable radix sort
-cudaError_t launch_order_1d(const double* x, uint64_t* order_out, uint64_t n, cudaStream_t stream);
+// 1D node order on the device: node ranks sorted by ([component key,] x, rank), stable radix sorts; d_component may be null
+cudaError_t launch_order_1d(const double* x, const uint32_t* d_component, uint64_t* order_out, uint64_t n, cudaStream_t stream);
 
 // coordinate format conversion: reference X/Y (double, index 2*node+end) <-> device float4-per-node
 cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n_nodes, cudaStream_t stream);
@@ -136,8 +136,8 @@ cudaError_t launch_add_f32(float* out, const float* a, const float* b, uint64_t 
 cudaError_t launch_sub_f64(double* out, const double* a, const double* b, uint64_t n, cudaStream_t stream);
 cudaError_t launch_add_f64(double* out, const double* a, const double* b, uint64_t n, cudaStream_t stream);
 
-// sampled path stress: per-stream partial sums (STRESS_STREAMS entries each), `per` pairs per stream
-cudaError_t launch_stress(int dims, const uint64_t* first, uint32_t P, uint64_t S, const StepRec* steps, const float* xy,
+// sampled path stress (local = 1: the near-pair variant, orc_local_stress_*): per-stream partial sums (STRESS_STREAMS entries each), `per` pairs per stream
+cudaError_t launch_stress(int dims, int local, const uint64_t* first, uint32_t P, uint64_t S, const StepRec* steps, const float* xy,
                           const double* x1d, uint64_t per, uint64_t seed, double* acc_out, unsigned long long* used_out, cudaStream_t stream);
 
 // verification hook: first n_terms draws of one stream, produced by the same device sampler

@@ -144,15 +144,18 @@ void common_config(const Args& a, const pgsgd::FlatGraph& fg, bool is_sort, pgsg
     else if (a.has("path-sgd-min-term-updates-nodes")) c.min_term_updates = (uint64_t) (a.num("path-sgd-min-term-updates-nodes", 0) * (double) N);
     else c.min_term_updates = (uint64_t) ((is_sort ? 1.0 : 10.0) * (double) S);
     c.eta_max = a.has("path-sgd-eta-max") ? a.num("path-sgd-eta-max", 0) : (double) all.max_steps * (double) all.max_steps;
-    if (is_sort) {  // sort_main.cpp:387-412
+    if (is_sort) {  // sort_main.cpp:387-412: -k / -I are taken as given (no clamp), q = 100 unless space > space_max
         const uint64_t max_len = all.max_bp;
-        c.space = a.has("path-sgd-zipf-space") ? std::min(a.u64("path-sgd-zipf-space", 0), max_len) : max_len;
-        c.space_max = a.has("path-sgd-zipf-space-max") ? std::min(c.space, a.u64("path-sgd-zipf-space-max", 0)) : 100;
-        if (a.has("path-sgd-zipf-space-quantization-step")) {
+        c.space = a.has("path-sgd-zipf-space") && a.u64("path-sgd-zipf-space", 0) ? a.u64("path-sgd-zipf-space", 0) : max_len;
+        c.space_max = a.has("path-sgd-zipf-space-max") && a.u64("path-sgd-zipf-space-max", 0) ? a.u64("path-sgd-zipf-space-max", 0) : 100;
+        if (a.has("path-sgd-zipf-space-quantization-step") && a.u64("path-sgd-zipf-space-quantization-step", 0)) {
             c.space_quantization_step = std::max<uint64_t>(2, a.u64("path-sgd-zipf-space-quantization-step", 0));
         } else {
-            const uint64_t max_dists = std::max<uint64_t>(c.space_max + 1, 100);
-            c.space_quantization_step = std::max<uint64_t>(2, (uint64_t) std::ceil((double) (c.space - c.space_max) / (double) (max_dists - c.space_max)));
+            const uint64_t max_dists = std::max<uint64_t>(c.space_max + 1, 100);   // MAX_NUMBER_OF_ZIPF_DISTRIBUTIONS
+            if (c.space > c.space_max && max_dists > c.space_max)
+                c.space_quantization_step = std::max<uint64_t>(2, (uint64_t) std::ceil((double) (c.space - c.space_max) / (double) (max_dists - c.space_max)));
+            else
+                c.space_quantization_step = 100;
         }
     } else {  // layout_main.cpp:261-266
         c.space = a.has("path-sgd-zipf-space") ? std::min(a.u64("path-sgd-zipf-space", 0), all.max_steps) : all.max_steps;
@@ -441,11 +444,35 @@ int main_sort(int argc, char** argv) {
     if (pgsgd_sort_1d(&v, &c, frozen.empty() ? nullptr : frozen.data(), 0, X.data(), &st) != PGSGD_OK) { std::cerr << "[odgi::sort] error: " << pgsgd_last_error() << std::endl; return 1; }
     if (a.has("progress"))
         std::cerr << "[odgi::path_linear_sgd] 1D path-guided SGD: " << st.term_updates << " term updates in " << st.seconds_iterations << " s on the GPU" << std::endl;
-    // path_linear_sgd_order (path_sgd.cpp:638-683): sort by (weak component, pos, handle).  The reference clears its
-    // component map before reading it (path_sgd.cpp:588), so the component key is constant there; mirrored here.
+    // path_linear_sgd_order (path_sgd.cpp:638-683): sort by (weak component, pos, handle), components numbered by their
+    // average node id (:557-573).  The reference clear()s its component map before reading it (:588), but clear() leaves
+    // the storage in place and the unchecked operator[] reads still return the ids: the running binary does order by
+    // component (checked against the reference on a graph with interleaved components, tests/golden/order_multi3.json).
+    std::vector<uint32_t> comp_key(N, 0);
+    {
+        std::vector<uint32_t> comp = components_of(fg, a.str("idx"));   // ranks of THIS run's graph (reordered with -H)
+        if (!old_of_new.empty()) {   // components_of numbers by the input ids the L lines carry
+            std::vector<uint32_t> by_new(N);
+            for (uint64_t r = 0; r < N; ++r) by_new[r] = comp[old_of_new[r]];
+            comp.swap(by_new);
+        }
+        const uint32_t n_comp = comp.empty() ? 0 : *std::max_element(comp.begin(), comp.end()) + 1;
+        std::vector<double> id_sum(n_comp, 0.0);
+        std::vector<uint64_t> cnt(n_comp, 0);
+        for (uint64_t r = 0; r < N; ++r) { id_sum[comp[r]] += (double) (r + 1); ++cnt[comp[r]]; }
+        std::vector<std::pair<double, uint32_t>> by_avg;
+        for (uint32_t k = 0; k < n_comp; ++k) by_avg.emplace_back(id_sum[k] / (double) cnt[k], k);
+        std::sort(by_avg.begin(), by_avg.end());
+        std::vector<uint32_t> key_of(n_comp);
+        for (uint32_t i = 0; i < n_comp; ++i) key_of[by_avg[i].second] = i;
+        for (uint64_t r = 0; r < N; ++r) comp_key[r] = key_of[comp[r]];
+    }
     std::vector<uint64_t> order(N);
     std::iota(order.begin(), order.end(), 0);
-    std::sort(order.begin(), order.end(), [&](uint64_t i, uint64_t j) { return X[i] < X[j] || (X[i] == X[j] && i < j); });
+    std::sort(order.begin(), order.end(), [&](uint64_t i, uint64_t j) {
+        if (comp_key[i] != comp_key[j]) return comp_key[i] < comp_key[j];
+        return X[i] < X[j] || (X[i] == X[j] && i < j);
+    });
     // node ids of the INPUT graph, in sorted order (with -H the run worked on the reordered graph)
     auto input_id = [&](uint64_t r) { return (uint64_t) (old_of_new.empty() ? r : old_of_new[r]) + 1; };
     std::ofstream f(a.str("out"));

@@ -436,11 +436,41 @@ def XY_to_xy(X, Y, dtype=np.float32) -> np.ndarray:
     return a.reshape(-1)
 
 
+def component_keys(n_nodes: int, path_first_step, step_node, edges=()) -> np.ndarray:
+    """The weak-component key path_linear_sgd_order sorts by (path_sgd.cpp:552-586): weakly connected components of the
+    graph (consecutive path steps are edges; `edges` adds node-rank pairs the paths do not cover, i.e. the remaining L
+    lines), numbered by ascending average node id.  Returns the key of every node rank."""
+    parent = np.arange(n_nodes, dtype=np.int64)
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    first = np.asarray(path_first_step, dtype=np.int64)
+    sn = np.asarray(step_node, dtype=np.int64)
+    pairs = [(int(a), int(b)) for a, b in edges]
+    for p in range(len(first) - 1):
+        seg = sn[first[p]:first[p + 1]]
+        pairs.extend(zip(seg[:-1].tolist(), seg[1:].tolist()))
+    for a, b in pairs:
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[max(ra, rb)] = min(ra, rb)
+    root = np.array([find(i) for i in range(n_nodes)])
+    roots = np.unique(root)
+    avg = sorted((float(np.mean(np.nonzero(root == r)[0] + 1)), int(r)) for r in roots)   # node id = rank + 1
+    key_of = {r: k for k, (_, r) in enumerate(avg)}
+    return np.array([key_of[int(r)] for r in root], dtype=np.uint32)
+
+
 def order_from_x(x: np.ndarray, component: Optional[np.ndarray] = None) -> np.ndarray:
     """path_linear_sgd_order's sort (path_sgd.cpp:650-658): by (weak component, pos, handle integer).
-    NB the reference clears weak_components_map before reading it (path_sgd.cpp:588), so on a
-    single-component graph — and in practice on every graph — the component key is constant; pass
-    component=None to mirror that.  Returns node ranks in sorted order."""
+    The reference clear()s weak_components_map before reading it (path_sgd.cpp:588), but clear() leaves the storage in
+    place and the unchecked reads still return the component ids: the running reference DOES sort by component
+    (tests/golden/order_multi3.json, made by scripts/make_order_golden.py).  component = component_keys(...) or None
+    for a single-component graph.  Returns node ranks in sorted order."""
     n = len(x)
     comp = np.zeros(n, dtype=np.uint64) if component is None else np.asarray(component, dtype=np.uint64)
     handle = np.arange(n, dtype=np.uint64) << np.uint64(1)

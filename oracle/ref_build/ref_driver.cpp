@@ -284,10 +284,21 @@ static int cmd_sort(int argc, char** argv) {
     std::vector<uint64_t> order;
     auto t0 = std::chrono::steady_clock::now();
     if (want_order) {
+        // The order is derived from an X the function does not return; the iteration boundaries depend on a 1 ms poll, so a
+        // second run would not reproduce it even single-threaded.  The reference's own 1D .lay output (path_sgd.cpp:660-678:
+        // sorted position i holds the start coordinate of the i-th node of the order) gives the X of THIS run.
+        const std::string lay_path = std::string(argv[3]) + ".lay";
         std::vector<handle_t> o = algorithms::path_linear_sgd_order(L.graph, L.xp, L.paths, iter_max, iter_lr, U, delta, eps, eta_max, theta,
                                                                     space, space_max, space_q, cooling, threads, false, "", false, "",
-                                                                    false, "", target_sorting, target_nodes);
+                                                                    true, lay_path, target_sorting, target_nodes);
         for (auto& h : o) order.push_back(as_integer(h));
+        algorithms::layout::Layout lay;
+        std::ifstream lf(lay_path, std::ios::binary);
+        lay.load(lf);
+        const std::vector<double> sx = lay.get_X();
+        x.assign(N, 0.0);
+        for (uint64_t i = 0; i < o.size(); ++i) x[as_integer(o[i]) >> 1] = sx[2 * i];
+        unlink(lay_path.c_str());
     } else {
         x = algorithms::path_linear_sgd(L.graph, L.xp, L.paths, iter_max, iter_lr, U, delta, eps, eta_max, theta, space, space_max,
                                         space_q, cooling, threads, false, false, snapshots, target_sorting, target_nodes);

@@ -44,7 +44,10 @@ def test_schedule_matches_oracle(kw):
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("space,space_max,q,theta", [(3100, 1000, 100, 0.99), (337324, 100, 337224, 0.99), (50, 1000, 100, 0.99), (5000, 10, 7, 0.5)])
+# (1000, 1000, ...) and (100, 100, 2, ...): space == space_max, where the reference's loop stores one element past its table
+# (path_sgd_layout.cpp:92-95) — here the store is dropped; a longest path of exactly 1000 steps reaches it
+@pytest.mark.parametrize("space,space_max,q,theta", [(3100, 1000, 100, 0.99), (337324, 100, 337224, 0.99), (50, 1000, 100, 0.99), (5000, 10, 7, 0.5),
+                                                     (1000, 1000, 100, 0.99), (100, 100, 2, 0.99), (7, 7, 100, 0.5)])
 def test_zetas_match_oracle(space, space_max, q, theta):
     kw = dict(space=space, space_max=space_max, space_quantization_step=q, theta=theta)
     a = capi.zetas(capi.Config(**kw))
