@@ -109,10 +109,49 @@ def make_workload(name: str):
     return g, desc
 
 
-def cpu_baseline(workload: str, threads: int, iters: int = 2, warmup_iters: int = 0):
+def usable_cores():
+    """host threads this process may actually use: the scheduler affinity mask, capped by the cgroup CPU quota.
+    (os.cpu_count() is the machine's count: on a shared box it oversubscribes the reference's spinning workers.)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:       # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()
+            if q != "max":
+                quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                q, per = int(f.read()), int(g.read())
+                if q > 0:
+                    quota = q / per
+        except (OSError, ValueError):
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota)))
+    return n
+
+
+def cpu_threads():
+    """(threads to use, usable cores, 1-minute load average): cores other tenants of the box keep busy are left to them —
+    the reference's workers spin on per-node locks (src/odgi.cpp:65-71) and collapse when oversubscribed."""
+    usable = usable_cores()
+    try:
+        load1 = os.getloadavg()[0]
+    except OSError:
+        load1 = 0.0
+    free = usable - int(load1 + 0.5)
+    return max(min(usable, 4), min(usable, free)), usable, load1
+
+
+def cpu_baseline(workload: str, threads: int, iters: int = 2, warmup_iters: int = 0, single_thread_iters: int = 0):
     """Reference CPU implementation on the host cores, on a bounded sample of the workload.
     kind 'reference' = the unmodified reference compiled into oracle/_ref (std::thread workers, -Ofast);
-    falls back to kind 'port' (the oracle's C restatement, one core) when oracle/_ref was not built."""
+    falls back to kind 'port' (the oracle's C restatement, one core) when oracle/_ref was not built.
+    single_thread_iters > 0 adds a T = 1 run (T in {1, usable})."""
     from odgi_b200 import synth
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver_fast")
     if not os.path.exists(ref):
@@ -131,15 +170,24 @@ def cpu_baseline(workload: str, threads: int, iters: int = 2, warmup_iters: int 
             gfa = os.path.join(tmp, "sample.gfa")
             synth.write_gfa(g, gfa)
             out = os.path.join(tmp, "o.arr")
+
+            def run(t, n_iter, limit):
+                r = subprocess.run([ref, "layout", gfa, "-", out, f"threads={t}", f"iter_max={n_iter}"], cwd=tmp, capture_output=True,
+                                   text=True, timeout=limit)
+                return json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else None
+
             if warmup_iters:  # untimed: page cache, CPU clocks
-                subprocess.run([ref, "layout", gfa, "-", out, f"threads={threads}", f"iter_max={warmup_iters}"], cwd=tmp, capture_output=True,
-                               text=True, timeout=600)
-            r = subprocess.run([ref, "layout", gfa, "-", out, f"threads={threads}", f"iter_max={iters}"], cwd=tmp, capture_output=True,
-                               text=True, timeout=1200)
-            if r.returncode == 0:
-                info = json.loads(r.stdout.strip().splitlines()[-1])
-                return {"value": info["updates_per_sec"] / 1e6, "unit": "M updates/s", "cores": threads, "kind": "reference",
-                        "sample": sample + f"; {os.path.basename(ref)} (reference sources, -Ofast)", "seconds": info["seconds"]}
+                run(threads, max(2, warmup_iters), 600)
+            info = run(threads, iters, 1200)
+            if info is not None:
+                res = {"value": info["updates_per_sec"] / 1e6, "unit": "M updates/s", "cores": threads, "kind": "reference",
+                       "sample": sample + f"; {os.path.basename(ref)} (reference sources, -Ofast)", "seconds": info["seconds"]}
+                if single_thread_iters:
+                    one = run(1, max(2, single_thread_iters), 1200)
+                    if one is not None:
+                        res["single_thread"] = {"value": one["updates_per_sec"] / 1e6, "cores": 1, "iterations": max(2, single_thread_iters),
+                                                "seconds": one["seconds"]}
+                return res
     from oracle import oracle as orc
     go = orc.Graph(g.node_len, g.path_first_step, g.step_node, g.step_rev)
     cfg = orc.default_layout_config(go, iter_max=iters)
@@ -150,24 +198,65 @@ def cpu_baseline(workload: str, threads: int, iters: int = 2, warmup_iters: int 
     return {"value": n / dt / 1e6, "unit": "M updates/s", "cores": 1, "kind": "port", "sample": sample + "; oracle C restatement", "seconds": dt}
 
 
+def reference_cuda_kernel(workload: str = "mid", iter_max: int = 30):
+    """The reference's OWN CUDA kernel (src/cuda/layout.cu compiled unmodified for sm_100a: oracle/_ref/ref_gpu_driver),
+    measured live on this GPU.  north_star names it as the reported baseline the >= 10x target is judged against.  Default
+    graph 'mid' (same generator, 6e5 nodes / 4.6e7 steps): the driver needs the graph as GFA through odgi's own ingest,
+    seconds there, minutes at c4 (recorded c4 measurement: profiles/r01_reference_cuda_kernel_c4.json)."""
+    from odgi_b200 import synth
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_driver")
+    if not os.path.exists(drv):
+        return {"unavailable": "oracle/_ref/ref_gpu_driver was not built"}
+    g = synth.preset(workload, seed=42)
+    threads = max(4, cpu_threads()[0])
+    with tempfile.TemporaryDirectory() as tmp:
+        gfa = os.path.join(tmp, "g.gfa")
+        t0 = time.time()
+        synth.write_gfa(g, gfa)
+        t_gfa = time.time() - t0
+        r = subprocess.run([drv, gfa, "-", str(iter_max), str(threads)], cwd=tmp, capture_output=True, text=True, timeout=1500)
+        if r.returncode != 0:
+            return {"unavailable": f"ref_gpu_driver rc={r.returncode}: {r.stderr[-300:]}"}
+        info = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    return {"value": info["updates_per_sec"] / 1e6, "unit": "M updates/s", "n_gpus": 1, "workload": workload, "nodes": info["nodes"],
+            "steps": info["steps"], "iter_max": iter_max, "loop_s": info["loop_s"], "gfa_write_s": t_gfa, "gfa_load_s": info["gfa_load_s"],
+            "how": "cuda::gpu_layout called with iter_max and 2*iter_max, loop time by difference (the reference has no hook around its loop)"}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path on the box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads, usable, load1 = cpu_threads()
     # each step = one iteration (10*S updates) over a bounded sample of the workload (same generator, same haplotype count,
     # fewer sites): W untimed iterations, then K timed ones; the reference times its own SGD loop (graph load excluded)
     t0 = time.time()
     iters = max(2, args.steps)   # the reference's schedule divides by iter_max - 1
-    cb = cpu_baseline(args.workload, threads, iters=iters, warmup_iters=max(0, min(args.warmup, 3)))
+    cb = cpu_baseline(args.workload, threads, iters=iters, warmup_iters=max(0, min(args.warmup, 3)), single_thread_iters=2)
+    cbl = {"value": cb["value"], "unit": cb["unit"], "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
+           "usable_cores": usable, "machine_cores": os.cpu_count(), "loadavg_1m_before": load1}
+    if "single_thread" in cb:
+        cbl["single_thread"] = cb["single_thread"]
     line = {"impl": "reference", "metric": "M node-pair SGD updates/sec", "value": cb["value"], "unit": "M updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds"] / iters * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "sample": cb["sample"]},
-            "cpu_baseline": {"value": cb["value"], "unit": cb["unit"], "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
+            "cpu_baseline": cbl,
             "e2e": {"value": cb["value"], "unit": "M updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_cuda_arm(args):
+    """--impl reference-cuda: the reference's own CUDA kernel on this GPU (rank 0 only; it is a single-GPU program)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    wl = args.workload if args.workload != "c4" or args.force_c4 else "mid"
+    rk = reference_cuda_kernel(wl)
+    line = {"impl": "reference-cuda", "metric": "M node-pair SGD updates/sec", "unit": "M updates/s", "n_gpus": 1, "higher_is_better": True,
+            "dtype": "f32 storage, f64 arithmetic", "data": "synthetic", "config": {"workload": wl}}
+    line.update(rk)
     print(json.dumps(line), flush=True)
 
 
@@ -181,21 +270,26 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c4")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
+    ap.add_argument("--force-c4", action="store_true", help="--impl reference-cuda on c4 itself (writes a 9 GB GFA, ~6 minutes)")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip the live reference-CUDA-kernel leg of the default line")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--flags", type=int, default=0)
-    ap.add_argument("--multi", default="hybrid", choices=["hybrid", "peer", "allreduce", "sharded"],
-                    help="N>1: 'peer' = coordinates partitioned over the GPUs, updated through NVLink peer memory (one shared Hogwild); "
-                         "'allreduce' = replicated + 1 all-reduce/step (fastest, costs layout quality); 'hybrid' = allreduce for the first "
-                         "third of the schedule, peer afterwards (single-GPU layout quality); 'sharded' = allreduce with the step records dealt out "
-                         "over the ranks by path (capacity mode for graphs whose records do not fit one GPU; quality readout covers rank 0's paths)")
+    ap.add_argument("--multi", default="auto", choices=["auto", "hybrid", "peer", "allreduce", "sharded"],
+                    help="N>1: 'auto' (default) = allreduce where every replica still sees >= 60 updates per node and iteration (graphs many "
+                         "haplotypes deep, c4), else hybrid; 'allreduce' = replicated coordinates + 1 NCCL all-reduce/step (north_star's design); "
+                         "'peer' = coordinates partitioned over the GPUs, updated through NVLink peer memory (one shared Hogwild); 'hybrid' = allreduce "
+                         "for the first third of the schedule, peer afterwards; 'sharded' = allreduce with the step records dealt out over the ranks by "
+                         "path (capacity mode for graphs whose records do not fit one GPU; quality readout covers rank 0's paths)")
     ap.add_argument("--sampling", type=int, default=0, help="0 auto, 1 stream (reference-exact worker streams), 2 tile")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.impl == "reference-cuda":
+        return run_reference_cuda_arm(args)
 
     import odgi_b200
     from odgi_b200 import capi
@@ -223,7 +317,8 @@ def main():
     sharded = world > 1 and args.multi == "sharded"
     if sharded:
         g = odgi_b200.shard_paths(g, world, rank)   # this rank's paths only; node table whole
-    multi_mode = {"peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE, "sharded": capi.MULTI_ALLREDUCE}[args.multi]
+    multi_mode = {"auto": capi.MULTI_AUTO, "peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE,
+                  "sharded": capi.MULTI_ALLREDUCE}[args.multi]
     sampling_name = {1: "stream", 2: "tile"}.get(args.sampling, "tile" if g.S >= (1 << 22) else "stream")
     X0, Y0 = odgi_b200.layout_init(g, seed=42)
     U = cfg.min_term_updates
@@ -266,7 +361,8 @@ def main():
     wall = time.time() - t0
     barrier()
     clocks = sampler.stop()
-    dev_s = max_over_ranks(st["seconds_iterations"])
+    dev_s = max_over_ranks(st["seconds_iterations"])   # CUDA events around the whole call (both phases of a hybrid run + the switch)
+    wall_s = max_over_ranks(wall)
     assert st["iterations_run"] == K and st["kernel_launches"] == K
     # counted term updates of the whole job (every rank reports its own share)
     total_updates = st["term_updates"]
@@ -275,7 +371,13 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         total_updates = float(tt.item())
     assert abs(total_updates - K * U) <= 1e-3 * K * U, (total_updates, K * U)
-    value = total_updates / dev_s / 1e6
+    # 1 GPU: device time of the K launches (CUDA events on the kernels' stream).  N GPUs: the slowest rank's HOST wall clock
+    # between the barriers — collectives, phase switches and host-side waits included.
+    timed_s = dev_s if world == 1 else wall_s
+    value = total_updates / timed_s / 1e6
+    resolved = {capi.MULTI_ALLREDUCE: "allreduce", capi.MULTI_PEER: "peer", capi.MULTI_HYBRID: "hybrid"}.get(e.resolved_multi_mode(), "?") if world > 1 else None
+    if sharded:
+        resolved = "sharded"
     # layout quality of the COMPLETE schedule: finish the remaining iterations (untimed) and evaluate the sampled path
     # stress on the device (collective in multi-GPU runs)
     quality = None
@@ -339,17 +441,21 @@ def main():
         return
 
     peak, peak_src = load_peaks()
-    step_s = dev_s / K
+    step_s = timed_s / K
     achieved = (total_updates / K / world) * BYTES_PER_UPDATE_2D / step_s / 1e9   # per-GPU kernel: its share of the step's updates
+    # dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed ncu --set full capture of the
+    # 1-GPU launch (profiles/traffic_per_launch.json); a rank of an N-GPU run launches a different share, so null there
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         with open(tp) as f:
             traffic = json.load(f).get(args.workload)
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cb = cpu_baseline(args.workload, os.cpu_count() or 1, iters=10)   # ~10-30 s of host CPU work
+            threads, usable, load1 = cpu_threads()
+            cb = cpu_baseline(args.workload, threads, iters=10, single_thread_iters=2)   # ~10-30 s of host CPU work
+            cb["usable_cores"], cb["machine_cores"], cb["loadavg_1m_before"] = usable, os.cpu_count(), load1
         except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
             cb = {"value": None, "unit": "M updates/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
     line = {
@@ -361,35 +467,56 @@ def main():
                    "l2_policy": "inputs larger than L2" if g.S * 16 > 126e6 else "L2-resident graph (plumbing config)",
                    "parallelism": ("1 GPU" if world == 1 else
                                    f"coords partitioned over {world} GPUs, updated through NVLink peer memory (one shared Hogwild), tiles owned by node range"
-                                   if args.multi == "peer" else
+                                   if resolved == "peer" else
                                    f"hybrid over {world} GPUs: iterations < {iter_max // 3} replicated + 1 NCCL all-reduce/step, then coords partitioned and updated through NVLink peer memory"
-                                   if args.multi == "hybrid" else
+                                   if resolved == "hybrid" else
                                    f"step records dealt out over {world} GPUs by path (rank 0 holds {g.P} paths, {g.S} steps), replicated coords, 1 NCCL all-reduce/step"
                                    if sharded else f"replicated coords, term updates split over {world} GPU(s), 1 NCCL all-reduce/step"),
+                   "multi_mode": resolved, "multi_requested": args.multi if world > 1 else None,
+                   "timed": "CUDA events on the kernels' stream" if world == 1 else "host wall clock between barriers, max over ranks",
                    "device_bytes": dev_bytes, "coords_finite": finite},
         "gpu_launches": K * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_update": BYTES_PER_UPDATE_2D,
-                     "kernel": "pgsgd_tile_kernel<2,BATCH,smem_paths>" if sampling_name == "tile" else "pgsgd_iter_kernel<2,BATCH,smem_paths>",
+                     "kernel": ("pgsgd_tile_kernel<2,BATCH,...> (legacy)" if args.flags & 32 else "pgsgd_tile2_kernel<2,TMA,TILE>") if sampling_name == "tile"
+                     else "pgsgd_iter_kernel<2,BATCH,smem_paths>",
                      "kernel_ms": step_s * 1e3},
-        "clocks": clocks, "wall_s_timed_region": wall,
+        "clocks": clocks, "wall_s_timed_region": wall_s, "device_event_s_timed_region": dev_s,
     }
-    # the reference's own CUDA kernel (src/cuda/layout.cu recompiled for sm_100a), measured on this pool on the same graph:
-    # reported context, not a target (oracle/_ref/ref_gpu_driver; the driver needs the graph as GFA + odgi's ingest, minutes at c4)
-    rp = os.path.join(ROOT, "profiles", f"r01_reference_cuda_kernel_{args.workload}.json")
-    try:  # context only: never a reason to lose the bench line
-        with open(rp) as f:
-            rk = json.loads([ln for ln in f.read().splitlines() if ln.startswith("{")][-1])   # the driver's banner lines precede the JSON
-        line["reference_cuda_kernel"] = {"value": rk["updates_per_sec"] / 1e6, "unit": "M updates/s", "n_gpus": 1,
-                                         "source": os.path.relpath(rp, ROOT), "note": "recorded measurement, not re-run by bench.py"}
-    except (OSError, ValueError, KeyError, IndexError):
-        pass
+    # The reference's own CUDA kernel (src/cuda/layout.cu compiled unmodified for sm_100a): the reported baseline north_star's
+    # ">= 10x" is judged against.  Measured LIVE on this GPU on the 'mid' graph of the same generator, next to our kernel on
+    # the same graph; the c4 number is a recorded measurement (its GFA ingest through odgi takes minutes).
+    if world == 1 and not args.no_reference_cuda:
+        try:  # context only: never a reason to lose the bench line
+            rk = reference_cuda_kernel("mid")
+            if "value" in rk:
+                gm, _ = make_workload("mid")
+                cm = capi.layout_defaults(gm, iter_max=30, flags=args.flags, sampling=args.sampling)
+                Xm, Ym = odgi_b200.layout_init(gm, seed=42)
+                with odgi_b200.Engine(gm, device=local_rank) as em:
+                    em.set_coords_2d(Xm, Ym)
+                    em.run_range(cm, 2, 0, 3)
+                    sm = em.run_range(cm, 2, 3, 30)
+                ours = sm["term_updates"] / sm["seconds_iterations"] / 1e6
+                rk["ours_same_graph"] = {"value": ours, "unit": "M updates/s", "iterations": [3, 30]}
+                rk["ratio_ours_over_reference_kernel"] = ours / rk["value"]
+            rp = os.path.join(ROOT, "profiles", "r01_reference_cuda_kernel_c4.json")
+            if args.workload == "c4" and os.path.exists(rp):
+                with open(rp) as f:
+                    rec = json.loads([ln for ln in f.read().splitlines() if ln.startswith("{")][-1])
+                rk["recorded_c4"] = {"value": rec["updates_per_sec"] / 1e6, "unit": "M updates/s", "source": os.path.relpath(rp, ROOT),
+                                     "ratio_ours_over_reference_kernel": value / (rec["updates_per_sec"] / 1e6),
+                                     "note": "recorded in round 1 on this pool (same binary, same graph); not re-run: 9 GB GFA + 73 s ingest"}
+            line["reference_cuda_kernel"] = rk
+        except Exception as ex:
+            line["reference_cuda_kernel"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
     if quality:
         line["quality"] = quality
     if e2e:
         line["e2e"] = e2e
     if cb:
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "single_thread", "usable_cores", "machine_cores",
+                                                   "loadavg_1m_before") if k in cb}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

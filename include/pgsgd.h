@@ -145,7 +145,7 @@ int pgsgd_sort_1d(const pgsgd_graph_view* g, const pgsgd_config* cfg, const uint
 
 /* The same on n_gpus devices of ONE process (one host thread per GPU inside the call; multi_mode = PGSGD_MULTI_*): how a
  * single-process host such as odgi uses a whole box.  pgsgd_layout_2d / pgsgd_sort_1d dispatch here when the environment
- * variable PGSGD_GPUS is > 1 (PGSGD_MULTI = hybrid | allreduce | peer, default hybrid), so `PGSGD_GPUS=8 odgi layout --gpu`
+ * variable PGSGD_GPUS is > 1 (PGSGD_MULTI = auto | hybrid | allreduce | peer, default auto), so `PGSGD_GPUS=8 odgi layout --gpu`
  * needs no source change. */
 int pgsgd_layout_2d_multi(const pgsgd_graph_view* g, const pgsgd_config* cfg, int n_gpus, int multi_mode, double* X, double* Y,
                           pgsgd_stats* stats);
@@ -195,7 +195,14 @@ int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int 
 #define PGSGD_MULTI_ALLREDUCE 0
 #define PGSGD_MULTI_PEER      1
 #define PGSGD_MULTI_HYBRID    2
+/*  AUTO     : ALLREDUCE when every replica still sees at least PGSGD_AUTO_MIN_UPDATES_PER_NODE updates per node and
+ *             iteration (10 * steps / nodes / ranks in 2D, steps / nodes / ranks in 1D: graphs many haplotypes deep, where the
+ *             mean of the replicas anneals like one Hogwild), else HYBRID.  Resolved when the coordinates are uploaded. */
+#define PGSGD_MULTI_AUTO      3
+#define PGSGD_AUTO_MIN_UPDATES_PER_NODE 60.0
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode);
+/* the mode in effect (what AUTO resolved to; meaningful once coordinates are uploaded) */
+int pgsgd_engine_resolved_multi_mode(const pgsgd_engine* e);
 
 /* Path-sharded step records (graphs whose step records do not fit one GPU): a term always pairs two steps of
  * the SAME path, so the paths of a job can be dealt out over the ranks and every rank's engine is created from a view that

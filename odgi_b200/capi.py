@@ -21,7 +21,7 @@ PGSGD_FLAG_PLAIN_STORE = 4
 PGSGD_FLAG_TMA_STAGING = 8
 PGSGD_FLAG_KEEP_ADD = 16
 SAMPLING_AUTO, SAMPLING_STREAM, SAMPLING_TILE = 0, 1, 2
-MULTI_ALLREDUCE, MULTI_PEER, MULTI_HYBRID = 0, 1, 2
+MULTI_ALLREDUCE, MULTI_PEER, MULTI_HYBRID, MULTI_AUTO = 0, 1, 2, 3
 
 
 class PgsgdError(RuntimeError):
@@ -61,7 +61,7 @@ EXPORTED_SYMBOLS = [
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
     "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
-    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_set_shard", "pgsgd_engine_path_stress", "pgsgd_engine_local_stress", "pgsgd_engine_order_1d", "pgsgd_engine_order_1d_components", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
+    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_resolved_multi_mode", "pgsgd_engine_set_shard", "pgsgd_engine_path_stress", "pgsgd_engine_local_stress", "pgsgd_engine_order_1d", "pgsgd_engine_order_1d_components", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
 ]
 
 ABI_VERSION = 102  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
@@ -124,6 +124,7 @@ def lib():
         L.pgsgd_engine_attach_comm.argtypes = [vp, vp, i32, i32]
         L.pgsgd_engine_set_multi_mode.argtypes = [vp, i32]
         L.pgsgd_engine_set_shard.argtypes = [vp, u64]
+        L.pgsgd_engine_resolved_multi_mode.argtypes = [vp]
         L.pgsgd_engine_path_stress.argtypes = [vp, i32, u64, u64, vp]
         L.pgsgd_engine_order_1d.argtypes = [vp, vp]
         L.pgsgd_engine_order_1d_components.argtypes = [vp, vp, vp]
@@ -377,8 +378,12 @@ class Engine:
         return order
 
     def set_multi_mode(self, mode: int):
-        """0 = all-reduce of replicated coordinates, 1 = NVLink peer memory (partitioned coordinates)"""
+        """MULTI_ALLREDUCE | MULTI_PEER | MULTI_HYBRID | MULTI_AUTO (include/pgsgd.h)"""
         _check(lib().pgsgd_engine_set_multi_mode(self._h, mode))
+
+    def resolved_multi_mode(self) -> int:
+        """MULTI_* in effect (what MULTI_AUTO resolved to once the coordinates were uploaded)"""
+        return int(lib().pgsgd_engine_resolved_multi_mode(self._h))
 
     def set_shard(self, global_step_count: int):
         """this engine holds only some of the job's paths (graphio.partition_paths); 0 switches the mode off"""

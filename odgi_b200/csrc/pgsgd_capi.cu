@@ -12,7 +12,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <numeric>
+#include <tuple>
 #include <thread>
 #include <unistd.h>
 #include <string>
@@ -28,6 +31,21 @@ using namespace pgsgd;
 namespace {
 
 thread_local std::string g_last_error;
+
+// Process-level communicator cache: ncclCommInitRank costs ~1.5 s on an 8-GPU box, more than a whole c4 layout.  A
+// communicator is kept after its engine is destroyed and handed to the next engine this process attaches with the same
+// (device, n_ranks, rank) — every rank of a job re-attaches together (bench.py, the one-shot multi-GPU calls, a host that
+// lays out several graphs), so all ranks hit or miss the cache together.  PGSGD_COMM_CACHE=0 switches it off.
+struct CommKey {
+    int device, n_ranks, rank;
+    bool operator<(const CommKey& o) const { return std::tie(device, n_ranks, rank) < std::tie(o.device, o.n_ranks, o.rank); }
+};
+std::mutex g_comm_mu;
+std::map<CommKey, ncclComm_t> g_comm_cache;
+bool comm_cache_enabled() {
+    const char* s = getenv("PGSGD_COMM_CACHE");
+    return !(s && s[0] == '0');
+}
 
 int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -148,9 +166,13 @@ struct pgsgd_engine {
     double seconds_upload = 0;
     uint64_t h2d_bytes = 0;
     ncclComm_t comm = nullptr;
+    bool comm_cached = false;               // the communicator belongs to the process-level cache (not destroyed with the engine)
+    bool comm_warm = false;                 // a full-size collective has run on it (NCCL connects its channels lazily)
     int n_ranks = 1, rank = 0;
     // ---- peer mode (PGSGD_MULTI_PEER): coordinates partitioned by node range, accessed through NVLink peer memory ----
     int multi_mode = 0;                      // what the caller selected (PGSGD_MULTI_*)
+    int mode = 0;                            // what AUTO resolved to when the coordinates were uploaded (else == multi_mode)
+    cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;   // bracket a whole run_engine call (both phases of a hybrid run + the switch)
     int active_mode = 0;                     // what the run in progress uses: ALLREDUCE or PEER (HYBRID switches between them)
     bool coords_in_slices = false;           // the authoritative coordinates are in the peer slices (peer phase), not the replica
     bool peer_ready_2d = false, peer_ready_1d = false;
@@ -271,7 +293,7 @@ int setup_peer(pgsgd_engine* e, int dims) {
     if (!e->comm || e->n_ranks < 2) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator with at least 2 ranks");
     if (e->n_ranks > 8) return fail(PGSGD_ERR_ARG, "peer mode supports up to 8 ranks (one NVSwitch domain)");
     const int n = e->n_ranks;
-    e->part_chunk = (e->N + n - 1) / n;
+    e->part_chunk = ((e->N + n - 1) / n + 1) & ~1ull;   // even: the pipelined kernel fetches 1D coordinates as aligned 16-byte pairs
     for (int q = 0; q <= n; ++q) {
         const uint64_t lo = (uint64_t) q * e->part_chunk;
         e->part_lo[q] = (uint32_t) (lo < e->N ? lo : e->N);
@@ -444,9 +466,10 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     int tile_steps = TILE_STEPS;
     if (tile_mode) {
         const bool tma = (cfg->flags & PGSGD_FLAG_TMA_STAGING) != 0;
-        tile2 = !peer && !(cfg->flags & PGSGD_FLAG_LEGACY_TILE) && e->max_path_steps < (1ull << 31) && e->N < (1ull << 30);
+        tile2 = !(cfg->flags & PGSGD_FLAG_LEGACY_TILE) && e->max_path_steps < (1ull << 31) && e->N < (1ull << 30);
         if (tile2) {
-            if (cfg->flags & PGSGD_FLAG_HALF_TILE) tile_steps = 1024;
+            if (peer) tile_steps = TILE_STEPS;   // tile ownership lists are built for this size
+            else if (cfg->flags & PGSGD_FLAG_HALF_TILE) tile_steps = 1024;
             else if ((cfg->flags & PGSGD_FLAG_BIG_TILE) && !tma) tile_steps = 4096;
             batch = 1;
             smem = tile2_smem_bytes(tile_steps, tma, (uint32_t) e->P, &smem_paths);
@@ -621,6 +644,17 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         p.n_parts = (uint32_t) e->n_ranks;
         for (int q = 0; q < 9; ++q) p.part_lo[q] = e->part_lo[q];
         for (int q = 0; q < 8; ++q) { p.part_xy[q] = e->peer_xy[q]; p.part_x1d[q] = e->peer_x1d[q]; }
+        if (tile_mode && tile2) {   // the same walk over this rank's own tiles as the legacy kernel's (set above in p)
+            t2.n_parts = p.n_parts;
+            for (int q = 0; q < 9; ++q) t2.part_lo[q] = p.part_lo[q];
+            for (int q = 0; q < 8; ++q) { t2.part_xy[q] = p.part_xy[q]; t2.part_x1d[q] = p.part_x1d[q]; }
+            t2.tile_list = p.tile_list;
+            t2.n_tiles = p.n_tiles;
+            t2.n_visits = p.n_visits;
+            t2.last_visit_terms = p.last_visit_terms;
+            t2.visit_rank = p.visit_rank;
+            t2.visit_nranks = p.visit_nranks;
+        }
         rc = comm_barrier(e);  // nobody starts before every slice is in place
         if (rc) return rc;
     }
@@ -724,14 +758,16 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
 // NVLink peer memory.  Final stress equals the single-GPU one (oracle emulation + tests/test_gpu_multi.py), at most
 // of the all-reduce mode's throughput in the early phase.
 int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end, pgsgd_stats* stats) {
-    if (e->shard_global_steps && e->comm && e->multi_mode != PGSGD_MULTI_ALLREDUCE)
+    const int mode = e->comm ? e->mode : PGSGD_MULTI_ALLREDUCE;
+    if (e->shard_global_steps && e->comm && mode != PGSGD_MULTI_ALLREDUCE)
         return fail(PGSGD_ERR_STATE, "path-sharded step records need PGSGD_MULTI_ALLREDUCE (peer phases walk tiles by node range)");
-    if (!e->comm || e->multi_mode != PGSGD_MULTI_HYBRID) {
-        e->active_mode = e->comm ? e->multi_mode : PGSGD_MULTI_ALLREDUCE;
+    if (!e->comm || mode != PGSGD_MULTI_HYBRID) {
+        e->active_mode = mode;
         return run_phase(e, cfg, dims, iter_begin, iter_end, stats);
     }
     int rc = check_config(cfg);
     if (rc) return rc;
+    CU(cudaSetDevice(e->device));
     const uint64_t n_iters = dims == 1 ? cfg->iter_max + 1 : cfg->iter_max;
     if (iter_end > n_iters) iter_end = n_iters;
     const uint64_t sw = cfg->multi_switch_iteration ? cfg->multi_switch_iteration : cfg->iter_max / 3;
@@ -739,6 +775,8 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     memset(&a, 0, sizeof(a));
     memset(&b, 0, sizeof(b));
     bool ran_a = false, ran_b = false;
+    // one event pair around BOTH phases: the phase switch (slice scatter + barrier) is part of the job and of its time
+    CU(cudaEventRecord(e->ev_r0, e->stream));
     if (iter_begin < sw && !e->coords_in_slices) {
         e->active_mode = PGSGD_MULTI_ALLREDUCE;
         rc = run_phase(e, cfg, dims, iter_begin, iter_end < sw ? iter_end : sw, &a);
@@ -753,17 +791,55 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
         if (rc) return rc;
         ran_b = true;
     }
+    CU(cudaEventRecord(e->ev_r1, e->stream));
+    CU(cudaEventSynchronize(e->ev_r1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e->ev_r0, e->ev_r1));
     if (stats) {
         pgsgd_stats st = ran_a ? a : b;
         if (ran_a && ran_b) {
             st.iterations_run += b.iterations_run;
             st.term_updates += b.term_updates;
-            st.seconds_iterations += b.seconds_iterations;
             st.kernel_launches += b.kernel_launches;
             st.last_delta_max = b.last_delta_max;
             st.flags_used |= b.flags_used;
         }
+        st.seconds_iterations = ms * 1e-3;
         *stats = st;
+    }
+    return PGSGD_OK;
+}
+
+// AUTO: replicas + one all-reduce per iteration where every replica still sees enough updates per node and iteration for the
+// mean of the replicas to anneal like one Hogwild (deep graphs: many haplotypes per node), else the hybrid schedule whose
+// annealing phase is one shared Hogwild over NVLink (scripts/cpu_exp_allreduce_depth.py).
+int resolve_mode(const pgsgd_engine* e, int dims) {
+    if (e->multi_mode != PGSGD_MULTI_AUTO) return e->multi_mode;
+    if (!e->comm || e->n_ranks < 2 || e->shard_global_steps) return PGSGD_MULTI_ALLREDUCE;
+    const double per_replica = (dims == 2 ? 10.0 : 1.0) * (double) e->S / (double) e->N / (double) e->n_ranks;
+    return per_replica >= PGSGD_AUTO_MIN_UPDATES_PER_NODE ? PGSGD_MULTI_ALLREDUCE : PGSGD_MULTI_HYBRID;
+}
+
+// After a coordinate upload: resolve the mode, build what its phases need (peer slices + IPC mappings + tile ownership)
+// and run the first full-size collective now — NCCL connects its channels lazily, and none of this belongs to an iteration.
+int multi_prepare(pgsgd_engine* e, int dims) {
+    e->mode = resolve_mode(e, dims);
+    if (!e->comm) return PGSGD_OK;
+    if (e->mode == PGSGD_MULTI_PEER || e->mode == PGSGD_MULTI_HYBRID) {
+        if (!(dims == 2 ? e->peer_ready_2d : e->peer_ready_1d)) { int rc = setup_peer(e, dims); if (rc) return rc; }
+    }
+    if (e->mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, dims); if (rc) return rc; }
+    if (!e->comm_warm && e->mode != PGSGD_MULTI_PEER) {
+        const size_t count = dims == 2 ? 4 * e->N : e->N;
+        void* tmp = nullptr;
+        CU(cudaMalloc(&tmp, count * (dims == 2 ? sizeof(float) : sizeof(double))));
+        cudaMemsetAsync(tmp, 0, count * (dims == 2 ? sizeof(float) : sizeof(double)), e->stream);
+        ncclResult_t r = ncclAllReduce(tmp, tmp, count, dims == 2 ? ncclFloat : ncclDouble, ncclSum, e->comm, e->stream);
+        cudaError_t ce = cudaStreamSynchronize(e->stream);
+        cudaFree(tmp);
+        if (r != ncclSuccess) return fail(PGSGD_ERR_NCCL, "warm-up all-reduce: %s", ncclGetErrorString(r));
+        if (ce != cudaSuccess) return fail(PGSGD_ERR_CUDA, "warm-up all-reduce: %s", cudaGetErrorString(ce));
+        e->comm_warm = true;
     }
     return PGSGD_OK;
 }
@@ -841,7 +917,8 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
     int rc = PGSGD_OK;
     auto bail = [&](int code) { pgsgd_engine_destroy(e); return code; };
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(PGSGD_ERR_CUDA, "cudaStreamCreate failed"));
-    if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) return bail(fail(PGSGD_ERR_CUDA, "cudaEventCreate failed"));
+    if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess || cudaEventCreate(&e->ev_r0) != cudaSuccess ||
+        cudaEventCreate(&e->ev_r1) != cudaSuccess) return bail(fail(PGSGD_ERR_CUDA, "cudaEventCreate failed"));
 
     // With caller-supplied positions the node ranks are validated here; without, validation and the per-path bp offsets
     // (xp.cpp:607-616) are done on the device below — no O(S) host pass at all.
@@ -956,13 +1033,15 @@ void pgsgd_engine_destroy(pgsgd_engine* e) {
     cudaSetDevice(e->device);
     for (void* q : e->ipc_opened) cudaIpcCloseMemHandle(q);
     cudaFree(e->d_xy_part); cudaFree(e->d_x1d_part); cudaFree(e->d_tile_list);
-    if (e->comm) ncclCommDestroy(e->comm);
+    if (e->comm && !e->comm_cached) ncclCommDestroy(e->comm);
     cudaFree(e->d_steps); cudaFree(e->d_path_first); cudaFree(e->d_xy); cudaFree(e->d_xy_prev); cudaFree(e->d_x1d);
     cudaFree(e->d_trace); cudaFree(e->d_trace_count);
     cudaFree(e->d_ztab[0]); cudaFree(e->d_ztab[1]);
     cudaFree(e->d_x1d_prev); cudaFree(e->d_frozen); cudaFree(e->d_zetas); cudaFree(e->d_rng); cudaFree(e->d_delta); cudaFree(e->d_counted);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_r0) cudaEventDestroy(e->ev_r0);
+    if (e->ev_r1) cudaEventDestroy(e->ev_r1);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -985,7 +1064,7 @@ int pgsgd_engine_set_coords_2d(pgsgd_engine* e, const double* X, const double* Y
     cudaFree(dX); cudaFree(dY);
     if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "set_coords_2d: %s", cudaGetErrorString(err));
     e->coords_in_slices = false;
-    if (e->multi_mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, 2); if (rc) return rc; }
+    { int rc = multi_prepare(e, 2); if (rc) return rc; }
     e->have_2d = true;
     e->h2d_bytes += 4 * e->N * sizeof(double);
     e->seconds_upload += now_s() - t0;
@@ -1016,7 +1095,7 @@ int pgsgd_engine_set_coords_2d_f32(pgsgd_engine* e, const float* xy) {
     CU(cudaMemcpyAsync(e->d_xy, xy, 4 * e->N * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->coords_in_slices = false;
-    if (e->multi_mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, 2); if (rc) return rc; }
+    { int rc = multi_prepare(e, 2); if (rc) return rc; }
     e->have_2d = true;
     e->h2d_bytes += 4 * e->N * sizeof(float);
     return PGSGD_OK;
@@ -1040,7 +1119,7 @@ int pgsgd_engine_set_coords_1d(pgsgd_engine* e, const double* X) {
     CU(cudaMemcpyAsync(e->d_x1d, src, e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->coords_in_slices = false;
-    if (e->multi_mode == PGSGD_MULTI_PEER) { int rc = peer_scatter(e, 1); if (rc) return rc; }
+    { int rc = multi_prepare(e, 1); if (rc) return rc; }
     e->have_1d = true;
     e->h2d_bytes += e->N * sizeof(double);
     return PGSGD_OK;
@@ -1124,13 +1203,32 @@ int pgsgd_comm_unique_id(uint8_t id_out[128]) {
 int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int n_ranks, int rank) {
     if (!e || !unique_id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(PGSGD_ERR_ARG, "attach_comm: bad arguments");
     CU(cudaSetDevice(e->device));
-    if (e->comm) { ncclCommDestroy(e->comm); e->comm = nullptr; }
+    if (e->comm && !e->comm_cached) ncclCommDestroy(e->comm);
+    e->comm = nullptr;
+    e->comm_cached = false;
+    e->comm_warm = false;
     e->n_ranks = n_ranks;
     e->rank = rank;
     if (n_ranks == 1) return PGSGD_OK;
+    const CommKey key{e->device, n_ranks, rank};
+    if (comm_cache_enabled()) {
+        std::lock_guard<std::mutex> lk(g_comm_mu);
+        auto it = g_comm_cache.find(key);
+        if (it != g_comm_cache.end()) {
+            e->comm = it->second;
+            e->comm_cached = true;
+            e->comm_warm = true;
+            return PGSGD_OK;
+        }
+    }
     ncclUniqueId id;
     memcpy(&id, unique_id, sizeof(id));
     NC(ncclCommInitRank(&e->comm, n_ranks, id, rank));
+    if (comm_cache_enabled()) {
+        std::lock_guard<std::mutex> lk(g_comm_mu);
+        g_comm_cache[key] = e->comm;
+        e->comm_cached = true;
+    }
     return PGSGD_OK;
 }
 
@@ -1191,12 +1289,15 @@ int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out) { return pgsgd_e
 
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode) {
     if (!e) return fail(PGSGD_ERR_ARG, "set_multi_mode: NULL engine");
-    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_PEER && mode != PGSGD_MULTI_HYBRID) return fail(PGSGD_ERR_ARG, "unknown multi-GPU mode %d", mode);
-    if (mode != PGSGD_MULTI_ALLREDUCE && (!e->comm || e->n_ranks < 2)) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator (pgsgd_engine_attach_comm) with >= 2 ranks");
+    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_PEER && mode != PGSGD_MULTI_HYBRID && mode != PGSGD_MULTI_AUTO) return fail(PGSGD_ERR_ARG, "unknown multi-GPU mode %d", mode);
+    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_AUTO && (!e->comm || e->n_ranks < 2)) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator (pgsgd_engine_attach_comm) with >= 2 ranks");
     if (e->have_2d || e->have_1d) return fail(PGSGD_ERR_STATE, "select the multi-GPU mode before uploading coordinates");
     e->multi_mode = mode;
+    e->mode = mode == PGSGD_MULTI_AUTO ? PGSGD_MULTI_ALLREDUCE : mode;
     return PGSGD_OK;
 }
+
+int pgsgd_engine_resolved_multi_mode(const pgsgd_engine* e) { return e ? (e->comm ? e->mode : PGSGD_MULTI_ALLREDUCE) : -1; }
 
 int pgsgd_engine_set_shard(pgsgd_engine* e, uint64_t global_step_count) {
     if (!e) return fail(PGSGD_ERR_ARG, "set_shard: NULL engine");
@@ -1319,10 +1420,11 @@ static int env_gpus() {
 }
 static int env_multi_mode() {
     const char* s = getenv("PGSGD_MULTI");
-    if (!s) return PGSGD_MULTI_HYBRID;
+    if (!s) return PGSGD_MULTI_AUTO;
     if (!strcmp(s, "allreduce")) return PGSGD_MULTI_ALLREDUCE;
     if (!strcmp(s, "peer")) return PGSGD_MULTI_PEER;
-    return PGSGD_MULTI_HYBRID;
+    if (!strcmp(s, "hybrid")) return PGSGD_MULTI_HYBRID;
+    return PGSGD_MULTI_AUTO;
 }
 
 int pgsgd_layout_2d_multi(const pgsgd_graph_view* g, const pgsgd_config* cfg, int n_gpus, int multi_mode, double* X, double* Y, pgsgd_stats* stats) {

@@ -74,6 +74,12 @@ struct Tile2Params {
     unsigned long long* trace;
     unsigned long long* trace_count;
     uint64_t trace_cap;
+    // multi-GPU peer phases (see IterParams): coordinates partitioned by node range, every partition mapped through NVLink
+    uint32_t n_parts;
+    uint32_t part_lo[9];
+    float*  part_xy[8];
+    double* part_x1d[8];
+    const uint32_t* tile_list;  // the tiles this rank owns (2048-step tiles), or nullptr
 };
 
 constexpr int STRESS_STREAMS = 4096;   // generators of the sampled path stress (== ORC_STRESS_STREAMS of the oracle)

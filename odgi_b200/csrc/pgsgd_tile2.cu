@@ -21,7 +21,8 @@
 //   * stages tiles either with coalesced LDG.128 + STS.128 into one buffer or (PGSGD_FLAG_TMA_STAGING) with TMA bulk
 //     copies (cp.async.bulk + mbarrier, SASS UBLKCP) into two buffers, the next visit's tile in flight while the current
 //     one is worked on.
-// Not here (the legacy kernel keeps them): NVLink peer-partitioned coordinates, paths with >= 2^31 steps.
+// Peer phases of multi-GPU runs address the owner's coordinate slice through NVLink with the same pipeline (a remote
+// round trip is just a longer latency to overlap).  Not here (legacy kernel): paths with >= 2^31 steps.
 #include "pgsgd_kernels.cuh"
 
 namespace pgsgd {
@@ -82,6 +83,20 @@ __device__ __forceinline__ float pow_int(float a, int e) {
     return r;
 }
 
+// owner partition of a node (peer phases; n_parts <= 8: a branch-free range count)
+__device__ __forceinline__ uint32_t part_of(const Tile2Params& p, uint32_t node) {
+    uint32_t q = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) q += (k < (int) p.n_parts && node >= p.part_lo[k]) ? 1u : 0u;
+    return q;
+}
+__device__ __forceinline__ float* xy_base(const Tile2Params& p, uint32_t node) {
+    return p.n_parts <= 1 ? p.xy : p.part_xy[part_of(p, node)];
+}
+__device__ __forceinline__ double* x1d_base(const Tile2Params& p, uint32_t node) {
+    return p.n_parts <= 1 ? p.x1d : p.part_x1d[part_of(p, node)];
+}
+
 struct VisitInfo {
     unsigned long long base;    // global index of the tile's first step
     unsigned long long f;       // first step of the path the tile starts in
@@ -94,7 +109,8 @@ struct VisitInfo {
 template <typename FirstPtr>
 __device__ __forceinline__ void make_visit(const Tile2Params& p, FirstPtr first, uint64_t v, uint32_t tile_steps, VisitInfo* out) {
     const uint64_t pass = v / p.n_tiles, i = v - pass * p.n_tiles;
-    const uint64_t t_idx = (i * p.perm_mul[pass & 15] + p.perm_add[pass & 15]) % p.n_tiles;
+    uint64_t t_idx = (i * p.perm_mul[pass & 15] + p.perm_add[pass & 15]) % p.n_tiles;
+    if (p.tile_list) t_idx = p.tile_list[t_idx];   // peer phases: the k-th tile this rank owns
     const uint64_t base = t_idx * (uint64_t) tile_steps;
     const uint64_t end = base + tile_steps <= p.step_count ? base + tile_steps : p.step_count;
     const uint32_t pl = find_path(first, p.path_count, base);
@@ -229,8 +245,8 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
                         delta_max = fmaxf(delta_max, fabsf(Delta));
                         const float rr = Delta * rs;             // Delta / mag
                         const float r_x = rr * dx, r_y = rr * dy;
-                        float2* pa = reinterpret_cast<float2*>(p.xy) + c_ia;
-                        float2* pb = reinterpret_cast<float2*>(p.xy) + c_ib;
+                        float2* pa = reinterpret_cast<float2*>(xy_base(p, c_ia >> 1)) + c_ia;
+                        float2* pb = reinterpret_cast<float2*>(xy_base(p, c_ib >> 1)) + c_ib;
                         if (atomic_add) {
                             red_coord2(pa, -r_x, -r_y, pol_keep);
                             red_coord2(pb, r_x, r_y, pol_keep);
@@ -260,8 +276,8 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
                             const double Delta = mu * (mag - d) * 0.5;
                             delta_max = fmaxf(delta_max, (float) fabs(Delta));
                             const double r_x = Delta / mag * dx;
-                            double* qa = p.x1d + c_ia;
-                            double* qb = p.x1d + c_ib;
+                            double* qa = x1d_base(p, c_ia) + c_ia;
+                            double* qb = x1d_base(p, c_ib) + c_ib;
                             if (atomic_add) {
                                 if (c_upd & 1u) red_coord1(qa, -r_x, pol_keep);
                                 if (c_upd & 2u) red_coord1(qb, r_x, pol_keep);
@@ -309,8 +325,8 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
                         c_ia = b_ia;
                         c_ib = (rb.x >> 1) * 2u + end_b;
                         // the node's float4 {x0,y0,x1,y1} (16 bytes, one sector half) -> slot; the end is picked in stage C
-                        cp_async_16(slot_ca, reinterpret_cast<const float4*>(p.xy) + (c_ia >> 1), pol_keep);
-                        cp_async_16(slot_cb, reinterpret_cast<const float4*>(p.xy) + (c_ib >> 1), pol_keep);
+                        cp_async_16(slot_ca, reinterpret_cast<const float4*>(xy_base(p, c_ia >> 1)) + (c_ia >> 1), pol_keep);
+                        cp_async_16(slot_cb, reinterpret_cast<const float4*>(xy_base(p, c_ib >> 1)) + (c_ib >> 1), pol_keep);
                     } else {
                         const uint32_t na = b_ia, nb = rb.x >> 1;
                         uint32_t u = 3u;
@@ -327,8 +343,8 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
                             c_dij = 1.0f; c_upd = u;
                             c_dij_d = __ull2double_rn(d);
                             c_ia = na; c_ib = nb;
-                            cp_async_16(slot_ca, reinterpret_cast<const double2*>(p.x1d) + (na >> 1), pol_keep);
-                            cp_async_16(slot_cb, reinterpret_cast<const double2*>(p.x1d) + (nb >> 1), pol_keep);
+                            cp_async_16(slot_ca, reinterpret_cast<const double2*>(x1d_base(p, na)) + (na >> 1), pol_keep);
+                            cp_async_16(slot_cb, reinterpret_cast<const double2*>(x1d_base(p, nb)) + (nb >> 1), pol_keep);
                         }
                     }
                 }
