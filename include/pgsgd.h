@@ -242,6 +242,21 @@ int pgsgd_engine_local_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint6
 int pgsgd_engine_order_1d_components(pgsgd_engine* e, const uint32_t* node_component, uint64_t* order_out);
 int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out);   /* == node_component NULL */
 
+/* Sorting goodness of the graph as `order` would sort it: the two metrics of `odgi stats -l [-g] -s [-d]`
+ * (src/subcommand/stats_main.cpp:399-800, 1D branch), evaluated on the device over every consecutive step pair of every path.
+ * order: [N] node ranks in sorted order (e.g. from pgsgd_engine_order_1d) or NULL for the graph as it is.
+ * flags: PGSGD_GOODNESS_GAP_LINKS (-g: a link to the next node of the path's own ordered node set is not penalised),
+ *        PGSGD_GOODNESS_ORIENTATION (-d: orientation changes along a path are penalised).  All sums are integers: exact. */
+#define PGSGD_GOODNESS_GAP_LINKS   1u
+#define PGSGD_GOODNESS_ORIENTATION 2u
+typedef struct pgsgd_goodness {
+    double   mean_links_length_node, mean_links_length_nt;       /* in_node_space, in_nucleotide_space */
+    uint64_t num_links, num_gap_links;
+    double   sum_path_node_dist_node, sum_path_node_dist_nt;
+    uint64_t nodes, nucleotides, num_penalties, num_penalties_diff_orientation;
+} pgsgd_goodness;
+int pgsgd_engine_sort_goodness(pgsgd_engine* e, const uint64_t* order, uint32_t flags, pgsgd_goodness* out);
+
 /* Tile-sampling verification: with a trace buffer set, every term the tile kernel draws is recorded (first step,
  * partner step as global step indices, flips = flip_a | flip_b << 1) until the buffer is full. */
 int pgsgd_engine_set_trace(pgsgd_engine* e, uint64_t capacity);   /* 0 = off */

@@ -61,8 +61,15 @@ EXPORTED_SYMBOLS = [
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
     "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
-    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_resolved_multi_mode", "pgsgd_engine_set_shard", "pgsgd_engine_path_stress", "pgsgd_engine_local_stress", "pgsgd_engine_order_1d", "pgsgd_engine_order_1d_components", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
+    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_resolved_multi_mode", "pgsgd_engine_set_shard", "pgsgd_engine_path_stress", "pgsgd_engine_local_stress", "pgsgd_engine_order_1d", "pgsgd_engine_order_1d_components", "pgsgd_engine_sort_goodness", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
 ]
+
+class GoodnessC(C.Structure):
+    _fields_ = [("mean_links_length_node", C.c_double), ("mean_links_length_nt", C.c_double), ("num_links", C.c_uint64),
+                ("num_gap_links", C.c_uint64), ("sum_path_node_dist_node", C.c_double), ("sum_path_node_dist_nt", C.c_double),
+                ("nodes", C.c_uint64), ("nucleotides", C.c_uint64), ("num_penalties", C.c_uint64),
+                ("num_penalties_diff_orientation", C.c_uint64)]
+
 
 ABI_VERSION = 102  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
 _lib = None
@@ -128,6 +135,7 @@ def lib():
         L.pgsgd_engine_path_stress.argtypes = [vp, i32, u64, u64, vp]
         L.pgsgd_engine_order_1d.argtypes = [vp, vp]
         L.pgsgd_engine_order_1d_components.argtypes = [vp, vp, vp]
+        L.pgsgd_engine_sort_goodness.argtypes = [vp, vp, C.c_uint32, vp]
         L.pgsgd_engine_local_stress.argtypes = [vp, i32, u64, u64, vp]
         L.pgsgd_engine_sample_terms.argtypes = [vp, C.POINTER(ConfigC), i32, i32, dbl, u64, u64] + [vp] * 11
         L.pgsgd_engine_set_trace.argtypes = [vp, u64]
@@ -242,7 +250,8 @@ def sort_defaults(g: FlatGraph, **kw) -> Config:
     space = g.max_path_bp
     space_max = 100
     max_dists = max(space_max + 1, 100)
-    q = max(2, int(np.ceil((space - space_max) / (max_dists - space_max))))
+    # sort_main.cpp:402-411: the derived step only when space > space_max (else the reference falls back to 100)
+    q = max(2, int(np.ceil((space - space_max) / (max_dists - space_max)))) if space > space_max and max_dists > space_max else 100
     c = Config(iter_max=100, min_term_updates=g.S, eta_max=float(ms) * float(ms), space=space, space_max=space_max,
                space_quantization_step=q)
     for k, v in kw.items():
@@ -380,6 +389,13 @@ class Engine:
     def set_multi_mode(self, mode: int):
         """MULTI_ALLREDUCE | MULTI_PEER | MULTI_HYBRID | MULTI_AUTO (include/pgsgd.h)"""
         _check(lib().pgsgd_engine_set_multi_mode(self._h, mode))
+
+    def sort_goodness(self, order: Optional[np.ndarray] = None, gap_links: bool = True, orientation: bool = True) -> dict:
+        """`odgi stats -l [-g] -s [-d]` of the graph as `order` would sort it, on the device (pgsgd_engine_sort_goodness)"""
+        out = GoodnessC()
+        o = None if order is None else np.ascontiguousarray(order, dtype=np.uint64)
+        _check(lib().pgsgd_engine_sort_goodness(self._h, _ptr(o), (1 if gap_links else 0) | (2 if orientation else 0), C.byref(out)))
+        return {f: getattr(out, f) for f, _ in GoodnessC._fields_}
 
     def resolved_multi_mode(self) -> int:
         """MULTI_* in effect (what MULTI_AUTO resolved to once the coordinates were uploaded)"""

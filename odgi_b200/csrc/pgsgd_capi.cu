@@ -140,6 +140,7 @@ struct pgsgd_engine {
     bool any_multi_step_path = false;
     StepRec* d_steps = nullptr;
     uint64_t* d_path_first = nullptr;
+    uint32_t* d_node_len = nullptr;          // [N] kept for the sorting-goodness readout
     float* d_xy = nullptr;        // 2D coordinates
     float* d_xy_prev = nullptr;   // multi-GPU sum-of-deltas scratch
     double* d_x1d = nullptr;      // 1D coordinates
@@ -956,22 +957,23 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
 
     // flatten-to-device: SoA chunks are staged and packed into 16-byte step records by a device kernel
     uint32_t* d_node_len = nullptr;
-    if (cudaMalloc(&d_node_len, e->N * sizeof(uint32_t)) != cudaSuccess) return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc node_len staging failed"));
-    if ((err = cudaMemcpyAsync(d_node_len, g->node_len, e->N * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) { cudaFree(d_node_len); return cu_bail(err, "upload node_len"); }
+    if ((rc = dev_alloc(e, &e->d_node_len, e->N))) return bail(rc);
+    d_node_len = e->d_node_len;
+    if ((err = cudaMemcpyAsync(d_node_len, g->node_len, e->N * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream)) != cudaSuccess) { return cu_bail(err, "upload node_len"); }
     e->h2d_bytes += e->N * sizeof(uint32_t);
     uint32_t* d_sn = nullptr; uint8_t* d_sr = nullptr; uint64_t* d_sp = nullptr;
     uint32_t* d_depth = nullptr;  // steps per node, counted while packing
     unsigned long long* d_maxdup = nullptr;
     if (cudaMalloc(&d_depth, e->N * sizeof(uint32_t)) != cudaSuccess || cudaMemsetAsync(d_depth, 0, e->N * sizeof(uint32_t), e->stream) != cudaSuccess ||
         cudaMalloc(&d_maxdup, sizeof(unsigned long long)) != cudaSuccess || cudaMemsetAsync(d_maxdup, 0, sizeof(unsigned long long), e->stream) != cudaSuccess) {
-        cudaFree(d_node_len); cudaFree(d_depth); cudaFree(d_maxdup);
+        cudaFree(d_depth); cudaFree(d_maxdup);
         return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc depth table failed"));
     }
     if (pos) {
         const uint64_t CH = 1ull << 26;  // 64 Mi steps per staging chunk (832 MiB of SoA)
         const uint64_t ch = e->S < CH ? (e->S ? e->S : 1) : CH;
         bool ok = cudaMalloc(&d_sn, ch * 4) == cudaSuccess && cudaMalloc(&d_sp, ch * 8) == cudaSuccess && (!g->step_rev || cudaMalloc(&d_sr, ch) == cudaSuccess);
-        if (!ok) { cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
+        if (!ok) { cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
         for (uint64_t off = 0; off < e->S && err == cudaSuccess; off += ch) {
             const uint64_t n = e->S - off < ch ? e->S - off : ch;
             err = cudaMemcpyAsync(d_sn, g->step_node + off, n * 4, cudaMemcpyHostToDevice, e->stream);
@@ -988,7 +990,7 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
         int* d_bad = nullptr;
         bool ok = cudaMalloc(&d_sn, n * 4) == cudaSuccess && cudaMalloc(&d_sp, n * 8) == cudaSuccess && cudaMalloc(&d_bad, sizeof(int)) == cudaSuccess &&
                   (!g->step_rev || cudaMalloc(&d_sr, n) == cudaSuccess);
-        if (!ok) { cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_bad); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
+        if (!ok) { cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_bad); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
         err = cudaMemsetAsync(d_bad, 0, sizeof(int), e->stream);
         if (err == cudaSuccess) err = cudaMemcpyAsync(d_sn, g->step_node, e->S * 4, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev, e->S, cudaMemcpyHostToDevice, e->stream);
@@ -999,7 +1001,7 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
         cudaFree(d_bad);
         e->h2d_bytes += e->S * (4 + (g->step_rev ? 1 : 0));
         if (err == cudaSuccess && bad) {
-            cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
+            cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
             return bail(fail(PGSGD_ERR_UNOPT, "a step refers to a node rank >= node_count: ids are not compacted 1..N"));
         }
     }
@@ -1020,7 +1022,7 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
         e->max_path_bp = mb;
     }
     cudaFree(d_maxdup);
-    cudaFree(d_node_len); cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
+    cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
     if (err != cudaSuccess) return cu_bail(err, "flatten-to-device");
     if ((err = cudaStreamSynchronize(e->stream)) != cudaSuccess) return cu_bail(err, "engine create sync");
     e->seconds_upload = now_s() - t0;
@@ -1034,7 +1036,7 @@ void pgsgd_engine_destroy(pgsgd_engine* e) {
     for (void* q : e->ipc_opened) cudaIpcCloseMemHandle(q);
     cudaFree(e->d_xy_part); cudaFree(e->d_x1d_part); cudaFree(e->d_tile_list);
     if (e->comm && !e->comm_cached) ncclCommDestroy(e->comm);
-    cudaFree(e->d_steps); cudaFree(e->d_path_first); cudaFree(e->d_xy); cudaFree(e->d_xy_prev); cudaFree(e->d_x1d);
+    cudaFree(e->d_steps); cudaFree(e->d_path_first); cudaFree(e->d_node_len); cudaFree(e->d_xy); cudaFree(e->d_xy_prev); cudaFree(e->d_x1d);
     cudaFree(e->d_trace); cudaFree(e->d_trace_count);
     cudaFree(e->d_ztab[0]); cudaFree(e->d_ztab[1]);
     cudaFree(e->d_x1d_prev); cudaFree(e->d_frozen); cudaFree(e->d_zetas); cudaFree(e->d_rng); cudaFree(e->d_delta); cudaFree(e->d_counted);
@@ -1286,6 +1288,38 @@ int pgsgd_engine_order_1d_components(pgsgd_engine* e, const uint32_t* node_compo
 }
 
 int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out) { return pgsgd_engine_order_1d_components(e, nullptr, order_out); }
+
+int pgsgd_engine_sort_goodness(pgsgd_engine* e, const uint64_t* order, uint32_t flags, pgsgd_goodness* out) {
+    if (!e || !out) return fail(PGSGD_ERR_ARG, "sort_goodness: NULL argument");
+    CU(cudaSetDevice(e->device));
+    uint64_t* d_order = nullptr;
+    if (order) {
+        std::vector<uint8_t> seen(e->N, 0);
+        for (uint64_t k = 0; k < e->N; ++k) {
+            if (order[k] >= e->N || seen[order[k]]) return fail(PGSGD_ERR_ARG, "sort_goodness: order is not a permutation of the node ranks (entry %llu)", (unsigned long long) k);
+            seen[order[k]] = 1;
+        }
+        CU(cudaMalloc(&d_order, (e->N ? e->N : 1) * sizeof(uint64_t)));
+        cudaError_t ce = cudaMemcpy(d_order, order, e->N * sizeof(uint64_t), cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) { cudaFree(d_order); return fail(PGSGD_ERR_CUDA, "sort_goodness: %s", cudaGetErrorString(ce)); }
+    }
+    unsigned long long a[9];
+    cudaError_t err = launch_goodness(e->d_steps, e->d_path_first, nullptr, (uint32_t) e->P, e->S, e->N, e->d_node_len, d_order, flags, a, e->stream);
+    cudaFree(d_order);
+    if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "sort_goodness: %s", cudaGetErrorString(err));
+    memset(out, 0, sizeof(*out));
+    out->num_links = a[2];
+    out->num_gap_links = a[3];
+    out->mean_links_length_node = a[2] ? (double) a[0] / (double) a[2] : 0.0;
+    out->mean_links_length_nt = a[2] ? (double) a[1] / (double) a[2] : 0.0;
+    out->nodes = e->S;
+    out->nucleotides = a[6];
+    out->sum_path_node_dist_node = e->S ? (double) a[4] / (double) e->S : 0.0;
+    out->sum_path_node_dist_nt = a[6] ? (double) a[5] / (double) a[6] : 0.0;
+    out->num_penalties = a[7];
+    out->num_penalties_diff_orientation = a[8];
+    return PGSGD_OK;
+}
 
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode) {
     if (!e) return fail(PGSGD_ERR_ARG, "set_multi_mode: NULL engine");

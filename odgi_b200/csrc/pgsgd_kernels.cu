@@ -19,6 +19,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 
 namespace pgsgd {
 
@@ -962,6 +963,132 @@ cudaError_t launch_sample_terms(int dims, const SamplerParams& sp, const StepRec
     else if (dims == 1) sample_terms_kernel<1><<<1, 32, 0, stream>>>(sp, steps, seed, n_terms, out);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sorting-goodness readout on the device: `odgi stats -l [-g] -s [-d]` of the graph sorted by `order`
+// (src/subcommand/stats_main.cpp:399-800, 1D branch): every consecutive step pair of every path is a link; all sums are
+// 64-bit integers, so the result equals the oracle's (oracle.sort_goodness) exactly.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void scatter_rank_kernel(uint32_t* new_rank, const uint64_t* order, uint64_t n) {
+    const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) new_rank[order[k]] = (uint32_t) k;
+}
+__global__ void gather_len_by_order_kernel(uint64_t* out, const uint32_t* node_len, const uint64_t* order, uint64_t n) {
+    const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = node_len[order[k]];
+    if (k == n) out[k] = 0;
+}
+__global__ void step_rank_kernel(uint32_t* out, const StepRec* steps, const uint32_t* new_rank, uint64_t n) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = new_rank[steps[i].handle >> 1];
+}
+
+// acc: [0] mll node, [1] mll nt, [2] links, [3] gap links, [4] spd node, [5] spd nt, [6] nucleotides, [7] penalties, [8] diff orientation
+__global__ void goodness_kernel(const StepRec* steps, const uint64_t* first, uint32_t P, uint64_t S, const uint32_t* new_rank,
+                                const uint64_t* pm, const uint32_t* sorted_rank, uint32_t flags, unsigned long long* acc) {
+    unsigned long long a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint64_t s = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (uint64_t) gridDim.x * blockDim.x) {
+        const uint4 h = load_step(steps, s);
+        a[6] += h.y;
+        const uint32_t p = find_path(first, P, s);
+        const uint64_t lo = first[p], hi = first[p + 1];
+        if (s + 1 == hi) {            // end of path: "so the best metric equals 1" (stats_main.cpp:733-735)
+            a[4] += 1;
+            a[5] += h.y;
+            continue;
+        }
+        const uint4 i = load_step(steps, s + 1);
+        const uint32_t uh = new_rank[h.x >> 1], ui = new_rank[i.x >> 1], bh = h.x & 1u, bi = i.x & 1u;
+        a[2] += 1;
+        bool gap = false;
+        if (flags & 1u) {             // -g: the link to the next node of the path's own ordered node set is not penalised (:479-511)
+            uint64_t l = lo, r = hi;  // first element > uh in the path's sorted ranks
+            while (l < r) {
+                const uint64_t m = (l + r) >> 1;
+                if (sorted_rank[m] <= uh) l = m + 1; else r = m;
+            }
+            gap = l < hi && sorted_rank[l] == ui;
+        }
+        if (gap) {
+            a[3] += 1;
+        } else {
+            uint32_t ia = uh + (1u - bh), ib = ui + bi;
+            if (ib < ia) { const uint32_t t = ia; ia = ib; ib = t; }
+            a[0] += ib - ia;
+            a[1] += pm[ib] - pm[ia];
+        }
+        uint32_t x = uh, y = ui;
+        unsigned long long w = 1;
+        if (y < x) { x = ui; y = uh; w = 3; a[7] += 1; }
+        const unsigned long long dn = y - x, dt = pm[y] - pm[x];
+        a[4] += w * dn;
+        a[5] += w * dt;
+        if (bh != bi) {
+            a[8] += 1;
+            if (flags & 2u) { a[4] += 2 * dn; a[5] += 2 * dt; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        unsigned long long v = a[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(acc + k, v);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_goodness(const StepRec* steps, const uint64_t* first, const uint64_t* h_first, uint32_t P, uint64_t S, uint64_t N,
+                            const uint32_t* d_node_len, const uint64_t* d_order, uint32_t flags, unsigned long long* h_acc9, cudaStream_t stream) {
+    uint32_t *new_rank = nullptr, *sr_in = nullptr, *sr_out = nullptr;
+    uint64_t* pm = nullptr;
+    unsigned long long* acc = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0, tmp2 = 0;
+    uint64_t* own_order = nullptr;
+    cudaError_t e = cudaMalloc(&new_rank, (N ? N : 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&pm, (N + 1) * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&acc, 9 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(acc, 0, 9 * sizeof(unsigned long long), stream);
+    if (e == cudaSuccess && !d_order) {
+        e = cudaMalloc(&own_order, (N ? N : 1) * sizeof(uint64_t));
+        if (e == cudaSuccess) { iota_kernel<<<grid_for(N, 256), 256, 0, stream>>>(own_order, N); e = cudaGetLastError(); }
+        d_order = own_order;
+    }
+    if (e == cudaSuccess && N) {
+        scatter_rank_kernel<<<grid_for(N, 256), 256, 0, stream>>>(new_rank, d_order, N);
+        gather_len_by_order_kernel<<<grid_for(N + 1, 256), 256, 0, stream>>>(pm, d_node_len, d_order, N);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pm, pm, N + 1, stream);
+    if ((flags & 1u) && e == cudaSuccess && S) {
+        e = cudaMalloc(&sr_in, S * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&sr_out, S * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cub::DeviceSegmentedSort::SortKeys(tmp, tmp2, sr_in, sr_out, (int64_t) S, (int64_t) P, first, first + 1, stream);
+        if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, pm, pm, N + 1, stream);
+    if ((flags & 1u) && e == cudaSuccess && S) {
+        step_rank_kernel<<<grid_for(S, 256), 256, 0, stream>>>(sr_in, steps, new_rank, S);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cub::DeviceSegmentedSort::SortKeys(tmp, tmp_bytes, sr_in, sr_out, (int64_t) S, (int64_t) P, first, first + 1, stream);
+    }
+    if (e == cudaSuccess && S) {
+        const unsigned grid = (unsigned) (S / 256 + 1 < 148 * 16 ? S / 256 + 1 : 148 * 16);
+        goodness_kernel<<<grid, 256, 0, stream>>>(steps, first, P, S, new_rank, pm, sr_out, flags, acc);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_acc9, acc, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(tmp); cudaFree(new_rank); cudaFree(pm); cudaFree(acc); cudaFree(sr_in); cudaFree(sr_out); cudaFree(own_order);
+    (void) h_first;
+    return e;
 }
 
 }  // namespace pgsgd

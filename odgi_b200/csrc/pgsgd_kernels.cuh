@@ -130,6 +130,11 @@ cudaError_t launch_tile_repeats(const uint32_t* step_node, uint64_t n, unsigned 
 // 1D node order on the device: node ranks sorted by ([component key,] x, rank), stable radix sorts; d_component may be null
 cudaError_t launch_order_1d(const double* x, const uint32_t* d_component, uint64_t* order_out, uint64_t n, cudaStream_t stream);
 
+// sorting-goodness sums (odgi stats -l -g -s -d) of the graph sorted by d_order (device, [N] node ranks; null = as it is);
+// flags bit 0: -g (gap links not penalised), bit 1: -d (orientation changes penalised); h_acc9: see goodness_kernel
+cudaError_t launch_goodness(const StepRec* steps, const uint64_t* first, const uint64_t* h_first, uint32_t P, uint64_t S, uint64_t N,
+                            const uint32_t* d_node_len, const uint64_t* d_order, uint32_t flags, unsigned long long* h_acc9, cudaStream_t stream);
+
 // coordinate format conversion: reference X/Y (double, index 2*node+end) <-> device float4-per-node
 cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n_nodes, cudaStream_t stream);
 cudaError_t launch_XY_from_xy(double* X, double* Y, const float* xy, uint64_t n_nodes, cudaStream_t stream);

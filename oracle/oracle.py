@@ -220,7 +220,7 @@ def default_sort_config(g: Graph, **kw) -> Config:
     space = g.max_path_bp
     space_max = 100
     max_dists = max(space_max + 1, 100)
-    q = max(2, int(np.ceil((space - space_max) / (max_dists - space_max))))
+    q = max(2, int(np.ceil((space - space_max) / (max_dists - space_max)))) if space > space_max and max_dists > space_max else 100   # sort_main.cpp:402-411
     c = Config(iter_max=100, min_term_updates=g.S, eta_max=float(ms) * float(ms), space=space, space_max=space_max,
                space_quantization_step=q)
     for k, v in kw.items():
@@ -475,3 +475,63 @@ def order_from_x(x: np.ndarray, component: Optional[np.ndarray] = None) -> np.nd
     comp = np.zeros(n, dtype=np.uint64) if component is None else np.asarray(component, dtype=np.uint64)
     handle = np.arange(n, dtype=np.uint64) << np.uint64(1)
     return np.lexsort((handle, np.asarray(x, dtype=np.float64), comp)).astype(np.uint64)
+
+
+def sort_goodness(node_len, path_first_step, step_node, step_rev, order=None, dont_penalize_gap_links=True, penalize_diff_orientation=True):
+    """`odgi stats -l [-g] -s [-d]` on the graph sorted by `order` (node ranks in sorted order; None = the graph as it is):
+    mean_links_length and sum_of_path_node_distances in node space and nucleotide space, restated from
+    src/subcommand/stats_main.cpp:399-800 (1D branch; ids compact, so nspace[k] == k).  The reference publishes these for
+    DRB1-3123 before and after `odgi sort -Y` (docs/rst/tutorials/sort_layout.rst:101-106,175-186)."""
+    node_len = np.asarray(node_len, dtype=np.int64)
+    first = np.asarray(path_first_step, dtype=np.int64)
+    sn = np.asarray(step_node, dtype=np.int64)
+    rev = np.zeros(len(sn), dtype=np.int64) if step_rev is None else np.asarray(step_rev, dtype=np.int64)
+    n = len(node_len)
+    order = np.arange(n, dtype=np.int64) if order is None else np.asarray(order, dtype=np.int64)
+    new_rank = np.empty(n, dtype=np.int64)
+    new_rank[order] = np.arange(n, dtype=np.int64)
+    pm = np.concatenate(([0], np.cumsum(node_len[order])))          # position_map (:429-447): bp before sorted rank k
+    r = new_rank[sn]
+    S = len(sn)
+    is_last = np.zeros(S, dtype=bool)
+    is_last[first[1:][first[1:] > first[:-1]] - 1] = True
+    src = np.nonzero(~is_last)[0]                                   # steps that have a next step in their path
+    uh, ui, bh, bi = r[src], r[src + 1], rev[src], rev[src + 1]
+    # ---- mean_links_length (:449-600) ----
+    gap = np.zeros(len(src), dtype=bool)
+    if dont_penalize_gap_links:
+        path_of = np.searchsorted(first, src, side="right") - 1
+        for p in range(len(first) - 1):
+            sel = path_of == p
+            if not sel.any():
+                continue
+            uniq = np.unique(r[first[p]:first[p + 1]])             # the ordered set of node numbers in the path (:479,487-491)
+            idx = np.searchsorted(uniq, uh[sel])
+            succ = np.where(idx + 1 < len(uniq), uniq[np.minimum(idx + 1, len(uniq) - 1)], -1)
+            gap[sel] = succ == ui[sel]
+    ia = uh + (1 - bh)
+    ib = ui + bi
+    lo, hi = np.minimum(ia, ib), np.maximum(ia, ib)
+    pen = ~gap
+    links = len(src)
+    mll_node = float((hi - lo)[pen].sum()) / links if links else 0.0
+    mll_nt = float((pm[hi] - pm[lo])[pen].sum()) / links if links else 0.0
+    # ---- sum_of_path_node_distances (:602-800) ----
+    a, b = np.minimum(uh, ui), np.maximum(uh, ui)
+    back = ui < uh
+    w = np.where(back, 3, 1)
+    d_node, d_nt = b - a, pm[b] - pm[a]
+    sum_node = int((w * d_node).sum())
+    sum_nt = int((w * d_nt).sum())
+    diff = bh != bi
+    if penalize_diff_orientation:
+        sum_node += int(2 * d_node[diff].sum())
+        sum_nt += int(2 * d_nt[diff].sum())
+    nonempty = first[1:] > first[:-1]
+    last_nodes = sn[first[1:][nonempty] - 1]
+    sum_node += int(nonempty.sum())                                 # "add end of path so the best metric equals 1" (:733-735)
+    sum_nt += int(node_len[last_nodes].sum())
+    len_node, len_nt = S, int(node_len[sn].sum())
+    return {"mean_links_length_node": mll_node, "mean_links_length_nt": mll_nt, "num_links": links, "num_gap_links": int(gap.sum()),
+            "sum_path_node_dist_node": sum_node / len_node if len_node else 0.0, "sum_path_node_dist_nt": sum_nt / len_nt if len_nt else 0.0,
+            "nodes": len_node, "nucleotides": len_nt, "num_penalties": int(back.sum()), "num_penalties_diff_orientation": int(diff.sum())}

@@ -72,3 +72,8 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# The flattened DRB1-3123_unsorted graph (the input of the reference's sorting tutorial, docs/rst/tutorials/sort_layout.rst)
+# was added with:  oracle/_ref/ref_driver dump /root/reference/test/DRB1-3123_unsorted.gfa u.arr  -> keep node_len,
+# path_first_step, step_node, step_rev, step_pos -> gzip -> tests/golden/DRB1-3123_unsorted.graph.arr.gz
