@@ -269,7 +269,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--workload", default="c4", help="c4 (default) | mid | small | tiny | test-graph name | c5 | c5s (rank-locally generated, path-sharded: "
+                                                    "BASELINE config 5 needs --gpus 8)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--force-c4", action="store_true", help="--impl reference-cuda on c4 itself (writes a 9 GB GFA, ~6 minutes)")
     ap.add_argument("--no-reference-cuda", action="store_true", help="skip the live reference-CUDA-kernel leg of the default line")
@@ -308,15 +309,39 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    g, desc = make_workload(args.workload)
     W, K = args.warmup, args.steps
     iter_max = max(30, W + K)
-    # the schedule's parameters (U, space, eta_max) are those of the WHOLE job, whatever a rank holds of it
-    cfg = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags, sampling=args.sampling)
-    job_steps = g.S
-    sharded = world > 1 and args.multi == "sharded"
-    if sharded:
-        g = odgi_b200.shard_paths(g, world, rank)   # this rank's paths only; node table whole
+    from odgi_b200 import synth
+    generated_sharded = args.workload in synth.SHARDED_PRESETS
+    if generated_sharded:
+        # BASELINE config 5 (and its small stand-in): every rank synthesises ITS OWN paths (p = rank mod world) plus the common node
+        # table — no process ever holds the whole graph; step records are path-sharded, coordinates replicated, one all-reduce/step.
+        # The reference's own CUDA kernel cannot run this size at all: 32-bit step index (src/cuda/layout.cu:207).
+        n_sites, n_paths = synth.SHARDED_PRESETS[args.workload]
+        g, my_paths = synth.generate_sharded(n_sites, n_paths, rank, world, seed=42)
+        desc = f"synthetic '{args.workload}' generated rank-locally (odgi_b200/synth.py generate_sharded, seed 42): {n_sites} sites x {n_paths} haplotypes"
+        tot = torch.tensor([float(g.S), float(g.max_path_steps)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            tmax = tot.clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tot[1] = tmax[1]
+        job_steps, job_max_steps = int(tot[0].item()), int(tot[1].item())
+        # layout_main.cpp:251-266 on the WHOLE job: U = 10 * S, space = longest path in steps, eta_max = that squared
+        cfg = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags, sampling=args.sampling)
+        cfg.min_term_updates = 10 * job_steps
+        cfg.space = job_max_steps
+        cfg.eta_max = float(job_max_steps) * float(job_max_steps)
+        sharded = world > 1
+        args.multi = "sharded" if sharded else args.multi
+    else:
+        g, desc = make_workload(args.workload)
+        # the schedule's parameters (U, space, eta_max) are those of the WHOLE job, whatever a rank holds of it
+        cfg = capi.layout_defaults(g, iter_max=iter_max, batch=args.batch, n_streams=args.streams, flags=args.flags, sampling=args.sampling)
+        job_steps = g.S
+        sharded = world > 1 and args.multi == "sharded"
+        if sharded:
+            g = odgi_b200.shard_paths(g, world, rank)   # this rank's paths only; node table whole
     multi_mode = {"auto": capi.MULTI_AUTO, "peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE,
                   "sharded": capi.MULTI_ALLREDUCE}[args.multi]
     sampling_name = {1: "stream", 2: "tile"}.get(args.sampling, "tile" if g.S >= (1 << 22) else "stream")
@@ -461,7 +486,7 @@ def main():
     line = {
         "metric": "M node-pair SGD updates/sec", "value": value, "unit": "M updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic" if args.workload in ("c4", "mid", "small", "tiny") else "reference test graph (flattened fixture)",
+        "data": "synthetic" if args.workload in ("c4", "mid", "small", "tiny", "c5", "c5s") else "reference test graph (flattened fixture)",
         "config": {"workload": args.workload, "description": desc, "nodes": g.N, "paths": g.P if not sharded else None, "steps_in_graph": job_steps,
                    "updates_per_step": U, "iter_max": iter_max, "timed_iterations": [W, W + K], "sampling": sampling_name, "batch": args.batch or "auto",
                    "l2_policy": "inputs larger than L2" if g.S * 16 > 126e6 else "L2-resident graph (plumbing config)",

@@ -1244,6 +1244,13 @@ static int stress_impl(pgsgd_engine* e, int dims, int local, uint64_t n_pairs, u
     unsigned long long* d_used = nullptr;
     CU(cudaMalloc(&d_acc, STRESS_STREAMS * sizeof(double)));
     if (cudaMalloc(&d_used, STRESS_STREAMS * sizeof(unsigned long long)) != cudaSuccess) { cudaFree(d_acc); return fail(PGSGD_ERR_NOMEM, "cudaMalloc failed"); }
+    // path-sharded records: every rank evaluates its own paths with its share of the pairs (own generator streams) and the
+    // sums are combined over the communicator below — a COLLECTIVE call then, like the getters of the peer modes
+    const bool collective = e->shard_global_steps != 0 && e->comm != nullptr;
+    if (collective) {
+        n_pairs = (uint64_t) ((unsigned __int128) n_pairs * e->S / e->shard_global_steps);
+        seed += (uint64_t) e->rank * STRESS_STREAMS;
+    }
     const uint64_t per = (n_pairs + STRESS_STREAMS - 1) / STRESS_STREAMS;
     cudaError_t err = launch_stress(dims, local, e->d_path_first, (uint32_t) e->P, e->S, e->d_steps, e->d_xy, e->d_x1d, per, seed, d_acc, d_used, e->stream);
     std::vector<double> acc(STRESS_STREAMS);
@@ -1256,7 +1263,19 @@ static int stress_impl(pgsgd_engine* e, int dims, int local, uint64_t n_pairs, u
     double total = 0;
     unsigned long long n = 0;
     for (int t = 0; t < STRESS_STREAMS; ++t) { total += acc[t]; n += used[t]; }
-    *stress_out = n ? total / (double) n : 0.0;
+    double pair[2] = {total, (double) n};
+    if (collective) {
+        double* d_pair = nullptr;
+        CU(cudaMalloc(&d_pair, 2 * sizeof(double)));
+        cudaError_t ce = cudaMemcpyAsync(d_pair, pair, sizeof(pair), cudaMemcpyHostToDevice, e->stream);
+        ncclResult_t r = ce == cudaSuccess ? ncclAllReduce(d_pair, d_pair, 2, ncclDouble, ncclSum, e->comm, e->stream) : ncclSuccess;
+        if (ce == cudaSuccess && r == ncclSuccess) ce = cudaMemcpyAsync(pair, d_pair, sizeof(pair), cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        cudaFree(d_pair);
+        if (r != ncclSuccess) return fail(PGSGD_ERR_NCCL, "path_stress: %s", ncclGetErrorString(r));
+        if (ce != cudaSuccess) return fail(PGSGD_ERR_CUDA, "path_stress: %s", cudaGetErrorString(ce));
+    }
+    *stress_out = pair[1] > 0 ? pair[0] / pair[1] : 0.0;
     return PGSGD_OK;
 }
 

@@ -105,3 +105,26 @@ def test_path_assignment_is_balanced_and_complete():
             assert np.array_equal(s.step_node[: hi - lo], g.step_node[lo:hi]) and np.array_equal(s.step_pos[: hi - lo], g.step_pos[lo:hi])
             seen += s.S
         assert seen == g.S
+
+
+def test_rank_local_generator_shards_one_well_defined_graph():
+    """synth.generate_sharded (BASELINE config 5's generator): the union of the ranks' shards is the same graph whatever the
+    number of ranks; every rank carries the whole node table; paths are dealt out p = rank (mod n_ranks)."""
+    import numpy as np
+    from odgi_b200 import synth
+    whole, ids = synth.generate_sharded(30_000, 7, 0, 1, seed=5)
+    assert ids == list(range(7)) and whole.P == 7
+    wf = whole.path_first_step.astype(np.int64)
+    for n_ranks in (2, 3, 8):
+        seen, steps = [], 0
+        for r in range(n_ranks):
+            g, mine = synth.generate_sharded(30_000, 7, r, n_ranks, seed=5)
+            assert mine == list(range(r, 7, n_ranks)) and np.array_equal(g.node_len, whole.node_len)
+            f = g.path_first_step.astype(np.int64)
+            for j, p in enumerate(mine):
+                assert np.array_equal(g.step_node[f[j]:f[j + 1]], whole.step_node[wf[p]:wf[p + 1]])
+                assert np.array_equal(g.step_rev[f[j]:f[j + 1]], whole.step_rev[wf[p]:wf[p + 1]])
+            seen += mine
+            steps += g.S
+        assert sorted(seen) == list(range(7)) and steps == whole.S
+    assert whole.step_node.max() < whole.N and whole.step_rev.sum() > 0   # inversions present
