@@ -112,13 +112,14 @@ def test_rank_local_generator_shards_one_well_defined_graph():
     number of ranks; every rank carries the whole node table; paths are dealt out p = rank (mod n_ranks)."""
     import numpy as np
     from odgi_b200 import synth
-    whole, ids = synth.generate_sharded(30_000, 7, 0, 1, seed=5)
+    kw = dict(seed=5, inv_per_mbp=20.0, dup_per_mbp=10.0)   # enough structural events at this size to exercise them
+    whole, ids = synth.generate_sharded(30_000, 7, 0, 1, **kw)
     assert ids == list(range(7)) and whole.P == 7
     wf = whole.path_first_step.astype(np.int64)
     for n_ranks in (2, 3, 8):
         seen, steps = [], 0
         for r in range(n_ranks):
-            g, mine = synth.generate_sharded(30_000, 7, r, n_ranks, seed=5)
+            g, mine = synth.generate_sharded(30_000, 7, r, n_ranks, **kw)
             assert mine == list(range(r, 7, n_ranks)) and np.array_equal(g.node_len, whole.node_len)
             f = g.path_first_step.astype(np.int64)
             for j, p in enumerate(mine):
@@ -127,4 +128,4 @@ def test_rank_local_generator_shards_one_well_defined_graph():
             seen += mine
             steps += g.S
         assert sorted(seen) == list(range(7)) and steps == whole.S
-    assert whole.step_node.max() < whole.N and whole.step_rev.sum() > 0   # inversions present
+    assert whole.step_node.max() < whole.N and whole.step_rev.sum() > 0 and whole.S > 7 * 30_000   # inversions and duplications present
