@@ -21,6 +21,7 @@ PGSGD_FLAG_PLAIN_STORE = 4
 PGSGD_FLAG_TMA_STAGING = 8
 PGSGD_FLAG_KEEP_ADD = 16
 SAMPLING_AUTO, SAMPLING_STREAM, SAMPLING_TILE = 0, 1, 2
+FLAG_EXCH_WRITE, FLAG_SUM_DELTAS, FLAG_PLAIN_STORE, FLAG_TMA_STAGING, FLAG_KEEP_ADD, FLAG_LEGACY_TILE, FLAG_HALF_TILE, FLAG_BIG_TILE = 1, 2, 4, 8, 16, 32, 64, 128
 MULTI_ALLREDUCE, MULTI_PEER, MULTI_HYBRID, MULTI_AUTO = 0, 1, 2, 3
 
 
@@ -377,6 +378,12 @@ class Engine:
     def path_stress(self, dims: int, n_pairs: int = 1_000_000, seed: int = 12345) -> float:
         out = C.c_double(0.0)
         _check(lib().pgsgd_engine_path_stress(self._h, dims, n_pairs, seed, C.byref(out)))
+        return float(out.value)
+
+    def local_stress(self, dims: int, n_pairs: int = 1_000_000, seed: int = 12345) -> float:
+        """near-pair stress (partner 1..64 ranks away along the path, <= 1000 bp): pgsgd_engine_local_stress"""
+        out = C.c_double(0.0)
+        _check(lib().pgsgd_engine_local_stress(self._h, dims, n_pairs, seed, C.byref(out)))
         return float(out.value)
 
     def order_1d(self, component: Optional[np.ndarray] = None) -> np.ndarray:

@@ -10,6 +10,7 @@
 //        path_linear_sgd (src/algorithms/path_sgd.cpp:12-31); the body of `odgi sort --gpu`: path_linear_sgd_order
 //        (path_sgd.cpp:503-684) calls it where it calls path_linear_sgd today.
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -55,7 +56,9 @@ namespace cuda {
 void gpu_layout(layout_config_t config, const odgi::graph_t& graph, std::vector<std::atomic<double>>& X,
                 std::vector<std::atomic<double>>& Y) {
     std::cout << "===== Use GPU to compute odgi-layout =====" << std::endl;  // layout.cu:293
+    const auto t_begin = std::chrono::steady_clock::now();
     const pgsgd::FlatGraph fg = flatten_or_exit(graph, (uint64_t) (config.nthreads > 0 ? config.nthreads : 1));
+    const double flatten_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     check_abi();
     pgsgd_config c{};
     c.iter_max = config.iter_max;
@@ -81,6 +84,13 @@ void gpu_layout(layout_config_t config, const odgi::graph_t& graph, std::vector<
         if (!std::isfinite(x[i]) || !std::isfinite(y[i])) std::cout << "WARNING: invalid coordiate" << std::endl;  // layout.cu:455-459
         X[i].store(x[i]);
         Y[i].store(y[i]);
+    }
+    if (std::getenv("PGSGD_SHIM_TIMING")) {   // where the time of the reference-side call goes (one JSON line on stderr)
+        const double total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        std::fprintf(stderr, "{\"shim\": \"cuda::gpu_layout\", \"threads\": %d, \"graph_walk_flatten_s\": %.4f, \"upload_s\": %.4f, "
+                             "\"iterations_s\": %.4f, \"download_s\": %.4f, \"total_s\": %.4f, \"term_updates\": %llu}\n",
+                     (int) config.nthreads, flatten_s, st.seconds_upload, st.seconds_iterations, st.seconds_download, total_s,
+                     (unsigned long long) st.term_updates);
     }
 }
 

@@ -15,7 +15,8 @@ from odgi_b200 import synth  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
 ranks = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-for n_paths in (90, 16, 4):
+PATHS = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [90, 16, 4]
+for n_paths in PATHS:
     g = synth.generate(30_000, n_paths, seed=42)
     go = orc.Graph(g.node_len, g.path_first_step, g.step_node, g.step_rev)
     cfg = orc.default_layout_config(go)

@@ -131,11 +131,12 @@ def _stress_band(golden_dir, key):
 
 
 def _assert_in_band(values, band):
-    """mean over seeds within max(1 %, 2 sigma_ref) of the reference mean; every single run within 2.5 %"""
+    """|stress_gpu - mean(stress_cpu)| <= max(1 % of the reference mean, 2 sigma_cpu), applied to the mean over
+    the seeds.  A SINGLE run drawn from the reference's own distribution leaves a 2-sigma band one time in ~16 (the reference
+    mean itself comes from six runs), so the per-run gate is max(1 %, 3 sigma): the same bound, one sigma wider."""
     mean, sd = band["mean"], band["sd"]
-    tol = max(0.01 * mean, 2 * sd)
-    assert abs(np.mean(values) - mean) <= tol, (values, mean, sd)
-    assert all(abs(v - mean) <= 0.025 * mean + 2 * sd for v in values), (values, mean, sd)
+    assert abs(np.mean(values) - mean) <= max(0.01 * mean, 2 * sd), (values, mean, sd)
+    assert all(abs(v - mean) <= max(0.01 * mean, 3 * sd) for v in values), (values, mean, sd)
 
 
 @pytest.mark.parametrize("name", ["DRB1-3123", "chr6.C4"])
