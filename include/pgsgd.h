@@ -110,6 +110,12 @@ typedef struct pgsgd_config {
 #define PGSGD_FLAG_HALF_TILE   64u  /* pipelined tile kernel: 1024-step tiles (with TMA_STAGING: two 1024-step buffers = the footprint of
                                        one 2048-step buffer) */
 #define PGSGD_FLAG_BIG_TILE   128u  /* pipelined tile kernel: 4096-step tiles (experiments: occupancy vs in-tile partner rate) */
+#define PGSGD_FLAG_SWEEP_TILES 256u /* pipelined tile kernel: every pass walks the tiles in path order from a random offset (tile = (i + add) mod
+                                       n_tiles) instead of a random bijection: the CTAs resident at any time then work on ONE contiguous window of the
+                                       step array, whose records and coordinates stay in L2 — partners a megabase away are L2 hits, not random DRAM
+                                       sectors (the measured wall: ~69 G DRAM sectors/s) */
+#define PGSGD_FLAG_L2_WINDOW  512u /* coordinates pinned in L2 by a persisting access-policy window on the engine's stream instead of
+                                       per-instruction evict_last hints */
 #define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
 
 typedef struct pgsgd_stats {

@@ -6,6 +6,7 @@
 // that cuda::gpu_layout does for itself (layout.cu:325-410).
 #include "../../include/pgsgd.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -660,6 +661,23 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         if (rc) return rc;
     }
 
+    if ((cfg->flags & PGSGD_FLAG_L2_WINDOW) && tile_mode && tile2 && !peer) {
+        // pin the coordinate array in L2: persisting carve-out + access-policy window on this stream (reset after the loop)
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, e->device));
+        const size_t bytes = dims == 2 ? 4 * e->N * sizeof(float) : e->N * sizeof(double);
+        const size_t carve = std::min<size_t>((size_t) prop.persistingL2CacheMaxSize, bytes);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = dims == 2 ? (void*) e->d_xy : (void*) e->d_x1d;
+        attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t) prop.accessPolicyMaxWindowSize);
+        attr.accessPolicyWindow.hitRatio = bytes ? std::min(1.0f, (float) carve / (float) bytes) : 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+    }
     CU(cudaEventRecord(e->ev0, e->stream));
     uint64_t iter = iter_begin;
     for (; iter < n_iters; ++iter) {
@@ -680,7 +698,7 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
             for (int k = 0; k < 16; ++k) {
                 uint64_t mul;
                 do { mul = splitmix64_next(sm) % nt; } while (nt > 1 && (mul == 0 || std::gcd(mul, nt) != 1));
-                if (nt == 1) mul = 1;
+                if (nt == 1 || (tile2 && (cfg->flags & PGSGD_FLAG_SWEEP_TILES))) mul = 1;   // sweep: path order from a random offset
                 p.perm_mul[k] = t2.perm_mul[k] = mul;
                 p.perm_add[k] = t2.perm_add[k] = splitmix64_next(sm) % nt;
             }
@@ -742,6 +760,14 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     }
     CU(cudaEventRecord(e->ev1, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    if ((cfg->flags & PGSGD_FLAG_L2_WINDOW) && tile_mode && tile2 && !peer) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+    }
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     unsigned long long counted = 0;

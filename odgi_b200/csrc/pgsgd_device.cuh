@@ -288,6 +288,12 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     return p;
 }
 
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 __device__ __forceinline__ uint4 load_step(const StepRec* steps, uint64_t i, uint64_t policy) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"

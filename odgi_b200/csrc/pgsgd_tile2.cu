@@ -162,8 +162,10 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
     g.s1 = p.rng[p.rng_stride + tid];
     g.s2 = p.rng[2 * p.rng_stride + tid];
     g.s3 = p.rng[3 * p.rng_stride + tid];
-    const uint64_t pol_stream = l2_policy_evict_first();
-    const uint64_t pol_keep = l2_policy_evict_last();
+    // step records: evict_first (a stream with no reuse) — except in sweep order, where the resident CTAs share one window of
+    // the step array and a record fetched by one CTA is the far partner of its neighbours: normal priority keeps it around
+    const uint64_t pol_stream = (p.flags & 256u) ? l2_policy_evict_normal() : l2_policy_evict_first();
+    const uint64_t pol_keep = (p.flags & 512u) ? l2_policy_evict_normal() : l2_policy_evict_last();
     const bool atomic_add = (p.flags & 5u) == 0;
     const bool st_mode = (p.flags & 4u) != 0;
     uint32_t done = 0;
