@@ -69,10 +69,18 @@ __device__ __forceinline__ float pow_hack_frac(float a, float frac) {
     const int t = 1072632447 + __float2int_rd(frac * (float) (hi - 1072632447));
     return __int_as_float((t - 0x38000000) << 3);
 }
+// a^e for the integer part of the Zipf exponent alpha = 1 / (1 - theta) (99 for the reference's theta = 0.99: 1 - 0.99 is
+// not exact in binary).  e < 128: seven squarings with the multiplies selected by the (launch-uniform) bits of e, unrolled —
+// no loop, no divergence; larger exponents take the generic loop.
 __device__ __forceinline__ float pow_int(float a, int e) {
-    if (e == 100) {  // theta = 0.99 (the reference default): a^100 = a^64 * a^32 * a^4
-        const float a2 = a * a, a4 = a2 * a2, a8 = a4 * a4, a16 = a8 * a8, a32 = a16 * a16, a64 = a32 * a32;
-        return a64 * a32 * a4;
+    if (e < 128) {
+        float r = (e & 1) ? a : 1.0f;
+#pragma unroll
+        for (int k = 1; k < 7; ++k) {
+            a *= a;
+            if ((e >> k) & 1) r *= a;
+        }
+        return r;
     }
     float r = 1.0f;
     while (e) {
