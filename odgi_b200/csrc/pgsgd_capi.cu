@@ -692,15 +692,15 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         p.sp.zipf = make_zipf_const(theta_zipf);
         p.sp.zipf_f = make_zipf_const_f(p.sp.zipf);
         if (tile_mode) {
-            // one bijection of the tile index per pass: i -> (i * mul + add) mod n_tiles with gcd(mul, n_tiles) = 1
+            // one keyed pseudo-random permutation of the tile index per pass (tile_perm, pgsgd_device.cuh); sweep order
+            // (experiments): path order from a random offset
             const uint64_t nt = tile2 ? t2.n_tiles : p.n_tiles;
             uint64_t sm = cfg->seed ^ (0x9e3779b97f4a7c15ULL * (iter + 1));
+            const bool sweep = tile2 && (cfg->flags & PGSGD_FLAG_SWEEP_TILES);
             for (int k = 0; k < 16; ++k) {
-                uint64_t mul;
-                do { mul = splitmix64_next(sm) % nt; } while (nt > 1 && (mul == 0 || std::gcd(mul, nt) != 1));
-                if (nt == 1 || (tile2 && (cfg->flags & PGSGD_FLAG_SWEEP_TILES))) mul = 1;   // sweep: path order from a random offset
-                p.perm_mul[k] = t2.perm_mul[k] = mul;
-                p.perm_add[k] = t2.perm_add[k] = splitmix64_next(sm) % nt;
+                const uint64_t key = splitmix64_next(sm);
+                p.perm_mul[k] = t2.perm_mul[k] = sweep ? 0 : 1;
+                p.perm_add[k] = t2.perm_add[k] = sweep ? key % nt : key;
             }
             if (tile2) {
                 t2.eta = p.eta;

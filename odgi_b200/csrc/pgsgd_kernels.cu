@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256, BATCH >= 4 ? 2 : (BATCH == 2 ? 3 : TILE_B
     // visits of this rank: v = visit_rank + k * visit_nranks; CTA c takes k = c, c + gridDim.x, ...
     auto tile_base_of = [&](uint64_t v) -> uint64_t {
         const uint64_t pass = v / p.n_tiles, i = v - pass * p.n_tiles;
-        uint64_t t_idx = (i * p.perm_mul[pass & 15] + p.perm_add[pass & 15]) % p.n_tiles;
+        uint64_t t_idx = p.perm_mul[pass & 15] ? tile_perm(i, p.n_tiles, p.perm_add[pass & 15]) : (i + p.perm_add[pass & 15]) % p.n_tiles;
         if (p.tile_list) t_idx = p.tile_list[t_idx];  // peer mode: the k-th tile this rank owns
         return t_idx * (uint64_t) TILE_STEPS;
     };

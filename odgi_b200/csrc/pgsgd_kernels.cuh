@@ -28,8 +28,8 @@ struct IterParams {
     uint64_t n_visits;          // tile visits of this launch (all ranks); visit v is handled by CTA v % gridDim of rank v % n_ranks
     uint64_t n_tiles;           // ceil(S / TILE_STEPS)
     uint64_t last_visit_terms;  // terms of the final visit (<= TILE_STEPS)
-    uint64_t perm_mul[16];      // per pass: tile = (i * perm_mul[pass] + perm_add[pass]) % n_tiles, a bijection on [0, n_tiles)
-    uint64_t perm_add[16];
+    uint64_t perm_mul[16];      // per pass: 1 = tile = tile_perm(i, n_tiles, key = perm_add[pass]) (keyed pseudo-random permutation);
+    uint64_t perm_add[16];      //           0 = sweep order, tile = (i + perm_add[pass]) % n_tiles
     uint32_t visit_rank, visit_nranks;  // this rank handles visits v with v % visit_nranks == visit_rank
     // ---- multi-GPU peer mode: the coordinate array is PARTITIONED by node range over the GPUs of the box and every
     //      GPU reads / reds the owner's slice directly through NVLink peer memory (no replica, no all-reduce) ----

@@ -117,7 +117,7 @@ struct VisitInfo {
 template <typename FirstPtr>
 __device__ __forceinline__ void make_visit(const Tile2Params& p, FirstPtr first, uint64_t v, uint32_t tile_steps, VisitInfo* out) {
     const uint64_t pass = v / p.n_tiles, i = v - pass * p.n_tiles;
-    uint64_t t_idx = (i * p.perm_mul[pass & 15] + p.perm_add[pass & 15]) % p.n_tiles;
+    uint64_t t_idx = p.perm_mul[pass & 15] ? tile_perm(i, p.n_tiles, p.perm_add[pass & 15]) : (i + p.perm_add[pass & 15]) % p.n_tiles;
     if (p.tile_list) t_idx = p.tile_list[t_idx];   // peer phases: the k-th tile this rank owns
     const uint64_t base = t_idx * (uint64_t) tile_steps;
     const uint64_t end = base + tile_steps <= p.step_count ? base + tile_steps : p.step_count;
