@@ -248,6 +248,16 @@ int pgsgd_engine_local_stress(pgsgd_engine* e, int dims, uint64_t n_pairs, uint6
 int pgsgd_engine_order_1d_components(pgsgd_engine* e, const uint32_t* node_component, uint64_t* order_out);
 int pgsgd_engine_order_1d(pgsgd_engine* e, uint64_t* order_out);   /* == node_component NULL */
 
+/* The step right after the 2D hot path, on the device: odgi's binary layout container (`.lay`,
+ * algorithms::layout::Layout::serialize, src/algorithms/layout.cpp:43-61: min_value + sdsl::enc_vector<elias_delta,128> over the
+ * bit patterns of coordinate - min_value) of the resident 2D coordinates, after the per-component stacking `odgi layout` applies
+ * first (src/subcommand/layout_main.cpp:402-435: bounding box per weak component, 1000-unit border).
+ * node_component: [N] id of every node's weak component, numbered as the caller's weakly_connected_component_vectors returns
+ * them, n_components of them — or NULL to serialise the coordinates as they are.  The file is byte-identical to what the host
+ * writer (odgi_b200/host/lay_format.hpp, pinned on files written by the reference) produces from the downloaded coordinates.
+ * Call with buf == NULL to learn the size (*n_bytes), then with a buffer of at least that many bytes. */
+int pgsgd_engine_encode_lay(pgsgd_engine* e, const uint32_t* node_component, uint32_t n_components, uint8_t* buf, uint64_t cap, uint64_t* n_bytes);
+
 /* Sorting goodness of the graph as `order` would sort it: the two metrics of `odgi stats -l [-g] -s [-d]`
  * (src/subcommand/stats_main.cpp:399-800, 1D branch), evaluated on the device over every consecutive step pair of every path.
  * order: [N] node ranks in sorted order (e.g. from pgsgd_engine_order_1d) or NULL for the graph as it is.

@@ -62,7 +62,7 @@ EXPORTED_SYMBOLS = [
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
     "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
-    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_resolved_multi_mode", "pgsgd_engine_set_shard", "pgsgd_engine_path_stress", "pgsgd_engine_local_stress", "pgsgd_engine_order_1d", "pgsgd_engine_order_1d_components", "pgsgd_engine_sort_goodness", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
+    "pgsgd_engine_attach_comm", "pgsgd_engine_set_multi_mode", "pgsgd_engine_resolved_multi_mode", "pgsgd_engine_set_shard", "pgsgd_engine_path_stress", "pgsgd_engine_local_stress", "pgsgd_engine_order_1d", "pgsgd_engine_order_1d_components", "pgsgd_engine_sort_goodness", "pgsgd_engine_encode_lay", "pgsgd_engine_sample_terms", "pgsgd_engine_set_trace", "pgsgd_engine_get_trace", "pgsgd_schedule", "pgsgd_zetas",
 ]
 
 class GoodnessC(C.Structure):
@@ -137,6 +137,7 @@ def lib():
         L.pgsgd_engine_order_1d.argtypes = [vp, vp]
         L.pgsgd_engine_order_1d_components.argtypes = [vp, vp, vp]
         L.pgsgd_engine_sort_goodness.argtypes = [vp, vp, C.c_uint32, vp]
+        L.pgsgd_engine_encode_lay.argtypes = [vp, vp, C.c_uint32, vp, u64, vp]
         L.pgsgd_engine_local_stress.argtypes = [vp, i32, u64, u64, vp]
         L.pgsgd_engine_sample_terms.argtypes = [vp, C.POINTER(ConfigC), i32, i32, dbl, u64, u64] + [vp] * 11
         L.pgsgd_engine_set_trace.argtypes = [vp, u64]
@@ -403,6 +404,17 @@ class Engine:
         o = None if order is None else np.ascontiguousarray(order, dtype=np.uint64)
         _check(lib().pgsgd_engine_sort_goodness(self._h, _ptr(o), (1 if gap_links else 0) | (2 if orientation else 0), C.byref(out)))
         return {f: getattr(out, f) for f, _ in GoodnessC._fields_}
+
+    def encode_lay(self, component: Optional[np.ndarray] = None) -> bytes:
+        """the resident 2D layout as odgi's .lay file, encoded on the device (pgsgd_engine_encode_lay); component: [N] weak
+        component id per node (the per-component stacking of `odgi layout` is applied first) or None"""
+        comp = None if component is None else np.ascontiguousarray(component, dtype=np.uint32)
+        k = 0 if comp is None else int(comp.max()) + 1
+        n = C.c_uint64(0)
+        _check(lib().pgsgd_engine_encode_lay(self._h, _ptr(comp), k, None, 0, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        _check(lib().pgsgd_engine_encode_lay(self._h, _ptr(comp), k, _ptr(buf), n.value, C.byref(n)))
+        return buf.tobytes()
 
     def resolved_multi_mode(self) -> int:
         """MULTI_* in effect (what MULTI_AUTO resolved to once the coordinates were uploaded)"""

@@ -1376,6 +1376,71 @@ int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode) {
     return PGSGD_OK;
 }
 
+int pgsgd_engine_encode_lay(pgsgd_engine* e, const uint32_t* node_component, uint32_t n_components, uint8_t* buf, uint64_t cap, uint64_t* n_bytes) {
+    if (!e || !n_bytes) return fail(PGSGD_ERR_ARG, "encode_lay: NULL argument");
+    if (!e->have_2d) return fail(PGSGD_ERR_STATE, "no 2D coordinates on the device");
+    if (node_component && n_components == 0) return fail(PGSGD_ERR_ARG, "encode_lay: n_components is 0");
+    CU(cudaSetDevice(e->device));
+    if (e->coords_in_slices && e->peer_ready_2d) { int rc = peer_gather(e, 2); if (rc) return rc; }
+    uint32_t* d_comp = nullptr;
+    double *d_xo = nullptr, *d_yo = nullptr;
+    auto cleanup = [&]() { cudaFree(d_comp); cudaFree(d_xo); cudaFree(d_yo); };
+    if (node_component) {
+        for (uint64_t r = 0; r < e->N; ++r)
+            if (node_component[r] >= n_components) return fail(PGSGD_ERR_ARG, "encode_lay: node %llu has component %u >= n_components", (unsigned long long) r, node_component[r]);
+        cudaError_t ce = cudaMalloc(&d_comp, e->N * sizeof(uint32_t));
+        if (ce == cudaSuccess) ce = cudaMemcpy(d_comp, node_component, e->N * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        // bounding box per component on the device, the stacking itself (K values, sequential) on the host: layout_main.cpp:406-420
+        std::vector<double> stats(3 * (size_t) n_components), xo(n_components), yo(n_components);
+        if (ce == cudaSuccess) ce = launch_component_ranges(e->d_xy, d_comp, e->N, n_components, stats.data(), e->stream);
+        const double border = 1000.0;
+        double curr_y_offset = border;
+        for (uint32_t k = 0; k < n_components; ++k) {
+            const double min_x = stats[3 * k], min_y = stats[3 * k + 1], max_y = stats[3 * k + 2];
+            xo[k] = min_x - border;
+            yo[k] = curr_y_offset - min_y;
+            curr_y_offset += (max_y - min_y) + border;
+        }
+        if (ce == cudaSuccess) ce = cudaMalloc(&d_xo, n_components * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc(&d_yo, n_components * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMemcpy(d_xo, xo.data(), n_components * sizeof(double), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(d_yo, yo.data(), n_components * sizeof(double), cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) { cleanup(); return fail(PGSGD_ERR_CUDA, "encode_lay: %s", cudaGetErrorString(ce)); }
+    }
+    LayEncoded enc;
+    cudaError_t err = launch_encode_lay(e->d_xy, e->N, d_comp, d_xo, d_yo, &enc, e->stream);
+    cleanup();
+    if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "encode_lay: %s", cudaGetErrorString(err));
+    const uint64_t zw = (enc.z_bits + 63) / 64, sw = (enc.sp_bits + 63) / 64;
+    const uint64_t total = 8 + 8 + (8 + 1 + zw * 8) + (8 + 1 + sw * 8);
+    *n_bytes = total;
+    int rc = PGSGD_OK;
+    if (buf) {
+        if (cap < total) rc = fail(PGSGD_ERR_ARG, "encode_lay: buffer of %llu bytes, need %llu", (unsigned long long) cap, (unsigned long long) total);
+        else {
+            uint8_t* q = buf;
+            memcpy(q, &enc.min_value, 8); q += 8;
+            memcpy(q, &enc.n_vals, 8); q += 8;
+            memcpy(q, &enc.z_bits, 8); q += 8;
+            *q++ = 1;
+            err = cudaMemcpy(q, enc.d_z, zw * 8, cudaMemcpyDeviceToHost); q += zw * 8;
+            memcpy(q, &enc.sp_bits, 8); q += 8;
+            *q++ = (uint8_t) enc.width;
+            if (err == cudaSuccess) err = cudaMemcpy(q, enc.d_sp, sw * 8, cudaMemcpyDeviceToHost);
+            for (int k = 0; k < 2; ++k)   // the closing sample (0, |z| + 1)
+                if (enc.tail_bits[k] && enc.tail_word + k < sw) {
+                    unsigned long long w;
+                    memcpy(&w, q + (enc.tail_word + k) * 8, 8);
+                    w |= enc.tail_bits[k];
+                    memcpy(q + (enc.tail_word + k) * 8, &w, 8);
+                }
+            if (err != cudaSuccess) rc = fail(PGSGD_ERR_CUDA, "encode_lay: %s", cudaGetErrorString(err));
+        }
+    }
+    cudaFree(enc.d_z); cudaFree(enc.d_sp);
+    return rc;
+}
+
 int pgsgd_engine_resolved_multi_mode(const pgsgd_engine* e) { return e ? (e->comm ? e->mode : PGSGD_MULTI_ALLREDUCE) : -1; }
 
 int pgsgd_engine_set_shard(pgsgd_engine* e, uint64_t global_step_count) {

@@ -135,6 +135,22 @@ cudaError_t launch_order_1d(const double* x, const uint32_t* d_component, uint64
 cudaError_t launch_goodness(const StepRec* steps, const uint64_t* first, const uint64_t* h_first, uint32_t P, uint64_t S, uint64_t N,
                             const uint32_t* d_node_len, const uint64_t* d_order, uint32_t flags, unsigned long long* h_acc9, cudaStream_t stream);
 
+// ---- `.lay` on the device (pgsgd_lay.cu) ----
+struct LayEncoded {
+    double min_value;
+    uint64_t n_vals, z_bits, sp_bits;
+    unsigned width;
+    unsigned long long* d_z;      // Elias-delta code words (device; the caller frees)
+    unsigned long long* d_sp;     // sample table words (device; the caller frees) — OR tail_bits into words tail_word, tail_word + 1
+    uint64_t tail_word;
+    unsigned long long tail_bits[2];
+};
+// per-component {min_x, min_y, max_y} of the resident 2D coordinates (h_stats: [3K] doubles)
+cudaError_t launch_component_ranges(const float* xy, const uint32_t* d_comp, uint64_t n_nodes, uint32_t K, double* h_stats, cudaStream_t stream);
+// Layout(X, Y).serialize of the resident coordinates (as doubles, moved by the per-component offsets when d_comp != null)
+cudaError_t launch_encode_lay(const float* xy, uint64_t n_nodes, const uint32_t* d_comp, const double* d_x_off, const double* d_y_off,
+                              LayEncoded* out, cudaStream_t stream);
+
 // coordinate format conversion: reference X/Y (double, index 2*node+end) <-> device float4-per-node
 cudaError_t launch_xy_from_XY(float* xy, const double* X, const double* Y, uint64_t n_nodes, cudaStream_t stream);
 cudaError_t launch_XY_from_xy(double* X, double* Y, const float* xy, uint64_t n_nodes, cudaStream_t stream);
