@@ -23,7 +23,7 @@ extern "C" {
 
 /* Bumped whenever a struct below changes size or meaning.  Callers compare PGSGD_VERSION (what they were compiled against)
  * with pgsgd_version() (what they loaded) before the first call: a stale binary would otherwise pass short structs. */
-#define PGSGD_VERSION 102 /* 0.1.2 */
+#define PGSGD_VERSION 103 /* 0.1.3 */
 
 typedef enum pgsgd_status {
     PGSGD_OK = 0,
@@ -90,8 +90,10 @@ typedef struct pgsgd_config {
  *          coalesced 128-bit loads and uses each of its steps once as a first step; tile visits follow per-pass
  *          bijections, so over an iteration every step is a first step exactly floor(U/S) (+1) times — the same
  *          uniform marginal with the first pick's sampling noise removed.  ~1 random HBM read per term or fewer.
- *  AUTO  : TILE for graphs whose step records exceed the L2 (>= 2^22 steps) and that are large enough for the
- *          in-flight cap, else STREAM. */
+ *  AUTO  : TILE for graphs whose step records exceed the L2 (>= 2^22 steps), that are at least PGSGD_AUTO_TILE_MIN_DEPTH steps
+ *          deep per node on average (haplotype depth) and large enough for the in-flight cap, else STREAM.  (On a 6-haplotype
+ *          graph tile sampling left the reference's far-stress band, from 12 haplotypes on it does not: DESIGN.md 5.) */
+#define PGSGD_AUTO_TILE_MIN_DEPTH 8ull
 #define PGSGD_SAMPLING_AUTO   0u
 #define PGSGD_SAMPLING_STREAM 1u
 #define PGSGD_SAMPLING_TILE   2u
@@ -129,6 +131,7 @@ typedef struct pgsgd_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t flags_used;                   /* PGSGD_FLAG_* actually in effect (the engine switches to EXCH_WRITE by itself
                                               when a hub node would see too many concurrent red.adds) */
+    uint64_t sampling_used;                /* PGSGD_SAMPLING_STREAM or _TILE: what AUTO resolved to (last phase run) */
 } pgsgd_stats;
 
 typedef struct pgsgd_engine pgsgd_engine;   /* opaque: device-resident graph + coordinates + RNG streams */

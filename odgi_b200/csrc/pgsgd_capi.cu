@@ -455,7 +455,12 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     // ---- sampling mode and launch shape ----
     const int block = 256;
     const size_t smem_first = (e->P + 1) * sizeof(uint64_t);
-    bool tile_mode = cfg->sampling == PGSGD_SAMPLING_TILE || (cfg->sampling == PGSGD_SAMPLING_AUTO && e->S >= (1ull << 22));
+    // AUTO: tile sampling for graphs whose step records exceed the L2 (>= 2^22 steps) AND that are at least 8 steps deep per
+    // node on average.  On a 6-haplotype, 3.6e6-node graph (5 steps per node) tile sampling ends 10-35 % above the reference's
+    // far-stress band with a heavy tail over seeds while stream sampling sits inside it; from 10 steps per node on the two
+    // agree (profiles/r02_tile_vs_stream_depth.log).  Shallow graphs therefore keep the reference-exact stream sampler.
+    bool tile_mode = cfg->sampling == PGSGD_SAMPLING_TILE ||
+                     (cfg->sampling == PGSGD_SAMPLING_AUTO && e->S >= (1ull << 22) && e->S >= PGSGD_AUTO_TILE_MIN_DEPTH * e->N);
     int batch = cfg->batch ? (int) cfg->batch : 1;  // 64 registers, 4 CTAs/SM: occupancy beats per-thread batching (profiles/)
     bool smem_paths = false;
     size_t smem = 0;
@@ -583,6 +588,7 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         }
     }
     st.flags_used |= p.flags;
+    st.sampling_used = tile_mode ? PGSGD_SAMPLING_TILE : PGSGD_SAMPLING_STREAM;
     p.smem_paths = smem_paths ? 1u : 0u;
     p.trace = e->d_trace;
     p.trace_count = e->d_trace_count;
@@ -830,6 +836,7 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
             st.kernel_launches += b.kernel_launches;
             st.last_delta_max = b.last_delta_max;
             st.flags_used |= b.flags_used;
+            st.sampling_used = b.sampling_used;
         }
         st.seconds_iterations = ms * 1e-3;
         *stats = st;
