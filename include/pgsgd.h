@@ -163,6 +163,15 @@ int pgsgd_sort_1d_multi(const pgsgd_graph_view* g, const pgsgd_config* cfg, int 
 
 /* ---- engine API (graph stays resident in HBM; used by the one-shot calls, by bench.py and by multi-GPU runs) ---- */
 int  pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** out);
+/* The same engine straight from GFA text: the caller finds the `P` lines and hands over the byte range of each
+ * line's step list ("12+,13-,..." — text[field_begin[p] .. field_end[p]), no tab, no newline), plus the node lengths from the `S`
+ * lines; the step lists are uploaded as text and parsed ON THE DEVICE (one thread per step), then flattened there as above.
+ * No per-step host work: replaces the path walk of cuda::gpu_layout (src/cuda/layout.cu:371-410) and this repo's own host
+ * parser (odgi_b200/host/gfa_lite.hpp).  Node ids must be the numbers 1..node_count (PGSGD_ERR_UNOPT otherwise). */
+int  pgsgd_engine_create_from_gfa_paths(const uint32_t* node_len, uint64_t node_count, const char* text, const uint64_t* field_begin,
+                                        const uint64_t* field_end, uint64_t path_count, int device, pgsgd_engine** out);
+/* what the default schedule parameters are derived from (layout_main.cpp:251-266, sort_main.cpp:355-412); any pointer may be NULL */
+int  pgsgd_engine_graph_stats(const pgsgd_engine* e, uint64_t* step_count, uint64_t* max_path_steps, uint64_t* max_path_bp, uint64_t* max_node_depth);
 void pgsgd_engine_destroy(pgsgd_engine* e);
 int  pgsgd_engine_device(const pgsgd_engine* e);
 uint64_t pgsgd_engine_device_bytes(const pgsgd_engine* e);

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgsgd_b200.so")
-SOURCES = ["pgsgd_kernels.cu", "pgsgd_tile2.cu", "pgsgd_lay.cu", "pgsgd_capi.cu"]
+SOURCES = ["pgsgd_kernels.cu", "pgsgd_tile2.cu", "pgsgd_lay.cu", "pgsgd_gfa.cu", "pgsgd_capi.cu"]
 HEADERS = ["pgsgd_device.cuh", "pgsgd_kernels.cuh"]
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

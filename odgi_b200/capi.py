@@ -10,6 +10,8 @@ import os
 from dataclasses import dataclass, field
 from typing import Optional
 
+import types
+
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -59,7 +61,7 @@ class StatsC(C.Structure):
 EXPORTED_SYMBOLS = [
     "pgsgd_last_error", "pgsgd_version", "pgsgd_device_count", "pgsgd_layout_2d", "pgsgd_sort_1d", "pgsgd_layout_2d_multi",
     "pgsgd_sort_1d_multi",
-    "pgsgd_engine_create", "pgsgd_engine_destroy", "pgsgd_engine_device", "pgsgd_engine_device_bytes",
+    "pgsgd_engine_create", "pgsgd_engine_create_from_gfa_paths", "pgsgd_engine_graph_stats", "pgsgd_engine_destroy", "pgsgd_engine_device", "pgsgd_engine_device_bytes",
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
     "pgsgd_engine_get_coords_2d_f32", "pgsgd_engine_set_coords_1d", "pgsgd_engine_get_coords_1d",
     "pgsgd_engine_set_frozen_1d", "pgsgd_engine_run_2d", "pgsgd_engine_run_1d", "pgsgd_engine_run_range", "pgsgd_comm_unique_id",
@@ -116,6 +118,8 @@ def lib():
         L.pgsgd_layout_2d_multi.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), i32, i32, vp, vp, C.POINTER(StatsC)]
         L.pgsgd_sort_1d_multi.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), i32, i32, vp, i32, vp, C.POINTER(StatsC)]
         L.pgsgd_engine_create.argtypes = [C.POINTER(GraphView), i32, C.POINTER(vp)]
+        L.pgsgd_engine_create_from_gfa_paths.argtypes = [vp, u64, vp, vp, vp, u64, i32, C.POINTER(vp)]
+        L.pgsgd_engine_graph_stats.argtypes = [vp, vp, vp, vp, vp]
         L.pgsgd_engine_destroy.argtypes = [vp]
         L.pgsgd_engine_destroy.restype = None
         L.pgsgd_engine_device.argtypes = [vp]
@@ -281,6 +285,55 @@ def zetas(cfg: Config) -> np.ndarray:
     return z
 
 
+def scan_gfa(path: str):
+    """The host side of the device GFA ingest: line boundaries, node lengths from the S lines (ids must be 1..N), and the byte
+    range of every P line's step list.  No per-step work.  Returns (node_len u32[N], file bytes u8[], field_begin u64[P],
+    field_end u64[P], path names)."""
+    data = np.fromfile(path, dtype=np.uint8)
+    nl = np.flatnonzero(data == 10)
+    starts = np.concatenate(([0], nl + 1))
+    ends = np.concatenate((nl, [data.size]))
+    keep = starts < ends
+    starts, ends = starts[keep], ends[keep]
+    tabs = np.flatnonzero(data == 9)
+    first = data[starts]
+    # S lines: "S <id> <sequence> ..." -> length of field 3 (or LN:i: when the sequence is '*')
+    s_idx = np.flatnonzero(first == ord("S"))
+    t1 = np.searchsorted(tabs, starts[s_idx])            # index of the first tab of each S line
+    id_b, id_e = tabs[t1] + 1, tabs[t1 + 1]
+    seq_b = tabs[t1 + 1] + 1
+    t3 = np.minimum(t1 + 2, tabs.size - 1)
+    seq_e = np.where((t1 + 2 < tabs.size) & (tabs[t3] < ends[s_idx]), tabs[t3], ends[s_idx])
+    ids = np.array([int(bytes(data[b:e])) for b, e in zip(id_b, id_e)], dtype=np.int64) if s_idx.size < 200_000 else None
+    if ids is None:   # vectorised decimal parse for big graphs
+        ids = np.zeros(s_idx.size, dtype=np.int64)
+        width = int((id_e - id_b).max())
+        for k in range(width):
+            pos = id_e - 1 - k
+            ok = pos >= id_b
+            ids += np.where(ok, (data[np.where(ok, pos, 0)].astype(np.int64) - 48) * 10 ** k, 0)
+    n = int(ids.max()) if ids.size else 0
+    if ids.size != n or np.unique(ids).size != n or ids.min() != 1:
+        raise PgsgdError(-1, "node ids are not exactly 1..N")
+    node_len = np.zeros(n, dtype=np.uint32)
+    lens = (seq_e - seq_b).astype(np.uint32)
+    star = (lens == 1) & (data[seq_b] == ord("*"))
+    for j in np.flatnonzero(star):   # sequence omitted: LN:i: tag
+        line = bytes(data[starts[s_idx[j]]:ends[s_idx[j]]])
+        k = line.find(b"LN:i:")
+        lens[j] = int(line[k + 5:].split(b"\t")[0]) if k >= 0 else 0
+    node_len[ids - 1] = lens
+    # P lines: "P <name> <steps> ..." -> byte range of field 3
+    p_idx = np.flatnonzero(first == ord("P"))
+    t1 = np.searchsorted(tabs, starts[p_idx])
+    fb = tabs[t1 + 1] + 1
+    t3 = np.minimum(t1 + 2, tabs.size - 1)
+    fe = np.where((t1 + 2 < tabs.size) & (tabs[t3] < ends[p_idx]), tabs[t3], ends[p_idx])
+    fe = np.where((fe > fb) & (data[np.maximum(fe, 1) - 1] == 13), fe - 1, fe)   # CRLF files
+    names = [bytes(data[tabs[a] + 1:tabs[a + 1]]).decode() for a in t1]
+    return node_len, data, fb.astype(np.uint64), fe.astype(np.uint64), names
+
+
 class Engine:
     """Device-resident graph + coordinates (pgsgd_engine)."""
 
@@ -289,6 +342,24 @@ class Engine:
         self._h = C.c_void_p()
         gv = g.view()
         _check(lib().pgsgd_engine_create(C.byref(gv), device, C.byref(self._h)))
+
+    @classmethod
+    def from_gfa(cls, path: str, device: int = 0) -> "Engine":
+        """Engine straight from a GFA file: the host only finds the lines (scan_gfa); the P-line step lists are parsed on the
+        device (pgsgd_engine_create_from_gfa_paths).  self.g then carries only N, P, S and the node lengths."""
+        node_len, data, fb, fe, names = scan_gfa(path)
+        e = cls.__new__(cls)
+        e._h = C.c_void_p()
+        _check(lib().pgsgd_engine_create_from_gfa_paths(_ptr(node_len), len(node_len), _ptr(data), _ptr(fb), _ptr(fe), len(fb), device, C.byref(e._h)))
+        st = e.graph_stats()
+        e.g = types.SimpleNamespace(N=len(node_len), P=len(fb), S=st["step_count"], node_len=node_len, path_names=names,
+                                    max_path_steps=st["max_path_steps"], max_path_bp=st["max_path_bp"])
+        return e
+
+    def graph_stats(self) -> dict:
+        v = [C.c_uint64(0) for _ in range(4)]
+        _check(lib().pgsgd_engine_graph_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("step_count", "max_path_steps", "max_path_bp", "max_node_depth"), (int(x.value) for x in v)))
 
     def close(self):
         if self._h:

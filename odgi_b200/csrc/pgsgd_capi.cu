@@ -908,10 +908,13 @@ uint64_t pgsgd_zetas(const pgsgd_config* cfg, double* zetas_out, uint64_t cap) {
     return n;
 }
 
-int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** out) {
+// pre_sn / pre_sr: step arrays that are ALREADY on the device (parsed there from GFA text, pgsgd_gfa.cu); the view's host
+// step arrays are then null.  Ownership passes to this function once *pre_consumed is set.
+static int engine_create_impl(const pgsgd_graph_view* g, int device, uint32_t* pre_sn, uint8_t* pre_sr, bool* pre_consumed, pgsgd_engine** out) {
     if (!g || !out) return fail(PGSGD_ERR_ARG, "pgsgd_engine_create: NULL argument");
     *out = nullptr;
-    if (!g->node_len || !g->path_first_step || (!g->step_node && g->step_count)) return fail(PGSGD_ERR_ARG, "graph view has NULL arrays");
+    if (!g->node_len || !g->path_first_step || (!g->step_node && g->step_count && !pre_sn)) return fail(PGSGD_ERR_ARG, "graph view has NULL arrays");
+    if (pre_sn && g->step_pos) return fail(PGSGD_ERR_ARG, "device-resident step arrays come without positions");
     if (g->node_count == 0) return fail(PGSGD_ERR_ARG, "graph has no nodes");
     if (g->node_count >= (1ull << 31)) return fail(PGSGD_ERR_ARG, "more than 2^31-1 nodes are not supported by the 32-bit handle field");
     if (g->path_count >= (1ull << 32)) return fail(PGSGD_ERR_ARG, "too many paths");
@@ -965,9 +968,19 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
     {
         const uint64_t W = TILE_STEPS, nt = (g->step_count + W - 1) / W;
         e->tile_mid_node.resize(nt);
-        for (uint64_t t = 0; t < nt; ++t) {
-            const uint64_t lo = t * W, hi = lo + W < g->step_count ? lo + W : g->step_count;
-            e->tile_mid_node[t] = g->step_node[lo + (hi - lo) / 2];
+        if (pre_sn) {   // the steps never were on the host: gather the tile-centre nodes on the device
+            uint32_t* d_mid = nullptr;
+            cudaError_t ce = cudaMalloc(&d_mid, (nt ? nt : 1) * sizeof(uint32_t));
+            if (ce == cudaSuccess) ce = launch_gather_mid_nodes(pre_sn, g->step_count, W, nt, d_mid, e->stream);
+            if (ce == cudaSuccess && nt) ce = cudaMemcpyAsync(e->tile_mid_node.data(), d_mid, nt * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+            cudaFree(d_mid);
+            if (ce != cudaSuccess) return bail(fail(PGSGD_ERR_CUDA, "tile centre gather: %s", cudaGetErrorString(ce)));
+        } else {
+            for (uint64_t t = 0; t < nt; ++t) {
+                const uint64_t lo = t * W, hi = lo + W < g->step_count ? lo + W : g->step_count;
+                e->tile_mid_node[t] = g->step_node[lo + (hi - lo) / 2];
+            }
         }
     }
     // 1D default initialisation, kept on the host until asked for
@@ -1021,18 +1034,25 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
         // whole-array staging (5 B per step in, 8 B per step of scan scratch), positions by a device-wide scan
         const uint64_t n = e->S ? e->S : 1;
         int* d_bad = nullptr;
-        bool ok = cudaMalloc(&d_sn, n * 4) == cudaSuccess && cudaMalloc(&d_sp, n * 8) == cudaSuccess && cudaMalloc(&d_bad, sizeof(int)) == cudaSuccess &&
-                  (!g->step_rev || cudaMalloc(&d_sr, n) == cudaSuccess);
+        bool ok;
+        if (pre_sn) {   // parsed on the device: nothing to upload
+            d_sn = pre_sn; d_sr = pre_sr;
+            if (pre_consumed) *pre_consumed = true;
+            ok = cudaMalloc(&d_sp, n * 8) == cudaSuccess && cudaMalloc(&d_bad, sizeof(int)) == cudaSuccess;
+        } else {
+            ok = cudaMalloc(&d_sn, n * 4) == cudaSuccess && cudaMalloc(&d_sp, n * 8) == cudaSuccess && cudaMalloc(&d_bad, sizeof(int)) == cudaSuccess &&
+                 (!g->step_rev || cudaMalloc(&d_sr, n) == cudaSuccess);
+        }
         if (!ok) { cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_bad); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
         err = cudaMemsetAsync(d_bad, 0, sizeof(int), e->stream);
-        if (err == cudaSuccess) err = cudaMemcpyAsync(d_sn, g->step_node, e->S * 4, cudaMemcpyHostToDevice, e->stream);
-        if (err == cudaSuccess && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev, e->S, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess && !pre_sn) err = cudaMemcpyAsync(d_sn, g->step_node, e->S * 4, cudaMemcpyHostToDevice, e->stream);
+        if (err == cudaSuccess && !pre_sn && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev, e->S, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess) err = launch_flatten_on_device(e->d_steps, d_sn, d_sr, d_node_len, e->d_path_first, (uint32_t) e->P, (uint32_t) e->N, e->S, d_sp, d_bad, d_depth, e->stream);
         int bad = 0;
         if (err == cudaSuccess) err = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
         if (err == cudaSuccess && !bad) err = launch_tile_repeats(d_sn, e->S, d_maxdup, e->stream);
         cudaFree(d_bad);
-        e->h2d_bytes += e->S * (4 + (g->step_rev ? 1 : 0));
+        if (!pre_sn) e->h2d_bytes += e->S * (4 + (g->step_rev ? 1 : 0));
         if (err == cudaSuccess && bad) {
             cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
             return bail(fail(PGSGD_ERR_UNOPT, "a step refers to a node rank >= node_count: ids are not compacted 1..N"));
@@ -1060,6 +1080,74 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
     if ((err = cudaStreamSynchronize(e->stream)) != cudaSuccess) return cu_bail(err, "engine create sync");
     e->seconds_upload = now_s() - t0;
     *out = e;
+    return PGSGD_OK;
+}
+
+int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** out) {
+    return engine_create_impl(g, device, nullptr, nullptr, nullptr, out);
+}
+
+int pgsgd_engine_create_from_gfa_paths(const uint32_t* node_len, uint64_t node_count, const char* text, const uint64_t* field_begin,
+                                       const uint64_t* field_end, uint64_t path_count, int device, pgsgd_engine** out) {
+    if (!node_len || !out || (path_count && (!text || !field_begin || !field_end))) return fail(PGSGD_ERR_ARG, "create_from_gfa_paths: NULL argument");
+    *out = nullptr;
+    if (node_count == 0 || node_count >= (1ull << 31)) return fail(PGSGD_ERR_ARG, "create_from_gfa_paths: node_count out of range");
+    if (path_count >= (1ull << 32)) return fail(PGSGD_ERR_ARG, "too many paths");
+    int ndev = pgsgd_device_count();
+    if (ndev == 0) return fail(PGSGD_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(PGSGD_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    const double t0 = now_s();
+    // pack the step lists back to back (every list ends with an orientation character, the next one starts with a digit)
+    std::vector<uint64_t> packed_begin(path_count + 1, 0);
+    for (uint64_t p = 0; p < path_count; ++p) {
+        if (field_end[p] < field_begin[p]) return fail(PGSGD_ERR_ARG, "create_from_gfa_paths: field %llu ends before it begins", (unsigned long long) p);
+        packed_begin[p + 1] = packed_begin[p] + (field_end[p] - field_begin[p]);
+    }
+    const uint64_t n_bytes = packed_begin[path_count], n_alloc = (n_bytes + 15) / 16 * 16 + 16;
+    char* d_text = nullptr;
+    uint64_t *d_fb = nullptr, *d_pf = nullptr;
+    uint32_t* d_sn = nullptr;
+    uint8_t* d_sr = nullptr;
+    cudaStream_t stream = nullptr;
+    auto cleanup = [&]() { cudaFree(d_text); cudaFree(d_fb); cudaFree(d_pf); if (stream) cudaStreamDestroy(stream); };
+    cudaError_t ce = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_text, n_alloc);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(d_text + (n_alloc - 32 < n_alloc ? n_alloc - 32 : 0), 0, n_alloc < 32 ? n_alloc : 32, stream);
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_fb, (path_count + 1) * sizeof(uint64_t));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_pf, (path_count + 1) * sizeof(uint64_t));
+    for (uint64_t p = 0; p < path_count && ce == cudaSuccess; ++p)
+        if (field_end[p] > field_begin[p])
+            ce = cudaMemcpyAsync(d_text + packed_begin[p], text + field_begin[p], field_end[p] - field_begin[p], cudaMemcpyHostToDevice, stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_fb, packed_begin.data(), (path_count + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream);
+    uint64_t S = 0;
+    int bad = 0;
+    if (ce == cudaSuccess) ce = launch_parse_gfa_paths(d_text, n_bytes, d_fb, (uint32_t) path_count, (uint32_t) node_count, d_pf, &d_sn, &d_sr, &S, &bad, stream);
+    std::vector<uint64_t> path_first(path_count + 1, 0);
+    if (ce == cudaSuccess) ce = cudaMemcpy(path_first.data(), d_pf, (path_count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    cleanup();
+    if (ce != cudaSuccess) { cudaFree(d_sn); cudaFree(d_sr); return fail(ce == cudaErrorMemoryAllocation ? PGSGD_ERR_NOMEM : PGSGD_ERR_CUDA, "create_from_gfa_paths: %s", cudaGetErrorString(ce)); }
+    if (bad) { cudaFree(d_sn); cudaFree(d_sr); return fail(PGSGD_ERR_UNOPT, "a path step is not `<id>+` / `<id>-` with 1 <= id <= node_count: node ids must be the numbers 1..N"); }
+    pgsgd_graph_view v;
+    memset(&v, 0, sizeof(v));
+    v.node_count = node_count; v.path_count = path_count; v.step_count = S;
+    v.node_len = node_len; v.path_first_step = path_first.data();
+    bool consumed = false;
+    int rc = engine_create_impl(&v, device, d_sn, d_sr, &consumed, out);
+    if (!consumed) { cudaFree(d_sn); cudaFree(d_sr); }
+    if (rc == PGSGD_OK) {
+        (*out)->h2d_bytes += n_bytes;
+        (*out)->seconds_upload = now_s() - t0;
+    }
+    return rc;
+}
+
+int pgsgd_engine_graph_stats(const pgsgd_engine* e, uint64_t* step_count, uint64_t* max_path_steps, uint64_t* max_path_bp, uint64_t* max_node_depth) {
+    if (!e) return fail(PGSGD_ERR_ARG, "graph_stats: NULL engine");
+    if (step_count) *step_count = e->S;
+    if (max_path_steps) *max_path_steps = e->max_path_steps;
+    if (max_path_bp) *max_path_bp = e->max_path_bp;
+    if (max_node_depth) *max_node_depth = e->max_node_depth;
     return PGSGD_OK;
 }
 

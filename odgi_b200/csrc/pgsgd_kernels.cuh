@@ -135,6 +135,12 @@ cudaError_t launch_order_1d(const double* x, const uint32_t* d_component, uint64
 cudaError_t launch_goodness(const StepRec* steps, const uint64_t* first, const uint64_t* h_first, uint32_t P, uint64_t S, uint64_t N,
                             const uint32_t* d_node_len, const uint64_t* d_order, uint32_t flags, unsigned long long* h_acc9, cudaStream_t stream);
 
+// ---- GFA P-line step lists parsed on the device (pgsgd_gfa.cu) ----
+cudaError_t launch_parse_gfa_paths(const char* d_text, uint64_t n_bytes, const uint64_t* d_field_begin, uint32_t n_fields, uint32_t n_nodes,
+                                   uint64_t* d_path_first, uint32_t** d_step_node, uint8_t** d_step_rev, uint64_t* S_out, int* bad_out,
+                                   cudaStream_t stream);
+cudaError_t launch_gather_mid_nodes(const uint32_t* d_step_node, uint64_t S, uint64_t tile_steps, uint64_t n_tiles, uint32_t* d_out, cudaStream_t stream);
+
 // ---- `.lay` on the device (pgsgd_lay.cu) ----
 struct LayEncoded {
     double min_value;
