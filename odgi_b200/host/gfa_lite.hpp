@@ -92,4 +92,110 @@ inline FlatGraph read_gfa_flat(const std::string& path) {
     return fg;
 }
 
+
+// ---- the host half of the DEVICE ingest (pgsgd_engine_create_from_gfa_paths) ------------------------------------------
+// One pass over the mapped file with memchr: node lengths from the S lines, the link endpoints from the L lines (weak
+// components for the layout stacking) and, for every P line, only the BYTE RANGE of its step list — the steps themselves
+// (the bulk of a pangenome GFA) are parsed on the GPU.
+struct GfaIndex {
+    std::vector<uint32_t> node_len;
+    std::vector<std::string> path_names;
+    std::vector<uint64_t> field_begin, field_end;          // step list of path p: text[field_begin[p], field_end[p])
+    std::vector<std::pair<uint32_t, uint32_t>> links;      // node ranks of every L line
+    const char* text = nullptr;
+    size_t bytes = 0;
+    int fd = -1;
+    GfaIndex() = default;
+    GfaIndex(const GfaIndex&) = delete;
+    GfaIndex& operator=(const GfaIndex&) = delete;
+    ~GfaIndex();
+};
+
+}  // namespace pgsgd
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+namespace pgsgd {
+
+inline GfaIndex::~GfaIndex() {
+    if (text) munmap((void*) text, bytes);
+    if (fd >= 0) close(fd);
+}
+
+inline void scan_gfa(const std::string& path, GfaIndex& ix) {
+    ix.fd = open(path.c_str(), O_RDONLY);
+    if (ix.fd < 0) throw std::runtime_error("cannot open " + path);
+    struct stat sb;
+    if (fstat(ix.fd, &sb) != 0 || sb.st_size == 0) throw std::runtime_error("cannot stat " + path);
+    ix.bytes = (size_t) sb.st_size;
+    void* m = mmap(nullptr, ix.bytes, PROT_READ, MAP_PRIVATE, ix.fd, 0);
+    if (m == MAP_FAILED) throw std::runtime_error("cannot map " + path);
+    ix.text = (const char*) m;
+    madvise(m, ix.bytes, MADV_SEQUENTIAL);
+    std::vector<std::pair<uint64_t, uint32_t>> segs;
+    uint64_t max_id = 0;
+    auto field_end_of = [](const char* b, const char* line_end) {   // next tab, or the end of the line (without a CR)
+        const char* t = (const char*) std::memchr(b, '\t', (size_t) (line_end - b));
+        const char* e = t ? t : line_end;
+        if (!t && e > b && e[-1] == '\r') --e;
+        return e;
+    };
+    auto parse_id = [](const char* b, const char* e, uint64_t& id) {
+        id = 0;
+        if (b == e) return false;
+        for (const char* q = b; q < e; ++q) {
+            if ((unsigned) (*q - '0') > 9u) return false;
+            id = id * 10 + (uint64_t) (*q - '0');
+        }
+        return id != 0;
+    };
+    const char* p = ix.text;
+    const char* const end = ix.text + ix.bytes;
+    while (p < end) {
+        const char* nl = (const char*) std::memchr(p, '\n', (size_t) (end - p));
+        const char* le = nl ? nl : end;
+        if (le - p >= 2 && p[1] == '\t') {
+            if (p[0] == 'S') {
+                const char* b = p + 2;
+                const char* e = field_end_of(b, le);
+                uint64_t id;
+                if (!parse_id(b, e, id)) throw std::runtime_error("[odgi::layout] error: the graph is not optimized. Please run 'odgi sort' using -O, --optimize.");
+                const char* sb2 = e < le ? e + 1 : le;
+                const char* se = field_end_of(sb2, le);
+                uint32_t len = (uint32_t) (se - sb2);
+                if (len == 1 && *sb2 == '*') {
+                    len = 0;
+                    const char* tag = se;
+                    while (tag + 5 < le) { if (!std::memcmp(tag, "LN:i:", 5)) { len = (uint32_t) std::strtoull(tag + 5, nullptr, 10); break; } ++tag; }
+                }
+                segs.emplace_back(id, len);
+                if (id > max_id) max_id = id;
+            } else if (p[0] == 'P') {
+                const char* b = p + 2;
+                const char* e = field_end_of(b, le);
+                ix.path_names.emplace_back(b, (size_t) (e - b));
+                const char* fb = e < le ? e + 1 : le;
+                const char* fe = field_end_of(fb, le);
+                ix.field_begin.push_back((uint64_t) (fb - ix.text));
+                ix.field_end.push_back((uint64_t) (fe - ix.text));
+            } else if (p[0] == 'L') {
+                const char* b = p + 2;
+                const char* e = field_end_of(b, le);
+                uint64_t ia = 0, ib = 0;
+                const bool oka = parse_id(b, e, ia);
+                const char* o = e < le ? e + 1 : le;              // orientation field
+                const char* oe = field_end_of(o, le);
+                const char* b2 = oe < le ? oe + 1 : le;
+                const char* e2 = field_end_of(b2, le);
+                if (oka && parse_id(b2, e2, ib)) ix.links.emplace_back((uint32_t) (ia - 1), (uint32_t) (ib - 1));
+            }
+        }
+        p = nl ? nl + 1 : end;
+    }
+    if (max_id != segs.size()) throw std::runtime_error("[odgi::layout] error: the graph is not optimized. Please run 'odgi sort' using -O, --optimize.");
+    ix.node_len.assign(max_id, 0);
+    for (auto& sg : segs) ix.node_len[sg.first - 1] = sg.second;
+}
+
 }  // namespace pgsgd

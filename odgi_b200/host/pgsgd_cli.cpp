@@ -3,6 +3,7 @@
 // standalone: GFA in -> flattened graph -> C-ABI (include/pgsgd.h) -> .lay / TSV layout / node order out.
 // Everything that is not the PG-SGD path (the .og container, other sort pipelines, drawing) stays in odgi.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -41,7 +42,7 @@ const Flag LAYOUT_FLAGS[] = {
     {"K", "path-sgd-cooling", true}, {"F", "path-sgd-iteration-max-learning-rate", true}, {"k", "path-sgd-zipf-space", true},
     {"I", "path-sgd-zipf-space-max", true}, {"l", "path-sgd-zipf-space-quantization-step", true}, {"t", "threads", true},
     {"", "gpu", false}, {"P", "progress", false}, {"h", "help", false}, {"", "seed", true}, {"", "init-seed", true}, {"", "sampling", true},
-    {"u", "path-sgd-snapshot", true}, {"f", "path-sgd-use-paths", true}};
+    {"u", "path-sgd-snapshot", true}, {"f", "path-sgd-use-paths", true}, {"", "device-ingest", false}, {"", "timing", false}};
 const Flag SORT_FLAGS[] = {
     {"i", "idx", true}, {"o", "out", true}, {"Y", "path-sgd", false}, {"G", "path-sgd-min-term-updates-paths", true},
     {"U", "path-sgd-min-term-updates-nodes", true}, {"j", "path-sgd-delta", true}, {"g", "path-sgd-eps", true},
@@ -234,6 +235,100 @@ bool init_layout(const pgsgd::FlatGraph& fg, char mode, bool seeded, uint64_t se
 
 bool read_path_list(const std::string& file, const pgsgd::FlatGraph& fg, bool reject_duplicates, bool unknown_is_error, std::vector<uint64_t>& out);
 
+// `pgsgd layout --device-ingest`: the whole file-to-file path with no per-step and no per-node-coordinate host work —
+// the host maps the GFA and finds its lines (scan_gfa), the P-line step lists are parsed and flattened on the GPU
+// (pgsgd_engine_create_from_gfa_paths), the layout runs there, and the component stacking + `.lay` encoding
+// (layout_main.cpp:402-463) happen there too (pgsgd_engine_encode_lay).  Weak components come from the L lines.
+// --timing prints where the wall clock went as one JSON line on stderr.
+int layout_device_ingest(const Args& a) {
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    pgsgd::GfaIndex ix;
+    try { pgsgd::scan_gfa(a.str("idx"), ix); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
+    const double t_scan = now();
+    pgsgd_engine* e = nullptr;
+    if (pgsgd_engine_create_from_gfa_paths(ix.node_len.data(), ix.node_len.size(), ix.text, ix.field_begin.data(), ix.field_end.data(),
+                                           ix.field_begin.size(), 0, &e) != PGSGD_OK) {
+        std::cerr << "[odgi::layout] error: " << pgsgd_last_error() << std::endl;
+        return 1;
+    }
+    const double t_engine = now();
+    PathStats ps;
+    pgsgd_engine_graph_stats(e, &ps.sum_steps, &ps.max_steps, &ps.max_bp, nullptr);
+    pgsgd::FlatGraph fg;               // node table only: what the defaults and the initialisation read
+    fg.node_len = ix.node_len;
+    pgsgd_config c;
+    common_config(a, fg, false, c, &ps);
+    const uint64_t N = fg.node_len.size();
+    std::vector<double> X, Y;
+    int rc = init_layout(fg, a.str("layout-initialization", "d")[0], a.has("init-seed"), a.u64("init-seed", 0), X, Y) ? 0 : 1;
+    pgsgd_stats st;
+    std::memset(&st, 0, sizeof(st));
+    if (!rc) rc = pgsgd_engine_set_coords_2d(e, X.data(), Y.data());
+    const double t_init = now();
+    if (!rc) rc = pgsgd_engine_run_2d(e, &c, &st);
+    const double t_run = now();
+    // weak components from the links (union-find over node ranks), numbered by their smallest node as components_of does
+    Components uf(N);
+    for (auto& l : ix.links) if (l.first < N && l.second < N) uf.unite(l.first, l.second);
+    std::vector<uint32_t> comp(N);
+    uint32_t n_comp = 0;
+    {
+        std::map<uint32_t, uint32_t> ids;
+        for (uint32_t i = 0; i < N; ++i) {
+            const uint32_t r = uf.find(i);
+            auto it = ids.find(r);
+            if (it == ids.end()) it = ids.emplace(r, (uint32_t) ids.size()).first;
+            comp[i] = it->second;
+        }
+        n_comp = (uint32_t) ids.size();
+    }
+    uint64_t lay_bytes = 0;
+    if (!rc && a.has("out")) {
+        rc = pgsgd_engine_encode_lay(e, comp.data(), n_comp, nullptr, 0, &lay_bytes);
+        std::vector<uint8_t> buf(lay_bytes);
+        if (!rc) rc = pgsgd_engine_encode_lay(e, comp.data(), n_comp, buf.data(), buf.size(), &lay_bytes);
+        if (!rc) {
+            if (a.str("out") == "-") std::cout.write((const char*) buf.data(), (std::streamsize) buf.size());
+            else { std::ofstream f(a.str("out"), std::ios::binary); f.write((const char*) buf.data(), (std::streamsize) buf.size()); }
+        }
+    }
+    if (!rc && a.has("tsv")) {   // the text form needs the coordinates on the host: download + the host stacking, as without the flag
+        rc = pgsgd_engine_get_coords_2d(e, X.data(), Y.data());
+        if (!rc) {
+            const double border = 1000.0, inf = std::numeric_limits<double>::max();
+            std::vector<double> min_x(n_comp, inf), min_y(n_comp, inf), max_y(n_comp, std::numeric_limits<double>::lowest());
+            for (uint64_t r = 0; r < N; ++r)
+                for (uint64_t j = 2 * r; j <= 2 * r + 1; ++j) {
+                    min_x[comp[r]] = std::min(min_x[comp[r]], X[j]); min_y[comp[r]] = std::min(min_y[comp[r]], Y[j]); max_y[comp[r]] = std::max(max_y[comp[r]], Y[j]);
+                }
+            double curr = border;
+            std::vector<double> x_off(n_comp), y_off(n_comp);
+            for (uint32_t k = 0; k < n_comp; ++k) { x_off[k] = min_x[k] - border; y_off[k] = curr - min_y[k]; curr += (max_y[k] - min_y[k]) + border; }
+            std::ofstream fout;
+            std::ostream* out = &std::cout;
+            if (a.str("tsv") != "-") { fout.open(a.str("tsv")); out = &fout; }
+            *out << std::setprecision(std::numeric_limits<double>::digits10 + 1) << "idx\tX\tY\tcomponent" << std::endl;
+            for (uint32_t k = 0; k < n_comp; ++k)
+                for (uint64_t r = 0; r < N; ++r) {
+                    if (comp[r] != k) continue;
+                    for (uint64_t j = 2 * r; j <= 2 * r + 1; ++j) *out << j << "\t" << X[j] - x_off[k] << "\t" << Y[j] + y_off[k] << "\t" << k << '\n';
+                }
+        }
+    }
+    const double t_out = now();
+    if (e) pgsgd_engine_destroy(e);
+    if (rc) { std::cerr << "[odgi::layout] error: " << pgsgd_last_error() << std::endl; return 1; }
+    if (a.has("progress") || a.has("timing"))
+        std::fprintf(stderr, "{\"ingest\": \"device\", \"nodes\": %llu, \"paths\": %llu, \"steps\": %llu, \"gfa_bytes\": %llu, \"scan_lines_s\": %.4f, "
+                             "\"upload_parse_flatten_s\": %.4f, \"init_coords_s\": %.4f, \"iterations_s\": %.4f, \"run_call_s\": %.4f, "
+                             "\"components_stack_encode_write_s\": %.4f, \"lay_bytes\": %llu, \"total_s\": %.4f, \"term_updates\": %llu}\n",
+                     (unsigned long long) N, (unsigned long long) ix.field_begin.size(), (unsigned long long) ps.sum_steps, (unsigned long long) ix.bytes,
+                     t_scan - t0, t_engine - t_scan, t_init - t_engine, st.seconds_iterations, t_run - t_init, t_out - t_run,
+                     (unsigned long long) lay_bytes, t_out - t0, (unsigned long long) st.term_updates);
+    return 0;
+}
+
 int main_layout(int argc, char** argv) {
     Args a;
     if (!parse(argc, argv, LAYOUT_FLAGS, a, "layout") || a.has("help") || argc == 2) {
@@ -245,6 +340,7 @@ int main_layout(int argc, char** argv) {
     // layout_main.cpp:110-114
     if (!a.has("tsv") && !a.has("out")) { std::cerr << "[odgi::layout] error: Please specify an output file to where to store the layout via -o/--out=[FILE], -T/--tsv=[FILE]" << std::endl; return 1; }
     if (int rc = need_gpu(a, "layout")) return rc;
+    if (a.has("device-ingest")) return layout_device_ingest(a);
     pgsgd::FlatGraph fg;
     try { fg = pgsgd::read_gfa_flat(a.str("idx")); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
     pgsgd_config c;

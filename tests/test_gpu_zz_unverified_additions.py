@@ -168,8 +168,8 @@ with odgi_b200.Engine(mine, device=rank) as e:
     e.set_coords_2d_f32(orc.XY_to_xy(X0, Y0))
     st = e.run_2d(cd)
     xy = e.get_coords_2d_f32()
-    e.set_multi_mode(capi.MULTI_HYBRID)
-    try:
+    try:   # a mode that walks tiles by node range: refused (when it is selected after the upload, or when it would run)
+        e.set_multi_mode(capi.MULTI_HYBRID)
         e.run_2d(cd); refused = False
     except odgi_b200.PgsgdError:
         refused = True
