@@ -23,7 +23,7 @@ extern "C" {
 
 /* Bumped whenever a struct below changes size or meaning.  Callers compare PGSGD_VERSION (what they were compiled against)
  * with pgsgd_version() (what they loaded) before the first call: a stale binary would otherwise pass short structs. */
-#define PGSGD_VERSION 103 /* 0.1.3 */
+#define PGSGD_VERSION 104 /* 0.1.4 */
 
 typedef enum pgsgd_status {
     PGSGD_OK = 0,
@@ -132,6 +132,8 @@ typedef struct pgsgd_stats {
     uint64_t flags_used;                   /* PGSGD_FLAG_* actually in effect (the engine switches to EXCH_WRITE by itself
                                               when a hub node would see too many concurrent red.adds) */
     uint64_t sampling_used;                /* PGSGD_SAMPLING_STREAM or _TILE: what AUTO resolved to (last phase run) */
+    double   seconds_kernels;              /* of seconds_iterations: the SGD kernels (CUDA events per iteration) ... */
+    double   seconds_collectives;          /* ... and the collectives after them (transfer + waiting for the slowest rank); 0 on one GPU */
 } pgsgd_stats;
 
 typedef struct pgsgd_engine pgsgd_engine;   /* opaque: device-resident graph + coordinates + RNG streams */

@@ -51,7 +51,7 @@ class StatsC(C.Structure):
     _fields_ = [("iterations_run", C.c_uint64), ("term_updates", C.c_uint64), ("seconds_iterations", C.c_double),
                 ("seconds_upload", C.c_double), ("seconds_download", C.c_double), ("last_delta_max", C.c_double),
                 ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("flags_used", C.c_uint64),
-                ("sampling_used", C.c_uint64)]
+                ("sampling_used", C.c_uint64), ("seconds_kernels", C.c_double), ("seconds_collectives", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -75,7 +75,7 @@ class GoodnessC(C.Structure):
                 ("num_penalties_diff_orientation", C.c_uint64)]
 
 
-ABI_VERSION = 103  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
+ABI_VERSION = 104  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
 _lib = None
 
 

@@ -175,6 +175,7 @@ struct pgsgd_engine {
     int multi_mode = 0;                      // what the caller selected (PGSGD_MULTI_*)
     int mode = 0;                            // what AUTO resolved to when the coordinates were uploaded (else == multi_mode)
     cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;   // bracket a whole run_engine call (both phases of a hybrid run + the switch)
+    std::vector<cudaEvent_t> ev_pool;               // per-iteration events of multi-GPU runs (kernel | collective split)
     int active_mode = 0;                     // what the run in progress uses: ALLREDUCE or PEER (HYBRID switches between them)
     bool coords_in_slices = false;           // the authoritative coordinates are in the peer slices (peer phase), not the replica
     bool peer_ready_2d = false, peer_ready_1d = false;
@@ -728,6 +729,14 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         else if (tile_mode) CU(launch_tile_iteration(dims, batch, p, shape, e->stream));
         else CU(launch_iteration(dims, batch, p, shape, e->stream));
         ++st.kernel_launches;
+        if (e->comm) {   // kernel | collective split of this iteration (multi-GPU runs only)
+            while (e->ev_pool.size() < 2 * (iter - iter_begin + 1)) {
+                cudaEvent_t ev;
+                CU(cudaEventCreate(&ev));
+                e->ev_pool.push_back(ev);
+            }
+            CU(cudaEventRecord(e->ev_pool[2 * (iter - iter_begin)], e->stream));
+        }
         if (peer) {
             // no coordinate traffic here: every update already went to its owner through NVLink.  One 4-byte all-reduce per
             // iteration keeps the ranks in the same cooling-schedule step (and carries the early-stop statistic).
@@ -753,6 +762,7 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
             }
             if (track_delta) NC(ncclAllReduce(e->d_delta, e->d_delta, 1, ncclUint32, ncclMax, e->comm, e->stream));
         }
+        if (e->comm) CU(cudaEventRecord(e->ev_pool[2 * (iter - iter_begin) + 1], e->stream));
         if (track_delta) {
             // early stop (checker_lambda: path_sgd_layout.cpp:142, path_sgd.cpp:183): Delta_max <= delta
             unsigned int bits = 0;
@@ -781,6 +791,17 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     st.iterations_run = iter - iter_begin;
     st.term_updates = counted;
     st.seconds_iterations = ms * 1e-3;
+    st.seconds_kernels = st.seconds_iterations;
+    if (e->comm && st.iterations_run) {
+        double coll = 0;
+        for (uint64_t k = 0; k < st.iterations_run && 2 * k + 1 < e->ev_pool.size(); ++k) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, e->ev_pool[2 * k], e->ev_pool[2 * k + 1]) == cudaSuccess) coll += t * 1e-3;
+        }
+        cudaGetLastError();
+        st.seconds_collectives = coll;
+        st.seconds_kernels = st.seconds_iterations - coll;
+    }
     if (stats) *stats = st;
     return PGSGD_OK;
 }
@@ -837,6 +858,8 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
             st.last_delta_max = b.last_delta_max;
             st.flags_used |= b.flags_used;
             st.sampling_used = b.sampling_used;
+            st.seconds_kernels += b.seconds_kernels;
+            st.seconds_collectives += b.seconds_collectives;
         }
         st.seconds_iterations = ms * 1e-3;
         *stats = st;
@@ -1165,6 +1188,7 @@ void pgsgd_engine_destroy(pgsgd_engine* e) {
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_r0) cudaEventDestroy(e->ev_r0);
     if (e->ev_r1) cudaEventDestroy(e->ev_r1);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }

@@ -204,6 +204,9 @@ def test_bench_line_assembles_with_a_stand_in_engine(monkeypatch, capfd):
         def path_stress(self, dims, pairs, seed):
             return 1.0 / (1 + self.it)
 
+        def local_stress(self, dims, pairs, seed):
+            return 2.0 / (1 + self.it)
+
         def run_range(self, cfg, dims, lo, hi):
             n = max(0, min(hi, cfg.iter_max) - lo)
             self.it += n
