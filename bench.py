@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--multi", default="auto", choices=["auto", "hybrid", "peer", "allreduce", "sharded"],
                     help="N>1: 'auto' (default) = allreduce where every replica still sees >= 60 updates per node and iteration (graphs many "
-                         "haplotypes deep, c4), else hybrid; 'allreduce' = replicated coordinates + 1 NCCL all-reduce/step (north_star's design); "
+                         "haplotypes deep, c4), else peer; 'allreduce' = replicated coordinates + 1 NCCL all-reduce/step (north_star's design); "
                          "'peer' = coordinates partitioned over the GPUs, updated through NVLink peer memory (one shared Hogwild); 'hybrid' = allreduce "
                          "for the first third of the schedule, peer afterwards; 'sharded' = allreduce with the step records dealt out over the ranks by "
                          "path (capacity mode for graphs whose records do not fit one GPU; quality readout covers rank 0's paths)")

@@ -217,7 +217,8 @@ int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int 
 #define PGSGD_MULTI_HYBRID    2
 /*  AUTO     : ALLREDUCE when every replica still sees at least PGSGD_AUTO_MIN_UPDATES_PER_NODE updates per node and
  *             iteration (10 * steps / nodes / ranks in 2D, steps / nodes / ranks in 1D: graphs many haplotypes deep, where the
- *             mean of the replicas anneals like one Hogwild), else HYBRID.  Resolved when the coordinates are uploaded. */
+ *             mean of the replicas anneals like one Hogwild), else PEER (shallow graphs do not survive replica averaging,
+ *             not even for the first third of the schedule: DESIGN.md 6).  Resolved when the coordinates are uploaded. */
 #define PGSGD_MULTI_AUTO      3
 #define PGSGD_AUTO_MIN_UPDATES_PER_NODE 60.0
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode);

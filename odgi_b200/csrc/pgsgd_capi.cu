@@ -868,13 +868,15 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
 }
 
 // AUTO: replicas + one all-reduce per iteration where every replica still sees enough updates per node and iteration for the
-// mean of the replicas to anneal like one Hogwild (deep graphs: many haplotypes per node), else the hybrid schedule whose
-// annealing phase is one shared Hogwild over NVLink (scripts/cpu_exp_allreduce_depth.py).
+// mean of the replicas to anneal like one Hogwild (deep graphs: many haplotypes per node; c4 and mid at 8 GPUs end at or
+// below the single-GPU stress), else ONE shared Hogwild over NVLink peer memory from the first iteration: on the 6-haplotype
+// longthin graph 8 replicas end at a far stress of 1.0 (no layout at all) and even the hybrid schedule, whose first third is
+// replicated, at +33 % (profiles/r02_multi_suite_n8.jsonl).
 int resolve_mode(const pgsgd_engine* e, int dims) {
     if (e->multi_mode != PGSGD_MULTI_AUTO) return e->multi_mode;
     if (!e->comm || e->n_ranks < 2 || e->shard_global_steps) return PGSGD_MULTI_ALLREDUCE;
     const double per_replica = (dims == 2 ? 10.0 : 1.0) * (double) e->S / (double) e->N / (double) e->n_ranks;
-    return per_replica >= PGSGD_AUTO_MIN_UPDATES_PER_NODE ? PGSGD_MULTI_ALLREDUCE : PGSGD_MULTI_HYBRID;
+    return per_replica >= PGSGD_AUTO_MIN_UPDATES_PER_NODE ? PGSGD_MULTI_ALLREDUCE : PGSGD_MULTI_PEER;
 }
 
 // After a coordinate upload: resolve the mode, build what its phases need (peer slices + IPC mappings + tile ownership)
