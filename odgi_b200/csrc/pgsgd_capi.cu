@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -16,6 +17,7 @@
 #include <map>
 #include <mutex>
 #include <numeric>
+#include <random>
 #include <tuple>
 #include <thread>
 #include <unistd.h>
@@ -314,12 +316,18 @@ int setup_peer(pgsgd_engine* e, int dims) {
     CU(cudaMemsetAsync(mine, 0, bytes, e->stream));
     // what every rank publishes about its slice: the CUDA IPC handle (other processes map it) and, for ranks that are
     // threads of THIS process (single-process multi-GPU, e.g. the odgi shim), the raw pointer + device (peer access)
-    struct SliceInfo { cudaIpcMemHandle_t ipc; uint64_t pid; uint64_t ptr; int32_t device; int32_t pad; };
+    struct SliceInfo { cudaIpcMemHandle_t ipc; uint64_t pid /* process nonce */; uint64_t ptr; int32_t device; int32_t pad; };
     static_assert(sizeof(SliceInfo) == 88, "SliceInfo layout");
     SliceInfo info;
     memset(&info, 0, sizeof(info));
     CU(cudaIpcGetMemHandle(&info.ipc, mine));
-    info.pid = (uint64_t) getpid();
+    // "same process" is decided by a per-process random nonce, not by the pid: ranks in different PID namespaces (one process
+    // per container) can share a pid, and a foreign raw pointer must never be dereferenced
+    static const uint64_t process_nonce = []() {
+        std::random_device rd;
+        return ((uint64_t) rd() << 32) ^ (uint64_t) rd() ^ ((uint64_t) getpid() << 17) ^ (uint64_t) std::chrono::steady_clock::now().time_since_epoch().count();
+    }();
+    info.pid = process_nonce;
     info.ptr = (uint64_t) (uintptr_t) mine;
     info.device = e->device;
     uint8_t* d_h = nullptr;
@@ -1643,11 +1651,43 @@ static int run_multi_in_process(const pgsgd_graph_view* g, const pgsgd_config* c
     std::vector<std::string> errs(n_gpus);
     std::vector<pgsgd_stats> sts(n_gpus);
     std::vector<std::vector<double>> outX(n_gpus), outY(n_gpus);
+    // A rank that fails must not leave its siblings blocked in a collective: (1) every engine is created before any
+    // communicator is attached, and nobody attaches unless all creations succeeded; (2) a rank that fails later aborts every
+    // communicator of the call (ncclCommAbort unblocks the others' pending collectives, which then fail and return).
+    std::vector<pgsgd_engine*> engines(n_gpus, nullptr);
+    std::mutex mu;
+    std::condition_variable cv;
+    int created = 0;
+    bool create_failed = false, aborted = false;
+    auto abort_all = [&]() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (aborted) return;
+        aborted = true;
+        for (pgsgd_engine* q : engines)
+            if (q && q->comm) {
+                {
+                    std::lock_guard<std::mutex> lc(g_comm_mu);
+                    for (auto it = g_comm_cache.begin(); it != g_comm_cache.end();) it = it->second == q->comm ? g_comm_cache.erase(it) : std::next(it);
+                }
+                ncclCommAbort(q->comm);
+                q->comm = nullptr;
+            }
+    };
     std::vector<std::thread> threads;
     for (int r = 0; r < n_gpus; ++r) {
         threads.emplace_back([&, r]() {
             pgsgd_engine* e = nullptr;
             int c = pgsgd_engine_create(g, r, &e);
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                engines[r] = e;
+                if (c) create_failed = true;
+                ++created;
+                cv.notify_all();
+                cv.wait(lk, [&]() { return created == n_gpus; });
+                if (!c && create_failed) c = PGSGD_ERR_STATE;   // a sibling could not create its engine: nobody attaches
+            }
+            if (c == PGSGD_ERR_STATE && errs[r].empty()) errs[r] = "another GPU of the call failed to create its engine";
             if (!c) c = pgsgd_engine_attach_comm(e, id, n_gpus, r);
             if (!c) c = pgsgd_engine_set_multi_mode(e, multi_mode);
             if (!c) c = dims == 2 ? pgsgd_engine_set_coords_2d(e, X, Y) : pgsgd_engine_set_coords_1d(e, x_is_initialised ? X : nullptr);
@@ -1659,12 +1699,13 @@ static int run_multi_in_process(const pgsgd_graph_view* g, const pgsgd_config* c
                 if (dims == 2) { outY[r].resize(n_out); c = pgsgd_engine_get_coords_2d(e, outX[r].data(), outY[r].data()); }
                 else c = pgsgd_engine_get_coords_1d(e, outX[r].data());
             }
-            if (c) errs[r] = pgsgd_last_error();
+            if (c && errs[r].empty()) errs[r] = pgsgd_last_error();
             rcs[r] = c;
-            if (e) pgsgd_engine_destroy(e);
+            if (c && !create_failed) abort_all();
         });
     }
     for (auto& t : threads) t.join();
+    for (pgsgd_engine* q : engines) if (q) pgsgd_engine_destroy(q);
     for (int r = 0; r < n_gpus; ++r) if (rcs[r]) return fail(rcs[r], "GPU %d: %s", r, errs[r].c_str());
     memcpy(X, outX[0].data(), n_out * sizeof(double));
     if (dims == 2) memcpy(Y, outY[0].data(), n_out * sizeof(double));
