@@ -151,6 +151,13 @@ struct pgsgd_engine {
     uint8_t* d_frozen = nullptr;
     double* d_zetas = nullptr;
     uint64_t zetas_cap = 0;
+    // the zeta table costs O(space) bit-hack pows on the host (4.6e6 for c4: ~10 ms): kept across run calls with the same Zipf
+    // parameters, so that a caller stepping through the schedule (run_range per iteration) pays it once
+    std::vector<double> zetas_host;
+    uint64_t zkey_space = 0, zkey_max = 0, zkey_q = 0;
+    double zkey_theta = -1;
+    bool zetas_on_device = false;
+    int ztab_dims = 0;                        // for which dims the fp32 companions were uploaded (0 = not)
     float2* d_ztab[2] = {nullptr, nullptr};  // pipelined tile kernel: fp32 {zeta_n, 1/(1 - zeta_2/zeta_n)} for theta / for the 1D cooling theta
     uint64_t ztab_cap = 0;
     uint64_t max_path_bp = 0;                // largest end-adjusted position (pos + len) of any step: < 2^32 selects 32-bit distances
@@ -437,9 +444,20 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     if (cfg->space == 0) return fail(PGSGD_ERR_ARG, "space must be > 0");
 
     const std::vector<double> etas = build_schedule(*cfg);
-    const std::vector<double> zetas = build_zetas(*cfg);
-    rc = ensure_zetas(e, zetas);
-    if (rc) return rc;
+    if (e->zetas_host.empty() || e->zkey_space != cfg->space || e->zkey_max != cfg->space_max || e->zkey_q != cfg->space_quantization_step ||
+        e->zkey_theta != cfg->theta) {
+        e->zetas_host = build_zetas(*cfg);
+        e->zkey_space = cfg->space; e->zkey_max = cfg->space_max; e->zkey_q = cfg->space_quantization_step; e->zkey_theta = cfg->theta;
+        e->zetas_on_device = false;
+        e->ztab_dims = 0;
+    }
+    const std::vector<double>& zetas = e->zetas_host;
+    if (!e->zetas_on_device) {
+        rc = ensure_zetas(e, zetas);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(e->stream));
+        e->zetas_on_device = true;
+    }
 
     const uint64_t first_cooling_iteration = (uint64_t) std::floor(cfg->cooling_start * (double) cfg->iter_max);
     uint64_t n_iters = dims == 1 ? cfg->iter_max + 1 : cfg->iter_max;  // path_sgd.cpp:181 vs path_sgd_layout.cpp:140
@@ -653,9 +671,12 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         t2.delta_max_bits = p.delta_max_bits;
         t2.counted = p.counted;
         t2.trace = p.trace; t2.trace_count = p.trace_count; t2.trace_cap = p.trace_cap;
-        rc = upload_ztab(e, 0, zetas, cfg->theta);
-        if (!rc && dims == 1) rc = upload_ztab(e, 1, zetas, 0.001);   // 1D cooling: adj_theta with the zetas of the original theta (path_sgd.cpp:195,246)
-        if (rc) return rc;
+        if (e->ztab_dims != dims) {
+            rc = upload_ztab(e, 0, zetas, cfg->theta);
+            if (!rc && dims == 1) rc = upload_ztab(e, 1, zetas, 0.001);   // 1D cooling: adj_theta with the zetas of the original theta (path_sgd.cpp:195,246)
+            if (rc) return rc;
+            e->ztab_dims = dims;
+        }
     }
     if (peer) {
         p.n_parts = (uint32_t) e->n_ranks;
@@ -1591,6 +1612,8 @@ int pgsgd_engine_sample_terms(pgsgd_engine* e, const pgsgd_config* cfg, int dims
     CU(cudaSetDevice(e->device));
     rc = ensure_zetas(e, build_zetas(*cfg));
     if (rc) return rc;
+    e->zetas_on_device = false;   // the table on the device is this call's now
+    e->ztab_dims = 0;
     SamplerParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.path_first = e->d_path_first;
