@@ -136,13 +136,18 @@ def usable_cores():
 
 
 def cpu_threads():
-    """(threads to use, usable cores, 1-minute load average): cores other tenants of the box keep busy are left to them —
-    the reference's workers spin on per-node locks (src/odgi.cpp:65-71) and collapse when oversubscribed."""
+    """(threads to use, usable cores, 1-minute load average).  Inside a cpuset smaller than the machine (a 1-GPU lease: 16 of
+    128 cores) the usable cores are ours — the machine-wide load average is other tenants on other cores.  On the whole
+    machine the cores other processes keep busy are left to them: the reference's workers spin on per-node locks
+    (src/odgi.cpp:65-71) and collapse when oversubscribed (round 1: 128 workers on a 16-core lease -> 9x slower)."""
     usable = usable_cores()
+    machine = os.cpu_count() or usable
     try:
         load1 = os.getloadavg()[0]
     except OSError:
         load1 = 0.0
+    if usable < machine:
+        return usable, usable, load1
     free = usable - int(load1 + 0.5)
     return max(min(usable, 4), min(usable, free)), usable, load1
 

@@ -118,6 +118,8 @@ typedef struct pgsgd_config {
                                        sectors (the measured wall: ~69 G DRAM sectors/s) */
 #define PGSGD_FLAG_L2_WINDOW  512u /* coordinates pinned in L2 by a persisting access-policy window on the engine's stream instead of
                                        per-instruction evict_last hints */
+#define PGSGD_FLAG_COORD_LD_FIRST  1024u /* experiments: coordinate loads with L2::evict_first (reds keep evict_last) */
+#define PGSGD_FLAG_COORD_LD_NORMAL 2048u /* experiments: coordinate loads with L2::evict_normal */
 #define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
 
 typedef struct pgsgd_stats {

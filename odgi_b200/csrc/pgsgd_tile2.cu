@@ -174,6 +174,10 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
     // the step array and a record fetched by one CTA is the far partner of its neighbours: normal priority keeps it around
     const uint64_t pol_stream = (p.flags & 256u) ? l2_policy_evict_normal() : l2_policy_evict_first();
     const uint64_t pol_keep = (p.flags & 512u) ? l2_policy_evict_normal() : l2_policy_evict_last();
+    // experiments (PGSGD_FLAG_COORD_LD_FIRST / _NORMAL): the policy of the coordinate LOADS alone; the reds keep evict_last.
+    // A load of a line homed on the other die leaves a copy in the local L2 partition: if those copies are what pushes
+    // coordinate lines out (0.3-0.4 DRAM sectors per update on c4), a short-lived policy for them should show.
+    const uint64_t pol_cld = (p.flags & 1024u) ? l2_policy_evict_first() : ((p.flags & 2048u) ? l2_policy_evict_normal() : pol_keep);
     const bool atomic_add = (p.flags & 5u) == 0;
     const bool st_mode = (p.flags & 4u) != 0;
     uint32_t done = 0;
@@ -335,8 +339,8 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
                         c_ia = b_ia;
                         c_ib = (rb.x >> 1) * 2u + end_b;
                         // the node's float4 {x0,y0,x1,y1} (16 bytes, one sector half) -> slot; the end is picked in stage C
-                        cp_async_16(slot_ca, reinterpret_cast<const float4*>(xy_base(p, c_ia >> 1)) + (c_ia >> 1), pol_keep);
-                        cp_async_16(slot_cb, reinterpret_cast<const float4*>(xy_base(p, c_ib >> 1)) + (c_ib >> 1), pol_keep);
+                        cp_async_16(slot_ca, reinterpret_cast<const float4*>(xy_base(p, c_ia >> 1)) + (c_ia >> 1), pol_cld);
+                        cp_async_16(slot_cb, reinterpret_cast<const float4*>(xy_base(p, c_ib >> 1)) + (c_ib >> 1), pol_cld);
                     } else {
                         const uint32_t na = b_ia, nb = rb.x >> 1;
                         uint32_t u = 3u;
