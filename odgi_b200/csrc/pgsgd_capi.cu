@@ -648,13 +648,20 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
     Tile2Params t2;
     memset(&t2, 0, sizeof(t2));
     if (tile_mode && tile2) {
-        // same visit arithmetic with this kernel's tile size
+        // same visit arithmetic with this kernel's tile size; PGSGD_TILE_SWEEPS=T (experiment): T terms per staged step and
+        // visit — every step is still a first step floor(U/S) (+1) times per iteration, but a tile is fetched q/T times
         const uint64_t W = (uint64_t) tile_steps;
         const uint64_t U_job = sharded ? U_rank : U;
         const uint64_t q = U_job / e->S, rU = U_job % e->S;
         const uint64_t extra = (rU + W - 1) / W;
+        uint64_t T = 1;
+        if (const char* sv = getenv("PGSGD_TILE_SWEEPS")) T = (uint64_t) atoi(sv);
+        if (T < 1 || T > 64) T = 1;
         t2.n_tiles = (e->S + W - 1) / W;
-        t2.n_visits = q * t2.n_tiles + extra;
+        t2.sweeps = (uint32_t) T;
+        t2.full_passes = q / T;
+        t2.rem_sweeps = (uint32_t) (q % T);
+        t2.n_visits = (t2.full_passes + (t2.rem_sweeps ? 1 : 0)) * t2.n_tiles + extra;
         t2.last_visit_terms = rU ? rU - (extra - 1) * W : W;
         t2.visit_rank = p.visit_rank;
         t2.visit_nranks = p.visit_nranks;
@@ -692,6 +699,7 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
             t2.last_visit_terms = p.last_visit_terms;
             t2.visit_rank = p.visit_rank;
             t2.visit_nranks = p.visit_nranks;
+            t2.sweeps = 1; t2.rem_sweeps = 0; t2.full_passes = UINT64_MAX;   // one term per staged step and visit, every pass
         }
         rc = comm_barrier(e);  // nobody starts before every slice is in place
         if (rc) return rc;

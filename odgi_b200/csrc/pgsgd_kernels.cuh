@@ -71,6 +71,8 @@ struct Tile2Params {
     uint64_t n_visits, n_tiles, last_visit_terms;
     uint64_t perm_mul[16], perm_add[16];
     uint32_t visit_rank, visit_nranks;
+    uint32_t sweeps, rem_sweeps;   // terms per staged step and visit in the full passes / in the one pass after them
+    uint64_t full_passes;
     unsigned long long* trace;
     unsigned long long* trace_count;
     uint64_t trace_cap;

@@ -112,11 +112,17 @@ struct VisitInfo {
     uint32_t one_path;          // the whole tile lies inside that path
     uint32_t terms;             // first steps used in this visit (TILE, less for the last visit)
     uint32_t n_in_tile;         // steps present in the tile (TILE, less at the end of the step array)
+    uint32_t sweeps;            // terms per staged step in this visit (p.sweeps in full passes, the rest in the last ones)
+    uint32_t pad;
 };
 
 template <typename FirstPtr>
 __device__ __forceinline__ void make_visit(const Tile2Params& p, FirstPtr first, uint64_t v, uint32_t tile_steps, VisitInfo* out) {
+    // passes 0 .. full_passes-1: every tile once, p.sweeps terms per staged step; then (if any) one pass with the left-over
+    // sweeps; then the remainder of U mod S as single-sweep visits over the first tiles of one more pass
     const uint64_t pass = v / p.n_tiles, i = v - pass * p.n_tiles;
+    out->sweeps = pass < p.full_passes ? p.sweeps : ((pass == p.full_passes && p.rem_sweeps) ? p.rem_sweeps : 1u);
+    out->pad = 0;
     uint64_t t_idx = p.perm_mul[pass & 15] ? tile_perm(i, p.n_tiles, p.perm_add[pass & 15]) : (i + p.perm_add[pass & 15]) % p.n_tiles;
     if (p.tile_list) t_idx = p.tile_list[t_idx];   // peer phases: the k-th tile this rank owns
     const uint64_t base = t_idx * (uint64_t) tile_steps;
@@ -238,7 +244,8 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
         uint32_t c_upd = 0;       // 1D: bit0 move a, bit1 move b
 
 #pragma unroll 1
-        for (int i = 0; i < ROUNDS + 2; ++i) {
+        const int n_terms = ROUNDS * (int) vi.sweeps;   // this thread's terms in this visit: `sweeps` passes over its ROUNDS steps
+        for (int i = 0; i < n_terms + 2; ++i) {
             // ================= stage C(i-2): the update =================
             if (i >= 2) {
                 cp_async_wait<1>();   // coordinates of term i-2 landed (the one younger group is term i-1's step record)
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
                 c_dij = -1.0f;
             }
             // ================= stage B(i-1): partner record -> distance, coordinate loads =================
-            if (i >= 1 && i <= ROUNDS) {
+            if (i >= 1 && i <= n_terms) {
                 cp_async_wait<0>();   // the partner's step record landed in this thread's slot
                 c_dij = -1.0f;
                 if (b_rb & 2u) {
@@ -366,8 +373,8 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
                 b_rb = 0;
             }
             // ================= stage A(i): first step from the tile, partner draw, far record on its way =================
-            if (i < ROUNDS) {
-                const uint32_t j = (uint32_t) i * 256 + threadIdx.x;
+            if (i < n_terms) {
+                const uint32_t j = (uint32_t) (i % ROUNDS) * 256 + threadIdx.x;
                 b_rb = 0;
                 if (j < vi.terms && j < vi.n_in_tile) {
                     uint64_t f = vi.f;
