@@ -32,6 +32,28 @@ def drb1(golden_graphs, tmp_path_factory):
     return str(gfa), orc.Graph.from_arrays(a)
 
 
+def test_cli_layout_device_ingest(drb1, tmp_path):
+    """`pgsgd layout --device-ingest`: GFA lines found on the host, step lists parsed / flattened / laid out / stacked / .lay-encoded
+    on the GPU.  The .lay decodes to a layout in the reference's stress band; the TSV route gives the same component column."""
+    gfa, go = drb1
+    lay, back, tsv = tmp_path / "dev.lay", tmp_path / "dev.arr", tmp_path / "dev.tsv"
+    r = subprocess.run([CLI, "layout", "-i", gfa, "-o", str(lay), "-T", str(tsv), "--gpu", "--init-seed", "42", "--device-ingest", "--timing"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads([ln for ln in r.stderr.splitlines() if ln.startswith("{")][-1])
+    assert info["ingest"] == "device" and info["nodes"] == go.N and info["steps"] == go.S and info["term_updates"] == 30 * 10 * go.S
+    subprocess.run([CLI, "lay", "-i", str(lay), "-a", str(back)], check=True)
+    b = read_arrays(str(back))
+    assert b["X"].size == 2 * go.N and np.all(np.isfinite(b["X"])) and np.all(np.isfinite(b["Y"]))
+    band = _band("DRB1-3123.layout2d")
+    s = orc.path_stress_2d(go, b["X"], b["Y"], band["n_pairs"], band["seed"])   # the stacking is a translation: stress unchanged
+    assert abs(s - band["mean"]) <= 0.03 * band["mean"], (s, band["mean"])
+    rows = np.loadtxt(str(tsv), skiprows=1)
+    assert rows.shape == (2 * go.N, 4) and np.allclose(np.sort(rows[:, 0]), np.arange(2 * go.N))
+    # one component, moved to the (border, border) corner by layout_main.cpp:402-433
+    assert abs(b["X"].min() - 1000.0) < 1e-6 and abs(b["Y"].min() - 1000.0) < 1e-6
+
+
 def test_cli_layout_tsv(drb1, tmp_path):
     gfa, go = drb1
     tsv = tmp_path / "lay.tsv"
