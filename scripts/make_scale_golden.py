@@ -13,7 +13,7 @@ Stage 2 (`bands`): evaluate the oracle's far-pair stress AND local stress of eve
 tests/golden/stress_reference_scale.json {mean, sd, values} per graph / dimension / metric.
 
 Authoring container only (needs /root/reference via oracle/_ref).  Usage:
-  python scripts/make_scale_golden.py run  [graph ...] [--runs R] [--threads T] [--dims 2,1]
+  python scripts/make_scale_golden.py run  [graph ...] [--runs R] [--threads T[,T2,...]] [--first-run K] [--dims 2,1]
   python scripts/make_scale_golden.py bands
 """
 import json
@@ -41,7 +41,7 @@ def graph_of(name):
     return synth.generate(n_sites, n_paths, seed=42)
 
 
-def stage_run(names, runs, threads, dims):
+def stage_run(names, runs, threads, dims, first_run=0):
     from oracle import oracle as orc
     os.makedirs(SCRATCH, exist_ok=True)
     for name in names:
@@ -55,12 +55,16 @@ def stage_run(names, runs, threads, dims):
             X0, Y0 = orc.layout_init(go, seed=42)
             write_arrays(init, {"X": X0, "Y": Y0})
         for d in dims:
-            for r in range(runs):
+            for r in range(first_run, first_run + runs):
                 out = os.path.join(SCRATCH, f"{name}.{'layout2d' if d == 2 else 'sort1d'}.run{r}.arr")
                 if os.path.exists(out):
                     continue
                 t0 = time.time()
-                cmd = [REF, "layout", gfa, init, out + ".tmp", f"threads={threads}"] if d == 2 else [REF, "sort", gfa, out + ".tmp", f"threads={threads}"]
+                # The reference seeds worker thread t with 9399220 + t, always (path_sgd_layout.cpp:168): runs with ONE thread count
+                # share their random streams and differ by thread timing only.  A list of thread counts (--threads 8,7,5,4: run r
+                # uses entry r mod len) makes the runs sample different stream sets too, as scripts/make_stress_golden.py does.
+                th = threads[r % len(threads)]
+                cmd = [REF, "layout", gfa, init, out + ".tmp", f"threads={th}"] if d == 2 else [REF, "sort", gfa, out + ".tmp", f"threads={th}"]
                 p = subprocess.run(cmd, cwd=SCRATCH, capture_output=True, text=True)
                 if p.returncode != 0:
                     print("FAILED", cmd, p.stderr[-2000:], flush=True)
@@ -120,18 +124,20 @@ def main():
         raise SystemExit(__doc__)
     if a[0] == "bands":
         return stage_bands()
-    runs, threads, dims, names = 5, 6, [2, 1], []
+    runs, threads, dims, names, first_run = 5, [6], [2, 1], [], 0
     i = 1
     while i < len(a):
         if a[i] == "--runs":
             runs = int(a[i + 1]); i += 2
         elif a[i] == "--threads":
-            threads = int(a[i + 1]); i += 2
+            threads = [int(x) for x in a[i + 1].split(",")]; i += 2
+        elif a[i] == "--first-run":
+            first_run = int(a[i + 1]); i += 2
         elif a[i] == "--dims":
             dims = [int(x) for x in a[i + 1].split(",")]; i += 2
         else:
             names.append(a[i]); i += 1
-    stage_run(names or list(GRAPHS), runs, threads, dims)
+    stage_run(names or list(GRAPHS), runs, threads, dims, first_run)
 
 
 if __name__ == "__main__":
