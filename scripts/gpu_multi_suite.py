@@ -43,9 +43,13 @@ def sumr(x):
 
 
 names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c4"]
+ALL = {"allreduce": capi.MULTI_ALLREDUCE, "hybrid": capi.MULTI_HYBRID, "peer": capi.MULTI_PEER, "auto": capi.MULTI_AUTO}
 modes = [("allreduce", capi.MULTI_ALLREDUCE), ("hybrid", capi.MULTI_HYBRID)]
 if "--peer" in sys.argv:
     modes.append(("peer", capi.MULTI_PEER))
+for a in sys.argv[1:]:
+    if a.startswith("--modes="):
+        modes = [(m, ALL[m]) for m in a[8:].split(",")]
 W, K = 3, 12
 for name in names:
     g = synth.preset(name) if name in synth.PRESETS else synth.generate(3_000_000, 6, seed=42)
