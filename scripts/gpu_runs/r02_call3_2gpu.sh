@@ -5,7 +5,7 @@
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/r02_c3_gpus.txt 2>&1
-timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_host.py tests/test_gpu_zz_unverified_additions.py -q -k "two_rank or single_process or two_gpus or sharded" 2>&1 | tail -40 > gpurun_out/r02_c3_pytest_2gpu.log
+timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_host.py tests/test_gpu_more.py -q -k "two_rank or single_process or two_gpus or sharded" 2>&1 | tail -40 > gpurun_out/r02_c3_pytest_2gpu.log
 for MODE in auto hybrid peer; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --multi $MODE \
       > gpurun_out/r02_c3_bench_c4_n2_$MODE.json 2> gpurun_out/r02_c3_bench_c4_n2_$MODE.err

@@ -1,5 +1,7 @@
-"""GPU tests written AFTER round 1's GPU budget was spent: none of them has run on a device yet.  They live in
-their own file, last in collection order, so that `pytest -x` reaches every test that HAS been verified before any of these."""
+"""More GPU tests: odd-shaped and random graphs single-stream bit-exact, the path-sharded engine (1 and 2 ranks), the CLI's
+`.lay` / 1D-`.lay` / snapshot / `-H` outputs, the LPA 2D and chr6.C4 1D reference bands.  Written after round 1's GPU budget
+was spent (hence a file of their own); every one of them has since run green on a B200 (profiles/r02_pytest_gpu.log,
+profiles/r02_pytest_2gpu.log)."""
 import json
 import os
 import subprocess
