@@ -17,12 +17,14 @@ g = synth.preset(wl)
 band = json.load(open(os.path.join(ROOT, "tests", "golden", "stress_reference_scale.json")))[f"{wl}.sort1d"]
 print(f"workload={wl} N={g.N} S={g.S}  reference band far {band['far']['mean']:.6g} +- {band['far']['sd']:.3g}  local {band['local']['mean']:.5g} +- {band['local']['sd']:.3g}", flush=True)
 with odgi_b200.Engine(g) as e:
-    for n_streams in (0, 65536, 16384, 4096, 1024, 256):
+    counts = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 65536, 16384, 4096, 1024, 256]
+    seeds = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [9399220, 7]
+    for n_streams in counts:
         far, loc, rate = [], [], []
-        for seed in (9399220, 7):
+        for seed in seeds:
             cd = capi.sort_defaults(g, seed=seed, sampling=1, n_streams=n_streams)
             e.set_coords_1d(None)
             st = e.run_1d(cd)
             far.append(e.path_stress(1, 4_000_000, 12345)); loc.append(e.local_stress(1, 4_000_000, 12345))
             rate.append(st["term_updates"] / st["seconds_iterations"] / 1e9)
-        print(f"stream sampling, n_streams {n_streams or 'default':>8}: far {np.mean(far):.6g} [{' '.join(f'{v:.4g}' for v in far)}]  local {np.mean(loc):.5g}   {np.mean(rate):.2f} G/s", flush=True)
+        print(f"stream sampling, n_streams {n_streams or 'default':>8}: far {np.mean(far):.6g} sd {np.std(far, ddof=1):.2g} [{' '.join(f'{v:.4g}' for v in far)}]  local {np.mean(loc):.5g}   {np.mean(rate):.2f} G/s", flush=True)
