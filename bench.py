@@ -282,9 +282,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--flags", type=int, default=0)
-    ap.add_argument("--multi", default="auto", choices=["auto", "hybrid", "peer", "allreduce", "sharded"],
+    ap.add_argument("--multi", default="auto", choices=["auto", "hybrid", "peer", "allreduce", "single", "sharded"],
                     help="N>1: 'auto' (default) = allreduce where every replica still sees >= 60 updates per node and iteration (graphs many "
-                         "haplotypes deep, c4), else peer; 'allreduce' = replicated coordinates + 1 NCCL all-reduce/step (north_star's design); "
+                         "haplotypes deep, c4), else single (rank 0 alone + one broadcast: shallow graphs leave the reference band in every shared mode); 'allreduce' = replicated coordinates + 1 NCCL all-reduce/step (north_star's design); "
                          "'peer' = coordinates partitioned over the GPUs, updated through NVLink peer memory (one shared Hogwild); 'hybrid' = allreduce "
                          "for the first third of the schedule, peer afterwards; 'sharded' = allreduce with the step records dealt out over the ranks by "
                          "path (capacity mode for graphs whose records do not fit one GPU; quality readout covers rank 0's paths)")
@@ -348,7 +348,7 @@ def main():
         if sharded:
             g = odgi_b200.shard_paths(g, world, rank)   # this rank's paths only; node table whole
     multi_mode = {"auto": capi.MULTI_AUTO, "peer": capi.MULTI_PEER, "hybrid": capi.MULTI_HYBRID, "allreduce": capi.MULTI_ALLREDUCE,
-                  "sharded": capi.MULTI_ALLREDUCE}[args.multi]
+                  "single": capi.MULTI_SINGLE, "sharded": capi.MULTI_ALLREDUCE}[args.multi]
     sampling_name = {1: "stream", 2: "tile"}.get(args.sampling, "tile" if g.S >= (1 << 22) else "stream")
     X0, Y0 = odgi_b200.layout_init(g, seed=42)
     U = cfg.min_term_updates
@@ -393,7 +393,7 @@ def main():
     clocks = sampler.stop()
     dev_s = max_over_ranks(st["seconds_iterations"])   # CUDA events around the whole call (both phases of a hybrid run + the switch)
     wall_s = max_over_ranks(wall)
-    assert st["iterations_run"] == K and st["kernel_launches"] == K
+    assert st["iterations_run"] == K and st["kernel_launches"] in (K, 0)   # 0: a rank that only receives the broadcast (single mode)
     # counted term updates of the whole job (every rank reports its own share)
     total_updates = st["term_updates"]
     if dist is not None:
@@ -405,7 +405,7 @@ def main():
     # between the barriers — collectives, phase switches and host-side waits included.
     timed_s = dev_s if world == 1 else wall_s
     value = total_updates / timed_s / 1e6
-    resolved = {capi.MULTI_ALLREDUCE: "allreduce", capi.MULTI_PEER: "peer", capi.MULTI_HYBRID: "hybrid"}.get(e.resolved_multi_mode(), "?") if world > 1 else None
+    resolved = {capi.MULTI_ALLREDUCE: "allreduce", capi.MULTI_PEER: "peer", capi.MULTI_HYBRID: "hybrid", capi.MULTI_SINGLE: "single"}.get(e.resolved_multi_mode(), "?") if world > 1 else None
     if sharded:
         resolved = "sharded"
     # layout quality of the COMPLETE schedule: finish the remaining iterations (untimed) and evaluate the sampled path
@@ -501,6 +501,8 @@ def main():
                                    if resolved == "peer" else
                                    f"hybrid over {world} GPUs: iterations < {iter_max // 3} replicated + 1 NCCL all-reduce/step, then coords partitioned and updated through NVLink peer memory"
                                    if resolved == "hybrid" else
+                                   f"rank 0 runs the whole job, one broadcast of the coordinates to the other {world - 1} GPUs"
+                                   if resolved == "single" else
                                    f"step records dealt out over {world} GPUs by path (rank 0 holds {g.P} paths, {g.S} steps), replicated coords, 1 NCCL all-reduce/step"
                                    if sharded else f"replicated coords, term updates split over {world} GPU(s), 1 NCCL all-reduce/step"),
                    "multi_mode": resolved, "multi_requested": args.multi if world > 1 else None,

@@ -217,11 +217,15 @@ int pgsgd_engine_attach_comm(pgsgd_engine* e, const uint8_t unique_id[128], int 
 #define PGSGD_MULTI_ALLREDUCE 0
 #define PGSGD_MULTI_PEER      1
 #define PGSGD_MULTI_HYBRID    2
-/*  AUTO     : ALLREDUCE when every replica still sees at least PGSGD_AUTO_MIN_UPDATES_PER_NODE updates per node and
+/*  SINGLE   : rank 0 runs the whole job alone (the single-GPU result, exactly), the others receive the coordinates by one
+ *             broadcast.  For graphs that no way of sharing the work leaves inside the reference's stress band.
+ *  AUTO     : ALLREDUCE when every replica still sees at least PGSGD_AUTO_MIN_UPDATES_PER_NODE updates per node and
  *             iteration (10 * steps / nodes / ranks in 2D, steps / nodes / ranks in 1D: graphs many haplotypes deep, where the
- *             mean of the replicas anneals like one Hogwild), else PEER (shallow graphs do not survive replica averaging,
- *             not even for the first third of the schedule: DESIGN.md 6).  Resolved when the coordinates are uploaded. */
+ *             mean of the replicas anneals like one Hogwild), else SINGLE: a shallow graph measured at 8 GPUs ends at a far
+ *             stress of 1.0 with replicas, +33 % with HYBRID and +35-40 % with PEER, and is a fraction of a
+ *             second of work on one GPU.  Resolved when the coordinates are uploaded. */
 #define PGSGD_MULTI_AUTO      3
+#define PGSGD_MULTI_SINGLE    4
 #define PGSGD_AUTO_MIN_UPDATES_PER_NODE 60.0
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode);
 /* the mode in effect (what AUTO resolved to; meaningful once coordinates are uploaded) */

@@ -852,6 +852,42 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
     const int mode = e->comm ? e->mode : PGSGD_MULTI_ALLREDUCE;
     if (e->shard_global_steps && e->comm && mode != PGSGD_MULTI_ALLREDUCE)
         return fail(PGSGD_ERR_STATE, "path-sharded step records need PGSGD_MULTI_ALLREDUCE (peer phases walk tiles by node range)");
+    if (e->comm && mode == PGSGD_MULTI_SINGLE) {
+        // Rank 0 runs the job as if it were alone (the single-GPU result, exactly); the others wait for the broadcast of the
+        // coordinates.  For graphs that do not survive any way of sharing the work (shallow ones) and are, being
+        // shallow, a fraction of a second of work on one GPU.
+        CU(cudaSetDevice(e->device));
+        pgsgd_stats st;
+        memset(&st, 0, sizeof(st));
+        int rc = PGSGD_OK;
+        CU(cudaEventRecord(e->ev_r0, e->stream));
+        if (e->rank == 0) {
+            ncclComm_t comm = e->comm;
+            const int nr = e->n_ranks;
+            e->comm = nullptr; e->n_ranks = 1;
+            e->active_mode = PGSGD_MULTI_ALLREDUCE;
+            rc = run_phase(e, cfg, dims, iter_begin, iter_end, &st);
+            e->comm = comm; e->n_ranks = nr;
+        }
+        // what the others need to know: how many iterations ran (early stop) — travels in the delta word
+        unsigned int word = e->rank == 0 ? (rc ? 0xFFFFFFFFu : (unsigned int) st.iterations_run) : 0u;
+        CU(cudaMemcpyAsync(e->d_delta, &word, sizeof(word), cudaMemcpyHostToDevice, e->stream));
+        NC(ncclBroadcast(e->d_delta, e->d_delta, 1, ncclUint32, 0, e->comm, e->stream));
+        if (dims == 2) NC(ncclBroadcast(e->d_xy, e->d_xy, 4 * e->N, ncclFloat, 0, e->comm, e->stream));
+        else NC(ncclBroadcast(e->d_x1d, e->d_x1d, e->N, ncclDouble, 0, e->comm, e->stream));
+        CU(cudaMemcpyAsync(&word, e->d_delta, sizeof(word), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaEventRecord(e->ev_r1, e->stream));
+        CU(cudaEventSynchronize(e->ev_r1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e->ev_r0, e->ev_r1));
+        if (rc) return rc;
+        if (word == 0xFFFFFFFFu) return fail(PGSGD_ERR_STATE, "rank 0 of a PGSGD_MULTI_SINGLE run failed");
+        if (e->rank != 0) { st.iterations_run = word; st.seconds_upload = e->seconds_upload; st.h2d_bytes = e->h2d_bytes; }
+        st.seconds_collectives = ms * 1e-3 - (e->rank == 0 ? st.seconds_iterations : 0.0);
+        st.seconds_iterations = ms * 1e-3;
+        if (stats) *stats = st;
+        return PGSGD_OK;
+    }
     if (!e->comm || mode != PGSGD_MULTI_HYBRID) {
         e->active_mode = mode;
         return run_phase(e, cfg, dims, iter_begin, iter_end, stats);
@@ -906,14 +942,14 @@ int run_engine(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter
 
 // AUTO: replicas + one all-reduce per iteration where every replica still sees enough updates per node and iteration for the
 // mean of the replicas to anneal like one Hogwild (deep graphs: many haplotypes per node; c4 and mid at 8 GPUs end at or
-// below the single-GPU stress), else ONE shared Hogwild over NVLink peer memory from the first iteration: on the 6-haplotype
-// longthin graph 8 replicas end at a far stress of 1.0 (no layout at all) and even the hybrid schedule, whose first third is
-// replicated, at +33 % (profiles/r02_multi_suite_n8.jsonl).
+// below the single-GPU stress), else rank 0 alone + a broadcast: on the 6-haplotype longthin graph 8 replicas end at a far
+// stress of 1.0 (no layout at all), the hybrid schedule at +33 % and one shared Hogwild over NVLink peer memory at +35-40 %
+// (profiles/r02_multi_suite_n8.jsonl) — and such a graph is 0.2 s of work on one GPU.
 int resolve_mode(const pgsgd_engine* e, int dims) {
     if (e->multi_mode != PGSGD_MULTI_AUTO) return e->multi_mode;
     if (!e->comm || e->n_ranks < 2 || e->shard_global_steps) return PGSGD_MULTI_ALLREDUCE;
     const double per_replica = (dims == 2 ? 10.0 : 1.0) * (double) e->S / (double) e->N / (double) e->n_ranks;
-    return per_replica >= PGSGD_AUTO_MIN_UPDATES_PER_NODE ? PGSGD_MULTI_ALLREDUCE : PGSGD_MULTI_PEER;
+    return per_replica >= PGSGD_AUTO_MIN_UPDATES_PER_NODE ? PGSGD_MULTI_ALLREDUCE : PGSGD_MULTI_SINGLE;
 }
 
 // After a coordinate upload: resolve the mode, build what its phases need (peer slices + IPC mappings + tile ownership)
@@ -1526,8 +1562,8 @@ int pgsgd_engine_sort_goodness(pgsgd_engine* e, const uint64_t* order, uint32_t 
 
 int pgsgd_engine_set_multi_mode(pgsgd_engine* e, int mode) {
     if (!e) return fail(PGSGD_ERR_ARG, "set_multi_mode: NULL engine");
-    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_PEER && mode != PGSGD_MULTI_HYBRID && mode != PGSGD_MULTI_AUTO) return fail(PGSGD_ERR_ARG, "unknown multi-GPU mode %d", mode);
-    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_AUTO && (!e->comm || e->n_ranks < 2)) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator (pgsgd_engine_attach_comm) with >= 2 ranks");
+    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_PEER && mode != PGSGD_MULTI_HYBRID && mode != PGSGD_MULTI_AUTO && mode != PGSGD_MULTI_SINGLE) return fail(PGSGD_ERR_ARG, "unknown multi-GPU mode %d", mode);
+    if (mode != PGSGD_MULTI_ALLREDUCE && mode != PGSGD_MULTI_AUTO && mode != PGSGD_MULTI_SINGLE && (!e->comm || e->n_ranks < 2)) return fail(PGSGD_ERR_STATE, "peer mode needs an attached communicator (pgsgd_engine_attach_comm) with >= 2 ranks");
     if (e->have_2d || e->have_1d) return fail(PGSGD_ERR_STATE, "select the multi-GPU mode before uploading coordinates");
     e->multi_mode = mode;
     e->mode = mode == PGSGD_MULTI_AUTO ? PGSGD_MULTI_ALLREDUCE : mode;

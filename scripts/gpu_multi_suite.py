@@ -43,7 +43,7 @@ def sumr(x):
 
 
 names = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c4"]
-ALL = {"allreduce": capi.MULTI_ALLREDUCE, "hybrid": capi.MULTI_HYBRID, "peer": capi.MULTI_PEER, "auto": capi.MULTI_AUTO}
+ALL = {"allreduce": capi.MULTI_ALLREDUCE, "hybrid": capi.MULTI_HYBRID, "peer": capi.MULTI_PEER, "auto": capi.MULTI_AUTO, "single": capi.MULTI_SINGLE}
 modes = [("allreduce", capi.MULTI_ALLREDUCE), ("hybrid", capi.MULTI_HYBRID)]
 if "--peer" in sys.argv:
     modes.append(("peer", capi.MULTI_PEER))
@@ -59,7 +59,7 @@ for name in names:
     e.attach_comm(bcast_id(), world, rank)
     e.set_multi_mode(capi.MULTI_AUTO)
     e.set_coords_2d(X0, Y0)
-    auto = {capi.MULTI_ALLREDUCE: "allreduce", capi.MULTI_HYBRID: "hybrid", capi.MULTI_PEER: "peer"}[e.resolved_multi_mode()]
+    auto = {capi.MULTI_ALLREDUCE: "allreduce", capi.MULTI_HYBRID: "hybrid", capi.MULTI_PEER: "peer", capi.MULTI_SINGLE: "single"}[e.resolved_multi_mode()]
     e.close()
     for mname, mode in modes:
         e = odgi_b200.Engine(g, device=local)

@@ -50,6 +50,21 @@ for tag, flags in (("avg", 0), ("sum", capi.PGSGD_FLAG_SUM_DELTAS)):
     lst = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(lst, t)
     out[tag]["replicas_identical"] = bool(all(torch.equal(lst[0], x) for x in lst))
+# single mode (what AUTO picks for shallow graphs): rank 0 alone, one broadcast — with one worker stream the result is the
+# single-GPU one bit for bit, on every rank
+kw = dict(iter_max=4, min_term_updates=6000, eta_max=2000.0)
+cd = capi.layout_defaults(gd, n_streams=1, batch=1, sampling=capi.SAMPLING_STREAM, **kw)
+with odgi_b200.Engine(gd, device=rank) as e:
+    e.attach_comm(fresh_id(), world, rank)
+    e.set_multi_mode(capi.MULTI_SINGLE)
+    e.set_coords_2d_f32(orc.XY_to_xy(X0, Y0))
+    st = e.run_2d(cd)
+    xy = e.get_coords_2d_f32()
+_, ref1 = orc.layout_2d_f32(go, orc.default_layout_config(go, **kw), orc.XY_to_xy(X0, Y0), n_streams=1)
+t = torch.from_numpy(xy.copy()); lst = [torch.zeros_like(t) for _ in range(world)]; dist.all_gather(lst, t)
+cnt = torch.tensor([int(st["term_updates"])]); dist.all_reduce(cnt)
+out["single"] = {"equal": bool(np.array_equal(xy, ref1)), "identical": bool(all(torch.equal(lst[0], x) for x in lst)), "updates": int(cnt.item()),
+                 "iterations": int(st["iterations_run"])}
 # a default-shaped run on 2 GPUs: stress stays close to the single-GPU band (averaging costs a few percent, DESIGN.md §6)
 cd = capi.layout_defaults(gd)
 with odgi_b200.Engine(gd, device=rank) as e:
@@ -105,6 +120,7 @@ def test_two_rank_nccl_run_matches_emulation(tmp_path):
         assert res[tag]["replicas_identical"], res
         assert res[tag]["updates"] == 4 * 3000, res
         assert res[tag]["equal"], res
+    assert res["single"]["equal"] and res["single"]["identical"] and res["single"]["updates"] == 4 * 6000 and res["single"]["iterations"] == 4, res
     assert res["default_updates"] == 30 * 10 * 35059 // 2
     assert 0.06 < res["default_stress"] < 0.09, res
     # peer mode is one shared Hogwild: its stress sits in the single-GPU / reference band (no replica averaging loss)
