@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
         double c_dij_d = 0.0;     // 1D
         uint32_t c_upd = 0;       // 1D: bit0 move a, bit1 move b
 
-#pragma unroll 1
         const int n_terms = ROUNDS * (int) vi.sweeps;   // this thread's terms in this visit: `sweeps` passes over its ROUNDS steps
+#pragma unroll 1
         for (int i = 0; i < n_terms + 2; ++i) {
             // ================= stage C(i-2): the update =================
             if (i >= 2) {
