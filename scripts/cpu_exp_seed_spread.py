@@ -30,3 +30,7 @@ else:
     n, X, Y = orc.layout_2d(go, cfg, X, Y, n_streams=n_streams)
     far, loc = orc.path_stress_2d(go, X, Y, 4_000_000, 12345), orc.local_stress_2d(go, X, Y, 4_000_000, 12345)
 print(f"{name} dims={dims} seed={seed} n_streams={n_streams}: far {far:.6g} local {loc:.5g} updates {n} ({time.time() - t0:.0f} s)", flush=True)
+import json  # noqa: E402
+os.makedirs(os.path.join(ROOT, ".scratch", "scale_golden"), exist_ok=True)
+with open(os.path.join(ROOT, ".scratch", "scale_golden", "oracle_runs.jsonl"), "a") as f:   # picked up by make_scale_golden.py bands
+    f.write(json.dumps({"graph": name, "kind": "layout2d" if dims == 2 else "sort1d", "seed": seed, "n_streams": n_streams, "far": far, "local": loc}) + "\n")
