@@ -1336,7 +1336,10 @@ int pgsgd_engine_get_coords_2d_f32(pgsgd_engine* e, float* xy) {
 int pgsgd_engine_set_coords_1d(pgsgd_engine* e, const double* X) {
     if (!e) return fail(PGSGD_ERR_ARG, "set_coords_1d: NULL engine");
     CU(cudaSetDevice(e->device));
-    if (!e->d_x1d) { int rc = dev_alloc(e, &e->d_x1d, e->N); if (rc) return rc; }
+    if (!e->d_x1d) {   // one spare double: the pipelined kernel fetches 1D coordinates as aligned 16-byte pairs, so an odd N reads one past the end
+        int rc = dev_alloc(e, &e->d_x1d, e->N + 2); if (rc) return rc;
+        CU(cudaMemsetAsync(e->d_x1d + e->N, 0, 2 * sizeof(double), e->stream));
+    }
     const double* src = X ? X : e->h_x1d_default.data();
     CU(cudaMemcpyAsync(e->d_x1d, src, e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
