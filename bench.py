@@ -492,7 +492,7 @@ def main():
     line = {
         "metric": "M node-pair SGD updates/sec", "value": value, "unit": "M updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic" if args.workload in ("c4", "mid", "small", "tiny", "c5", "c5s") else "reference test graph (flattened fixture)",
+        "data": "synthetic" if args.workload in ("c4", "c4x", "mid", "small", "tiny", "c5", "c5s") else "reference test graph (flattened fixture)",
         "config": {"workload": args.workload, "description": desc, "nodes": g.N, "paths": g.P if not sharded else None, "steps_in_graph": job_steps,
                    "updates_per_step": U, "iter_max": iter_max, "timed_iterations": [W, W + K], "sampling": sampling_name, "batch": args.batch or "auto",
                    "l2_policy": "inputs larger than L2" if g.S * 16 > 126e6 else "L2-resident graph (plumbing config)",

@@ -18,6 +18,7 @@ PRESETS = {
     "small": (50_000, 16),
     "mid": (500_000, 90),             # ~6e5 nodes, ~4.5e7 steps  (0.7 GB of step records: beyond L2)
     "c4": (4_600_000, 90),            # ~5.5e6 nodes, ~4.2e8 steps (BASELINE config 4: 90-haplotype chr6-MHC scale)
+    "c4x": (5_500_000, 90),           # ~6.6e6 nodes, ~5.0e8 steps (the same generator at the upper reading of "~5e8 path steps")
 }
 
 
