@@ -519,7 +519,7 @@ def main():
     }
     # The reference's own CUDA kernel (src/cuda/layout.cu compiled unmodified for sm_100a): the reported baseline north_star's
     # ">= 10x" is judged against.  Measured LIVE on this GPU on the 'mid' graph of the same generator, next to our kernel on
-    # the same graph; the c4 number is a recorded measurement (its GFA ingest through odgi takes minutes).
+    # the same graph; the c4 number is a recorded measurement (its GFA ingest through odgi takes more than a minute).
     if world == 1 and not args.no_reference_cuda:
         try:  # context only: never a reason to lose the bench line
             rk = reference_cuda_kernel("mid")
@@ -534,13 +534,14 @@ def main():
                 ours = sm["term_updates"] / sm["seconds_iterations"] / 1e6
                 rk["ours_same_graph"] = {"value": ours, "unit": "M updates/s", "iterations": [3, 30]}
                 rk["ratio_ours_over_reference_kernel"] = ours / rk["value"]
-            rp = os.path.join(ROOT, "profiles", "r01_reference_cuda_kernel_c4.json")
+            rp = os.path.join(ROOT, "profiles", "r02_reference_cuda_kernel_c4.json")
             if args.workload == "c4" and os.path.exists(rp):
                 with open(rp) as f:
                     rec = json.loads([ln for ln in f.read().splitlines() if ln.startswith("{")][-1])
                 rk["recorded_c4"] = {"value": rec["updates_per_sec"] / 1e6, "unit": "M updates/s", "source": os.path.relpath(rp, ROOT),
                                      "ratio_ours_over_reference_kernel": value / (rec["updates_per_sec"] / 1e6),
-                                     "note": "recorded in round 1 on this pool (same binary, same graph); not re-run: 9 GB GFA + 73 s ingest"}
+                                     "note": "recorded in round 2 on this pool (scripts/gpu_runs/r02_call18.sh: same binary, same graph, 30 iterations; round 1 "
+                                             "recorded 8348 with 10); not re-run here: 4 GB of GFA and 72 s of odgi ingest"}
             line["reference_cuda_kernel"] = rk
         except Exception as ex:
             line["reference_cuda_kernel"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
