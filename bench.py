@@ -433,6 +433,7 @@ def main():
         gp = capi.FlatGraph(pin(g.node_len), pin(g.path_first_step), pin(g.step_node), None if g.step_rev is None else pin(g.step_rev),
                             None if g.step_pos is None else pin(g.step_pos))
         Xp, Yp = pin(X0), pin(Y0)
+        Xr, Yr = pin(np.zeros_like(X0)), pin(np.zeros_like(Y0))   # the caller's result buffers (the shim fills the caller's vectors)
         cfg_e = cfg
         barrier()
         t0 = time.time()
@@ -450,7 +451,7 @@ def main():
         t_up = time.time()
         st2 = e2.run_range(cfg_e, 2, 0, K)                  # the same number of steps
         t_run = time.time()
-        Xo, Yo = e2.get_coords_2d()                         # result download
+        Xo, Yo = e2.get_coords_2d(out=(Xr, Yr))             # result download into the caller's buffers
         t_down = time.time()
         phases = {"engine_create_flatten_upload_s": t_create - t0, "comm_attach_s": t_comm - t_create, "coords_upload_s": t_up - t_comm,
                   "run_call_s": t_run - t_up, "of_which_device_iterations_s": st2["seconds_iterations"], "coords_download_s": t_down - t_run}

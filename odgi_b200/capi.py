@@ -388,9 +388,15 @@ class Engine:
         assert X.size == 2 * self.g.N and Y.size == 2 * self.g.N
         _check(lib().pgsgd_engine_set_coords_2d(self._h, _ptr(X), _ptr(Y)))
 
-    def get_coords_2d(self):
-        X = np.empty(2 * self.g.N, dtype=np.float64)
-        Y = np.empty(2 * self.g.N, dtype=np.float64)
+    def get_coords_2d(self, out=None):
+        """(X, Y) as float64[2N]; `out` = caller-owned (X, Y) buffers to fill (what the odgi shim does with the caller's vectors)."""
+        if out is None:
+            X = np.empty(2 * self.g.N, dtype=np.float64)
+            Y = np.empty(2 * self.g.N, dtype=np.float64)
+        else:
+            X, Y = out
+            assert X.dtype == np.float64 and Y.dtype == np.float64 and X.size == 2 * self.g.N and Y.size == 2 * self.g.N
+            assert X.flags.c_contiguous and Y.flags.c_contiguous
         _check(lib().pgsgd_engine_get_coords_2d(self._h, _ptr(X), _ptr(Y)))
         return X, Y
 

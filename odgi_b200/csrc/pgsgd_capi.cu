@@ -171,7 +171,7 @@ struct pgsgd_engine {
     uint64_t trace_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::vector<double> h_x1d_default;  // cumulative bp of the node order (path_sgd.cpp:63-69)
+    std::vector<double> h_x1d_default;  // cumulative bp of the node order (path_sgd.cpp:63-69), built on first use
     bool have_2d = false, have_1d = false;
     uint64_t bytes = 0;
     double seconds_upload = 0;
@@ -1041,6 +1041,18 @@ static int engine_create_impl(const pgsgd_graph_view* g, int device, uint32_t* p
     }
 
     const double t0 = now_s();
+    // PGSGD_TIMING=1: phase times of this call as one JSON line on stderr (where does an engine's creation go?)
+    const bool timing = getenv("PGSGD_TIMING") != nullptr;
+    double t_prev = t0;
+    std::string timing_line;
+    auto mark = [&](const char* what) {
+        if (!timing) return;
+        const double t = now_s();
+        char buf[96];
+        snprintf(buf, sizeof buf, "%s\"%s_s\": %.4f", timing_line.empty() ? "" : ", ", what, t - t_prev);
+        timing_line += buf;
+        t_prev = t;
+    };
     pgsgd_engine* e = new pgsgd_engine();
     e->device = device;
     e->N = g->node_count; e->P = g->path_count; e->S = g->step_count;
@@ -1081,13 +1093,7 @@ static int engine_create_impl(const pgsgd_graph_view* g, int device, uint32_t* p
             }
         }
     }
-    // 1D default initialisation, kept on the host until asked for
-    e->h_x1d_default.resize(e->N);
-    {
-        uint64_t len = 0;
-        for (uint64_t r = 0; r < e->N; ++r) { e->h_x1d_default[r] = (double) len; len += g->node_len[r]; }
-    }
-
+    mark("host_prep");
     if ((rc = dev_alloc(e, &e->d_steps, e->S))) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_path_first, e->P + 1))) return bail(rc);
     if ((rc = dev_alloc(e, &e->d_delta, 1))) return bail(rc);
@@ -1142,12 +1148,15 @@ static int engine_create_impl(const pgsgd_graph_view* g, int device, uint32_t* p
                  (!g->step_rev || cudaMalloc(&d_sr, n) == cudaSuccess);
         }
         if (!ok) { cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_bad); return bail(fail(PGSGD_ERR_NOMEM, "cudaMalloc step staging failed")); }
+        mark("device_alloc");
         err = cudaMemsetAsync(d_bad, 0, sizeof(int), e->stream);
         if (err == cudaSuccess && !pre_sn) err = cudaMemcpyAsync(d_sn, g->step_node, e->S * 4, cudaMemcpyHostToDevice, e->stream);
         if (err == cudaSuccess && !pre_sn && g->step_rev) err = cudaMemcpyAsync(d_sr, g->step_rev, e->S, cudaMemcpyHostToDevice, e->stream);
+        if (timing) { cudaStreamSynchronize(e->stream); mark("step_upload"); }
         if (err == cudaSuccess) err = launch_flatten_on_device(e->d_steps, d_sn, d_sr, d_node_len, e->d_path_first, (uint32_t) e->P, (uint32_t) e->N, e->S, d_sp, d_bad, d_depth, e->stream);
         int bad = 0;
         if (err == cudaSuccess) err = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+        mark("flatten_on_device");
         if (err == cudaSuccess && !bad) err = launch_tile_repeats(d_sn, e->S, d_maxdup, e->stream);
         cudaFree(d_bad);
         if (!pre_sn) e->h2d_bytes += e->S * (4 + (g->step_rev ? 1 : 0));
@@ -1172,11 +1181,14 @@ static int engine_create_impl(const pgsgd_graph_view* g, int device, uint32_t* p
         if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
         e->max_path_bp = mb;
     }
+    mark("graph_statistics");
     cudaFree(d_maxdup);
     cudaFree(d_sn); cudaFree(d_sp); cudaFree(d_sr); cudaFree(d_depth);
     if (err != cudaSuccess) return cu_bail(err, "flatten-to-device");
     if ((err = cudaStreamSynchronize(e->stream)) != cudaSuccess) return cu_bail(err, "engine create sync");
+    mark("free_staging");
     e->seconds_upload = now_s() - t0;
+    if (timing) fprintf(stderr, "{\"pgsgd_engine_create\": {%s, \"total_s\": %.4f}}\n", timing_line.c_str(), e->seconds_upload);
     *out = e;
     return PGSGD_OK;
 }
@@ -1339,6 +1351,13 @@ int pgsgd_engine_set_coords_1d(pgsgd_engine* e, const double* X) {
     if (!e->d_x1d) {   // one spare double: the pipelined kernel fetches 1D coordinates as aligned 16-byte pairs, so an odd N reads one past the end
         int rc = dev_alloc(e, &e->d_x1d, e->N + 2); if (rc) return rc;
         CU(cudaMemsetAsync(e->d_x1d + e->N, 0, 2 * sizeof(double), e->stream));
+    }
+    if (!X && e->h_x1d_default.empty()) {   // default initialisation, built on first use: cumulative bp of the node order (path_sgd.cpp:63-69)
+        std::vector<uint32_t> len(e->N);
+        CU(cudaMemcpy(len.data(), e->d_node_len, e->N * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        e->h_x1d_default.resize(e->N);
+        uint64_t sum = 0;
+        for (uint64_t r = 0; r < e->N; ++r) { e->h_x1d_default[r] = (double) sum; sum += len[r]; }
     }
     const double* src = X ? X : e->h_x1d_default.data();
     CU(cudaMemcpyAsync(e->d_x1d, src, e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream));
