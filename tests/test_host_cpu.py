@@ -213,7 +213,11 @@ def test_bench_line_assembles_with_a_stand_in_engine(monkeypatch, capfd):
             return {"iterations_run": n, "kernel_launches": n, "term_updates": n * cfg.min_term_updates, "seconds_iterations": 1e-3 * n,
                     "h2d_bytes": 1000, "seconds_upload": 0.0}
 
-        def get_coords_2d(self):
+        def get_coords_2d(self, out=None):
+            if out is not None:
+                out[0][...] = self.X
+                out[1][...] = self.Y
+                return out
             return self.X, self.Y
 
         def close(self):
