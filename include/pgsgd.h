@@ -120,6 +120,10 @@ typedef struct pgsgd_config {
                                        per-instruction evict_last hints */
 #define PGSGD_FLAG_COORD_LD_FIRST  1024u /* experiments: coordinate loads with L2::evict_first (reds keep evict_last) */
 #define PGSGD_FLAG_COORD_LD_NORMAL 2048u /* experiments: coordinate loads with L2::evict_normal */
+#define PGSGD_FLAG_WINDOW_TILES 4096u /* experiments: tiles visited window by window — the tiles of ALL paths over one stretch of the node order
+                                         form a window; the resident CTAs work on ~grid/C windows at a time, C tiles (paths) of each (C from
+                                         PGSGD_WINDOW_C, default 3), so a window's coordinates are fetched into L2 once and reused by every
+                                         path that crosses it, while no node sees more than ~C concurrent tiles */
 #define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
 
 typedef struct pgsgd_stats {

@@ -197,6 +197,8 @@ struct pgsgd_engine {
     std::vector<void*> ipc_opened;
     std::vector<uint32_t> tile_mid_node;     // node of the middle step of every tile (tile -> owner rank)
     uint32_t* d_tile_list = nullptr;
+    uint32_t* d_window_list = nullptr;       // PGSGD_FLAG_WINDOW_TILES: all tiles, window by window (build_window_list)
+    uint64_t window_list_key = 0;            // (grid, C) the list was built for
     uint64_t my_tiles = 0, my_tile_steps = 0;
     // ---- path-sharded step records (pgsgd_engine_set_shard): this engine holds only some of the job's paths ----
     uint64_t shard_global_steps = 0;         // S of the whole job; 0 = the view is the whole graph
@@ -426,6 +428,45 @@ int peer_gather(pgsgd_engine* e, int dims) {
 }
 
 // iterations [iter_begin, iter_end) of the schedule cfg defines; iter_end == UINT64_MAX means "to the end"
+// PGSGD_FLAG_WINDOW_TILES: a visiting order of ALL tiles in which the CTAs resident at any time work on ~grid/C windows of the
+// node order with ~C tiles (paths) of each.  Window = depth (= S/N rounded) consecutive tiles of the tile list sorted by the
+// node in the tile's middle, i.e. roughly the tiles of all paths over one tile length of the node order.  The windows are
+// visited in a seeded random order, the tiles inside a window likewise; a group of grid/C windows is emitted round-robin.
+int build_window_list(pgsgd_engine* e, unsigned grid, unsigned C, uint64_t seed) {
+    const uint64_t key = ((uint64_t) grid << 32) | C;
+    if (e->d_window_list && e->window_list_key == key) return PGSGD_OK;
+    const uint64_t nt = e->tile_mid_node.size();
+    std::vector<uint32_t> T(nt);
+    for (uint64_t t = 0; t < nt; ++t) T[t] = (uint32_t) t;
+    std::stable_sort(T.begin(), T.end(), [&](uint32_t a, uint32_t b) { return e->tile_mid_node[a] < e->tile_mid_node[b]; });
+    const uint64_t D = std::max<uint64_t>(1, (e->S + e->N / 2) / e->N);
+    const uint64_t nw = (nt + D - 1) / D, A = std::max<uint64_t>(1, grid / std::max(1u, C));
+    uint64_t sm = seed ^ 0x5851f42d4c957f2dULL;
+    auto shuffle = [&](uint32_t* a, uint64_t n) {
+        for (uint64_t i = n; i > 1; --i) { const uint64_t j = splitmix64_next(sm) % i; std::swap(a[i - 1], a[j]); }
+    };
+    for (uint64_t w = 0; w < nw; ++w) shuffle(T.data() + w * D, std::min(D, nt - w * D));
+    std::vector<uint32_t> worder(nw);
+    for (uint64_t w = 0; w < nw; ++w) worder[w] = (uint32_t) w;
+    shuffle(worder.data(), nw);
+    std::vector<uint32_t> out;
+    out.reserve(nt);
+    for (uint64_t g0 = 0; g0 < nw; g0 += A) {
+        const uint64_t g1 = std::min(nw, g0 + A);
+        for (uint64_t r = 0; r < D; ++r)
+            for (uint64_t k = g0; k < g1; ++k) {
+                const uint64_t idx = (uint64_t) worder[k] * D + r;
+                if (idx < nt) out.push_back(T[idx]);
+            }
+    }
+    if (out.size() != nt) return fail(PGSGD_ERR_STATE, "window list: %llu of %llu tiles", (unsigned long long) out.size(), (unsigned long long) nt);
+    if (!e->d_window_list) { int rc = dev_alloc(e, &e->d_window_list, nt ? nt : 1); if (rc) return rc; }
+    CU(cudaMemcpyAsync(e->d_window_list, out.data(), nt * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->window_list_key = key;
+    return PGSGD_OK;
+}
+
 int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_begin, uint64_t iter_end, pgsgd_stats* stats) {
     int rc = check_config(cfg);
     if (rc) return rc;
@@ -705,6 +746,15 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
         if (rc) return rc;
     }
 
+    const bool window_order = (cfg->flags & PGSGD_FLAG_WINDOW_TILES) && tile_mode && tile2 && !peer && tile_steps == TILE_STEPS;
+    if (window_order) {
+        unsigned C = 3;
+        if (const char* sv = getenv("PGSGD_WINDOW_C")) C = (unsigned) atoi(sv);
+        if (C < 1 || C > 64) C = 3;
+        rc = build_window_list(e, (unsigned) shape.grid * (unsigned) t2.visit_nranks, C, cfg->seed);
+        if (rc) return rc;
+        t2.tile_list = e->d_window_list;
+    }
     if ((cfg->flags & PGSGD_FLAG_L2_WINDOW) && tile_mode && tile2 && !peer) {
         // pin the coordinate array in L2: persisting carve-out + access-policy window on this stream (reset after the loop)
         cudaDeviceProp prop;
@@ -740,7 +790,7 @@ int run_phase(pgsgd_engine* e, const pgsgd_config* cfg, int dims, uint64_t iter_
             // (experiments): path order from a random offset
             const uint64_t nt = tile2 ? t2.n_tiles : p.n_tiles;
             uint64_t sm = cfg->seed ^ (0x9e3779b97f4a7c15ULL * (iter + 1));
-            const bool sweep = tile2 && (cfg->flags & PGSGD_FLAG_SWEEP_TILES);
+            const bool sweep = tile2 && ((cfg->flags & PGSGD_FLAG_SWEEP_TILES) || window_order);   // window order: the list IS the order
             for (int k = 0; k < 16; ++k) {
                 const uint64_t key = splitmix64_next(sm);
                 p.perm_mul[k] = t2.perm_mul[k] = sweep ? 0 : 1;
@@ -1265,7 +1315,7 @@ void pgsgd_engine_destroy(pgsgd_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     for (void* q : e->ipc_opened) cudaIpcCloseMemHandle(q);
-    cudaFree(e->d_xy_part); cudaFree(e->d_x1d_part); cudaFree(e->d_tile_list);
+    cudaFree(e->d_xy_part); cudaFree(e->d_x1d_part); cudaFree(e->d_tile_list); cudaFree(e->d_window_list);
     if (e->comm && !e->comm_cached) ncclCommDestroy(e->comm);
     cudaFree(e->d_steps); cudaFree(e->d_path_first); cudaFree(e->d_node_len); cudaFree(e->d_xy); cudaFree(e->d_xy_prev); cudaFree(e->d_x1d);
     cudaFree(e->d_trace); cudaFree(e->d_trace_count);
