@@ -8,6 +8,7 @@
 #include <fstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 
 #include "pgsgd_flatten.hpp"
@@ -132,9 +133,6 @@ inline void scan_gfa(const std::string& path, GfaIndex& ix) {
     void* m = mmap(nullptr, ix.bytes, PROT_READ, MAP_PRIVATE, ix.fd, 0);
     if (m == MAP_FAILED) throw std::runtime_error("cannot map " + path);
     ix.text = (const char*) m;
-    madvise(m, ix.bytes, MADV_SEQUENTIAL);
-    std::vector<std::pair<uint64_t, uint32_t>> segs;
-    uint64_t max_id = 0;
     auto field_end_of = [](const char* b, const char* line_end) {   // next tab, or the end of the line (without a CR)
         const char* t = (const char*) std::memchr(b, '\t', (size_t) (line_end - b));
         const char* e = t ? t : line_end;
@@ -150,48 +148,95 @@ inline void scan_gfa(const std::string& path, GfaIndex& ix) {
         }
         return id != 0;
     };
-    const char* p = ix.text;
+    // The file is cut into pieces at line starts and the pieces are scanned by host threads (a 4 GB GFA is two memchr passes
+    // over 4 GB: ~1 s on one core); the pieces' findings are concatenated in file order.
+    struct Piece {
+        std::vector<std::pair<uint64_t, uint32_t>> segs;
+        uint64_t max_id = 0;
+        std::vector<std::string> path_names;
+        std::vector<uint64_t> field_begin, field_end;
+        std::vector<std::pair<uint32_t, uint32_t>> links;
+        bool not_optimized = false;
+    };
+    const char* const text = ix.text;
     const char* const end = ix.text + ix.bytes;
-    while (p < end) {
-        const char* nl = (const char*) std::memchr(p, '\n', (size_t) (end - p));
-        const char* le = nl ? nl : end;
-        if (le - p >= 2 && p[1] == '\t') {
-            if (p[0] == 'S') {
-                const char* b = p + 2;
-                const char* e = field_end_of(b, le);
-                uint64_t id;
-                if (!parse_id(b, e, id)) throw std::runtime_error("[odgi::layout] error: the graph is not optimized. Please run 'odgi sort' using -O, --optimize.");
-                const char* sb2 = e < le ? e + 1 : le;
-                const char* se = field_end_of(sb2, le);
-                uint32_t len = (uint32_t) (se - sb2);
-                if (len == 1 && *sb2 == '*') {
-                    len = 0;
-                    const char* tag = se;
-                    while (tag + 5 < le) { if (!std::memcmp(tag, "LN:i:", 5)) { len = (uint32_t) std::strtoull(tag + 5, nullptr, 10); break; } ++tag; }
+    unsigned n_pieces = std::thread::hardware_concurrency();
+    if (n_pieces == 0) n_pieces = 1;
+    if (n_pieces > 32) n_pieces = 32;
+    if (ix.bytes < (64u << 20)) n_pieces = 1;
+    if (const char* sv = std::getenv("PGSGD_SCAN_THREADS")) { const int v = std::atoi(sv); if (v >= 1 && v <= 256) n_pieces = (unsigned) v; }
+    std::vector<const char*> cut(n_pieces + 1, end);
+    cut[0] = text;
+    for (unsigned k = 1; k < n_pieces; ++k) {
+        const char* q = text + (ix.bytes / n_pieces) * k;
+        if (q < cut[k - 1]) q = cut[k - 1];
+        const char* nl = q < end ? (const char*) std::memchr(q, '\n', (size_t) (end - q)) : nullptr;
+        cut[k] = nl ? nl + 1 : end;
+    }
+    std::vector<Piece> pieces(n_pieces);
+    auto scan_piece = [&](unsigned k) {
+        Piece& pc = pieces[k];
+        const char* p = cut[k];
+        const char* const pend = cut[k + 1];
+        while (p < pend) {
+            const char* nl = (const char*) std::memchr(p, '\n', (size_t) (end - p));
+            const char* le = nl ? nl : end;
+            if (le - p >= 2 && p[1] == '\t') {
+                if (p[0] == 'S') {
+                    const char* b = p + 2;
+                    const char* e = field_end_of(b, le);
+                    uint64_t id;
+                    if (!parse_id(b, e, id)) { pc.not_optimized = true; return; }
+                    const char* sb2 = e < le ? e + 1 : le;
+                    const char* se = field_end_of(sb2, le);
+                    uint32_t len = (uint32_t) (se - sb2);
+                    if (len == 1 && *sb2 == '*') {
+                        len = 0;
+                        const char* tag = se;
+                        while (tag + 5 < le) { if (!std::memcmp(tag, "LN:i:", 5)) { len = (uint32_t) std::strtoull(tag + 5, nullptr, 10); break; } ++tag; }
+                    }
+                    pc.segs.emplace_back(id, len);
+                    if (id > pc.max_id) pc.max_id = id;
+                } else if (p[0] == 'P') {
+                    const char* b = p + 2;
+                    const char* e = field_end_of(b, le);
+                    pc.path_names.emplace_back(b, (size_t) (e - b));
+                    const char* fb = e < le ? e + 1 : le;
+                    const char* fe = field_end_of(fb, le);
+                    pc.field_begin.push_back((uint64_t) (fb - text));
+                    pc.field_end.push_back((uint64_t) (fe - text));
+                } else if (p[0] == 'L') {
+                    const char* b = p + 2;
+                    const char* e = field_end_of(b, le);
+                    uint64_t ia = 0, ib = 0;
+                    const bool oka = parse_id(b, e, ia);
+                    const char* o = e < le ? e + 1 : le;              // orientation field
+                    const char* oe = field_end_of(o, le);
+                    const char* b2 = oe < le ? oe + 1 : le;
+                    const char* e2 = field_end_of(b2, le);
+                    if (oka && parse_id(b2, e2, ib)) pc.links.emplace_back((uint32_t) (ia - 1), (uint32_t) (ib - 1));
                 }
-                segs.emplace_back(id, len);
-                if (id > max_id) max_id = id;
-            } else if (p[0] == 'P') {
-                const char* b = p + 2;
-                const char* e = field_end_of(b, le);
-                ix.path_names.emplace_back(b, (size_t) (e - b));
-                const char* fb = e < le ? e + 1 : le;
-                const char* fe = field_end_of(fb, le);
-                ix.field_begin.push_back((uint64_t) (fb - ix.text));
-                ix.field_end.push_back((uint64_t) (fe - ix.text));
-            } else if (p[0] == 'L') {
-                const char* b = p + 2;
-                const char* e = field_end_of(b, le);
-                uint64_t ia = 0, ib = 0;
-                const bool oka = parse_id(b, e, ia);
-                const char* o = e < le ? e + 1 : le;              // orientation field
-                const char* oe = field_end_of(o, le);
-                const char* b2 = oe < le ? oe + 1 : le;
-                const char* e2 = field_end_of(b2, le);
-                if (oka && parse_id(b2, e2, ib)) ix.links.emplace_back((uint32_t) (ia - 1), (uint32_t) (ib - 1));
             }
+            p = nl ? nl + 1 : end;
         }
-        p = nl ? nl + 1 : end;
+    };
+    if (n_pieces == 1) {
+        scan_piece(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned k = 0; k < n_pieces; ++k) th.emplace_back(scan_piece, k);
+        for (auto& t : th) t.join();
+    }
+    std::vector<std::pair<uint64_t, uint32_t>> segs;
+    uint64_t max_id = 0;
+    for (Piece& pc : pieces) {
+        if (pc.not_optimized) throw std::runtime_error("[odgi::layout] error: the graph is not optimized. Please run 'odgi sort' using -O, --optimize.");
+        segs.insert(segs.end(), pc.segs.begin(), pc.segs.end());
+        if (pc.max_id > max_id) max_id = pc.max_id;
+        for (auto& nm : pc.path_names) ix.path_names.emplace_back(std::move(nm));
+        ix.field_begin.insert(ix.field_begin.end(), pc.field_begin.begin(), pc.field_begin.end());
+        ix.field_end.insert(ix.field_end.end(), pc.field_end.begin(), pc.field_end.end());
+        ix.links.insert(ix.links.end(), pc.links.begin(), pc.links.end());
     }
     if (max_id != segs.size()) throw std::runtime_error("[odgi::layout] error: the graph is not optimized. Please run 'odgi sort' using -O, --optimize.");
     ix.node_len.assign(max_id, 0);

@@ -590,6 +590,25 @@ int main_sort(int argc, char** argv) {
     return 0;
 }
 
+// pgsgd scan -i g.gfa : what the line scan of the device ingest finds (counts and checksums; PGSGD_SCAN_THREADS = host threads)
+int main_scan(int argc, char** argv) {
+    std::string in;
+    for (int i = 2; i + 1 < argc; i += 2) if (!std::strcmp(argv[i], "-i")) in = argv[i + 1];
+    if (in.empty()) { std::cerr << "usage: pgsgd scan -i g.gfa" << std::endl; return 1; }
+    pgsgd::GfaIndex ix;
+    const auto t0 = std::chrono::steady_clock::now();
+    try { pgsgd::scan_gfa(in, ix); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    uint64_t h = 1469598103934665603ull, bp = 0;
+    auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+    for (uint32_t l : ix.node_len) { mix(l); bp += l; }
+    for (size_t p = 0; p < ix.field_begin.size(); ++p) { mix(ix.field_begin[p]); mix(ix.field_end[p]); for (char c : ix.path_names[p]) mix((unsigned char) c); }
+    for (auto& l : ix.links) { mix(l.first); mix(l.second); }
+    std::cout << "{\"nodes\": " << ix.node_len.size() << ", \"paths\": " << ix.field_begin.size() << ", \"links\": " << ix.links.size() << ", \"bp\": " << bp
+              << ", \"fnv\": " << h << ", \"seconds\": " << dt << "}" << std::endl;
+    return 0;
+}
+
 // pgsgd flatten -i g.gfa -o g.arr : the flattened graph as a PGSGDARR container (what bench.py / the tests load)
 int main_flatten(int argc, char** argv) {
     std::string in, out;
@@ -682,6 +701,7 @@ int main(int argc, char** argv) {
     if (sub == "sort") return main_sort(argc, argv);
     if (sub == "flatten") return main_flatten(argc, argv);
     if (sub == "lay") return main_lay(argc, argv);
+    if (sub == "scan") return main_scan(argc, argv);
     if (sub == "init") return main_init(argc, argv);
     std::cerr << "unknown subcommand " << sub << " (layout, sort, flatten, lay, init)" << std::endl;
     return 1;

@@ -295,3 +295,25 @@ def test_sort_target_paths_and_use_paths_preparation(golden_graphs, tmp_path):
     r = subprocess.run([CLI, "sort", "-i", str(gfa), "-o", str(tmp_path / "o.txt"), "-Y", "-H", str(tmp_path / "dup.txt"), "--prepared-out", str(prep)],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "duplicated path names" in r.stderr
+
+
+def test_gfa_line_scan_is_the_same_for_any_number_of_pieces(golden_graphs, tmp_path):
+    """the device ingest's host half (scan_gfa: line boundaries, S lengths, P fields) cuts the file into pieces for host threads:
+    what it finds must not depend on the cuts (PGSGD_SCAN_THREADS forces the piece count, also on a small file)"""
+    import json
+    g = odgi_b200.graph_from_arrays(golden_graphs["DRB1-3123"])
+    gfa = tmp_path / "g.gfa"
+    synth.write_gfa(g, str(gfa))
+    outs = []
+    for t in ("1", "2", "5", "64"):
+        r = subprocess.run([CLI, "scan", "-i", str(gfa)], capture_output=True, text=True, env={**os.environ, "PGSGD_SCAN_THREADS": t})
+        assert r.returncode == 0, r.stderr
+        d = json.loads(r.stdout)
+        d.pop("seconds")
+        outs.append(d)
+    assert all(o == outs[0] for o in outs[1:]), outs
+    assert outs[0]["nodes"] == g.N and outs[0]["paths"] == g.P and outs[0]["bp"] == int(g.node_len.sum())
+    bad = tmp_path / "bad.gfa"
+    bad.write_text("H\tVN:Z:1.0\nS\t1\tACGT\nS\t3\tA\nP\tp\t1+,3+\t*\n")
+    r = subprocess.run([CLI, "scan", "-i", str(bad)], capture_output=True, text=True, env={**os.environ, "PGSGD_SCAN_THREADS": "3"})
+    assert r.returncode == 1 and "not optimized" in r.stderr
