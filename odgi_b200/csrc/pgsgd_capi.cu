@@ -1247,6 +1247,60 @@ int pgsgd_engine_create(const pgsgd_graph_view* g, int device, pgsgd_engine** ou
     return engine_create_impl(g, device, nullptr, nullptr, nullptr, out);
 }
 
+// The step lists live in pageable (mmap'ed) host memory: a plain cudaMemcpy from there goes through the driver's own staging at
+// 3-4 GB/s.  Here host threads copy 16 MB chunks of the packed destination range into their own pinned buffers (two each) and
+// send them on their own streams, so that the host copies, and the PCIe transfers of different chunks, overlap.
+static cudaError_t upload_fields_staged(char* d_text, const char* text, const uint64_t* field_begin, const std::vector<uint64_t>& packed_begin,
+                                        uint64_t path_count, int device, cudaStream_t stream) {
+    const uint64_t n_bytes = packed_begin[path_count];
+    if (n_bytes == 0) return cudaSuccess;
+    uint64_t CH = 16ull << 20;
+    if (const char* sv = getenv("PGSGD_UPLOAD_CHUNK")) { const long long v = atoll(sv); if (v >= 256 && v <= (1ll << 30)) CH = (uint64_t) v; }   // tests: many chunks on a small file
+    const uint64_t n_chunks = (n_bytes + CH - 1) / CH;
+    unsigned T = std::thread::hardware_concurrency();
+    T = T >= 16 ? 6 : (T >= 8 ? 4 : 2);
+    if (const char* sv = getenv("PGSGD_UPLOAD_THREADS")) { const int v = atoi(sv); if (v >= 1 && v <= 32) T = (unsigned) v; }
+    if (T > n_chunks) T = (unsigned) n_chunks;
+    std::vector<cudaError_t> err(T, cudaSuccess);
+    auto worker = [&](unsigned t) {
+        cudaError_t e = cudaSetDevice(device);
+        char* buf[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaStream_t st = nullptr;
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+            e = cudaHostAlloc((void**) &buf[b], CH, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+        }
+        unsigned k = 0;
+        for (uint64_t c = t; c < n_chunks && e == cudaSuccess; c += T, ++k) {
+            const int b = (int) (k & 1);
+            if (k >= 2) e = cudaEventSynchronize(ev[b]);   // the transfer that last used this buffer is done
+            if (e != cudaSuccess) break;
+            const uint64_t lo = c * CH, hi = std::min(n_bytes, lo + CH);
+            // fields overlapping [lo, hi): packed_begin is sorted
+            uint64_t p = (uint64_t) (std::upper_bound(packed_begin.begin(), packed_begin.end(), lo) - packed_begin.begin()) - 1;
+            for (; p < path_count && packed_begin[p] < hi; ++p) {
+                const uint64_t a = std::max(lo, packed_begin[p]), z = std::min(hi, packed_begin[p + 1]);
+                if (z > a) memcpy(buf[b] + (a - lo), text + field_begin[p] + (a - packed_begin[p]), z - a);
+            }
+            e = cudaMemcpyAsync(d_text + lo, buf[b], hi - lo, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+        }
+        if (st) { const cudaError_t e2 = cudaStreamSynchronize(st); if (e == cudaSuccess) e = e2; }
+        for (int b = 0; b < 2; ++b) { if (ev[b]) cudaEventDestroy(ev[b]); if (buf[b]) cudaFreeHost(buf[b]); }
+        if (st) cudaStreamDestroy(st);
+        err[t] = e;
+    };
+    cudaError_t e0 = cudaStreamSynchronize(stream);   // the memset of the padding precedes the copies
+    if (e0 != cudaSuccess) return e0;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t) th.emplace_back(worker, t);
+    for (auto& x : th) x.join();
+    for (cudaError_t e : err) if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
 int pgsgd_engine_create_from_gfa_paths(const uint32_t* node_len, uint64_t node_count, const char* text, const uint64_t* field_begin,
                                        const uint64_t* field_end, uint64_t path_count, int device, pgsgd_engine** out) {
     if (!node_len || !out || (path_count && (!text || !field_begin || !field_end))) return fail(PGSGD_ERR_ARG, "create_from_gfa_paths: NULL argument");
@@ -1276,9 +1330,7 @@ int pgsgd_engine_create_from_gfa_paths(const uint32_t* node_len, uint64_t node_c
     if (ce == cudaSuccess) ce = cudaMemsetAsync(d_text + (n_alloc - 32 < n_alloc ? n_alloc - 32 : 0), 0, n_alloc < 32 ? n_alloc : 32, stream);
     if (ce == cudaSuccess) ce = cudaMalloc(&d_fb, (path_count + 1) * sizeof(uint64_t));
     if (ce == cudaSuccess) ce = cudaMalloc(&d_pf, (path_count + 1) * sizeof(uint64_t));
-    for (uint64_t p = 0; p < path_count && ce == cudaSuccess; ++p)
-        if (field_end[p] > field_begin[p])
-            ce = cudaMemcpyAsync(d_text + packed_begin[p], text + field_begin[p], field_end[p] - field_begin[p], cudaMemcpyHostToDevice, stream);
+    if (ce == cudaSuccess) ce = upload_fields_staged(d_text, text, field_begin, packed_begin, path_count, device, stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_fb, packed_begin.data(), (path_count + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream);
     uint64_t S = 0;
     int bad = 0;

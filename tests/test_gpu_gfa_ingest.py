@@ -52,6 +52,25 @@ def test_engine_from_gfa_text_on_a_graph_beyond_one_chunk(tmp_path):
         assert e1.local_stress(2, 400_000, 4) == e2.local_stress(2, 400_000, 4)
 
 
+def test_staged_text_upload_with_many_chunks_and_threads(tmp_path, monkeypatch):
+    """the step lists go host -> device through pinned staging buffers filled by host threads, 16 MB chunks of the packed range;
+    PGSGD_UPLOAD_CHUNK / PGSGD_UPLOAD_THREADS force many chunks (boundaries inside fields and between them) on a small file"""
+    g = synth.generate(20_000, 7, seed=4, inv_per_mbp=30.0, dup_per_mbp=10.0)
+    gfa = tmp_path / "g.gfa"
+    synth.write_gfa(g, str(gfa))
+    X0, Y0 = odgi_b200.layout_init(g, seed=1)
+    with odgi_b200.Engine(g) as e1:
+        e1.set_coords_2d(X0, Y0)
+        want = (e1.path_stress(2, 300_000, 3), e1.local_stress(2, 300_000, 4))
+    for chunk, threads in (("4096", "3"), ("1000", "5"), ("65536", "1")):
+        monkeypatch.setenv("PGSGD_UPLOAD_CHUNK", chunk)
+        monkeypatch.setenv("PGSGD_UPLOAD_THREADS", threads)
+        with odgi_b200.Engine.from_gfa(str(gfa)) as e2:
+            assert e2.graph_stats()["step_count"] == g.S
+            e2.set_coords_2d(X0, Y0)
+            assert (e2.path_stress(2, 300_000, 3), e2.local_stress(2, 300_000, 4)) == want, (chunk, threads)
+
+
 def test_engine_from_gfa_text_rejects_bad_ids(tmp_path):
     bad = tmp_path / "bad.gfa"
     bad.write_text("H\tVN:Z:1.0\nS\t1\tACGT\nS\t2\tA\nP\tx\t1+,3+\t*\n")   # node 3 does not exist
