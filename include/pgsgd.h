@@ -23,7 +23,7 @@ extern "C" {
 
 /* Bumped whenever a struct below changes size or meaning.  Callers compare PGSGD_VERSION (what they were compiled against)
  * with pgsgd_version() (what they loaded) before the first call: a stale binary would otherwise pass short structs. */
-#define PGSGD_VERSION 104 /* 0.1.4 */
+#define PGSGD_VERSION 105 /* 0.1.4 */
 
 typedef enum pgsgd_status {
     PGSGD_OK = 0,
@@ -147,6 +147,8 @@ typedef struct pgsgd_engine pgsgd_engine;   /* opaque: device-resident graph + c
 const char* pgsgd_last_error(void);
 int         pgsgd_version(void);
 int         pgsgd_device_count(void);       /* 0 when no usable CUDA device */
+int         pgsgd_device_warmup(int device); /* creates the device's CUDA context now (~0.2-0.3 s) instead of inside the first engine call: a caller
+                                                with host-side work to do first (reading a file) runs this on another thread meanwhile */
 
 /* ---- one-shot entry points (host buffers in, host buffers out) ------------------------------------
  * 2D: replaces  void cuda::gpu_layout(layout_config_t, const odgi::graph_t&, std::vector<std::atomic<double>>& X,

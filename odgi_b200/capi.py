@@ -60,7 +60,7 @@ class StatsC(C.Structure):
 
 # every symbol include/pgsgd.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "pgsgd_last_error", "pgsgd_version", "pgsgd_device_count", "pgsgd_layout_2d", "pgsgd_sort_1d", "pgsgd_layout_2d_multi",
+    "pgsgd_last_error", "pgsgd_version", "pgsgd_device_count", "pgsgd_device_warmup", "pgsgd_layout_2d", "pgsgd_sort_1d", "pgsgd_layout_2d_multi",
     "pgsgd_sort_1d_multi",
     "pgsgd_engine_create", "pgsgd_engine_create_from_gfa_paths", "pgsgd_engine_graph_stats", "pgsgd_engine_destroy", "pgsgd_engine_device", "pgsgd_engine_device_bytes",
     "pgsgd_engine_set_coords_2d", "pgsgd_engine_get_coords_2d", "pgsgd_engine_set_coords_2d_f32",
@@ -76,7 +76,7 @@ class GoodnessC(C.Structure):
                 ("num_penalties_diff_orientation", C.c_uint64)]
 
 
-ABI_VERSION = 104  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
+ABI_VERSION = 105  # PGSGD_VERSION of the include/pgsgd.h these ctypes structs mirror
 _lib = None
 
 
@@ -114,6 +114,7 @@ def lib():
             raise PgsgdError(-2, f"{LIB_PATH} has ABI {L.pgsgd_version()}, this binding mirrors include/pgsgd.h version {ABI_VERSION}: "
                                  "rebuild with `python -m odgi_b200.build`")
         L.pgsgd_device_count.restype = i32
+        L.pgsgd_device_warmup.argtypes = [i32]
         L.pgsgd_layout_2d.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), vp, vp, C.POINTER(StatsC)]
         L.pgsgd_sort_1d.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), vp, i32, vp, C.POINTER(StatsC)]
         L.pgsgd_layout_2d_multi.argtypes = [C.POINTER(GraphView), C.POINTER(ConfigC), i32, i32, vp, vp, C.POINTER(StatsC)]

@@ -1039,6 +1039,15 @@ int pgsgd_device_count(void) {
     return n;
 }
 
+int pgsgd_device_warmup(int device) {
+    const int ndev = pgsgd_device_count();
+    if (ndev == 0) return fail(PGSGD_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(PGSGD_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    CU(cudaFree(nullptr));
+    return PGSGD_OK;
+}
+
 int pgsgd_schedule(const pgsgd_config* cfg, double* etas_out) {
     if (!cfg || !etas_out || cfg->iter_max == 0) return fail(PGSGD_ERR_ARG, "pgsgd_schedule: bad arguments");
     std::vector<double> etas = build_schedule(*cfg);

@@ -17,6 +17,7 @@
 #include <random>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gfa_lite.hpp"
@@ -243,25 +244,31 @@ bool read_path_list(const std::string& file, const pgsgd::FlatGraph& fg, bool re
 int layout_device_ingest(const Args& a) {
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
+    std::thread warm([]() { pgsgd_device_warmup(0); });   // the CUDA context comes up while the host reads the file
     pgsgd::GfaIndex ix;
-    try { pgsgd::scan_gfa(a.str("idx"), ix); } catch (const std::exception& e) { std::cerr << e.what() << std::endl; return 1; }
+    try { pgsgd::scan_gfa(a.str("idx"), ix); } catch (const std::exception& e) { warm.join(); std::cerr << e.what() << std::endl; return 1; }
+    warm.join();
     const double t_scan = now();
+    pgsgd::FlatGraph fg;               // node table only: what the defaults and the initialisation read
+    fg.node_len = ix.node_len;
+    const uint64_t N = fg.node_len.size();
+    std::vector<double> X, Y;
+    bool init_ok = false;              // the initial layout needs the node table only: drawn while the device parses the paths
+    std::thread init([&]() { init_ok = init_layout(fg, a.str("layout-initialization", "d")[0], a.has("init-seed"), a.u64("init-seed", 0), X, Y); });
     pgsgd_engine* e = nullptr;
-    if (pgsgd_engine_create_from_gfa_paths(ix.node_len.data(), ix.node_len.size(), ix.text, ix.field_begin.data(), ix.field_end.data(),
-                                           ix.field_begin.size(), 0, &e) != PGSGD_OK) {
+    const int rc_create = pgsgd_engine_create_from_gfa_paths(ix.node_len.data(), ix.node_len.size(), ix.text, ix.field_begin.data(), ix.field_end.data(),
+                                                             ix.field_begin.size(), 0, &e);
+    const double t_engine = now();
+    init.join();
+    if (rc_create != PGSGD_OK) {
         std::cerr << "[odgi::layout] error: " << pgsgd_last_error() << std::endl;
         return 1;
     }
-    const double t_engine = now();
     PathStats ps;
     pgsgd_engine_graph_stats(e, &ps.sum_steps, &ps.max_steps, &ps.max_bp, nullptr);
-    pgsgd::FlatGraph fg;               // node table only: what the defaults and the initialisation read
-    fg.node_len = ix.node_len;
     pgsgd_config c;
     common_config(a, fg, false, c, &ps);
-    const uint64_t N = fg.node_len.size();
-    std::vector<double> X, Y;
-    int rc = init_layout(fg, a.str("layout-initialization", "d")[0], a.has("init-seed"), a.u64("init-seed", 0), X, Y) ? 0 : 1;
+    int rc = init_ok ? 0 : 1;
     pgsgd_stats st;
     std::memset(&st, 0, sizeof(st));
     if (!rc) rc = pgsgd_engine_set_coords_2d(e, X.data(), Y.data());
