@@ -124,6 +124,8 @@ typedef struct pgsgd_config {
                                          form a window; the resident CTAs work on ~grid/C windows at a time, C tiles (paths) of each (C from
                                          PGSGD_WINDOW_C, default 3), so a window's coordinates are fetched into L2 once and reused by every
                                          path that crosses it, while no node sees more than ~C concurrent tiles */
+#define PGSGD_FLAG_X_TILE_REPLACE 8192u  /* experiments (tile-sampling bias): tiles drawn with replacement instead of one bijection per pass */
+#define PGSGD_FLAG_X_STEP_RANDOM 16384u  /* experiments: the first step of a term drawn with replacement inside the staged tile instead of every step once */
 #define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
 
 typedef struct pgsgd_stats {

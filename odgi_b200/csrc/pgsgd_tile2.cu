@@ -124,6 +124,11 @@ __device__ __forceinline__ void make_visit(const Tile2Params& p, FirstPtr first,
     out->sweeps = pass < p.full_passes ? p.sweeps : ((pass == p.full_passes && p.rem_sweeps) ? p.rem_sweeps : 1u);
     out->pad = 0;
     uint64_t t_idx = p.perm_mul[pass & 15] ? tile_perm(i, p.n_tiles, p.perm_add[pass & 15]) : (i + p.perm_add[pass & 15]) % p.n_tiles;
+    if (p.flags & 8192u) {   // experiments: tiles drawn WITH replacement (a hash of the visit number) instead of a bijection per pass
+        uint64_t z = (v + 1) * 0x9e3779b97f4a7c15ULL + p.perm_add[pass & 15];
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL; z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL; z ^= z >> 31;
+        t_idx = __umul64hi(z, p.n_tiles);
+    }
     if (p.tile_list) t_idx = p.tile_list[t_idx];   // peer phases: the k-th tile this rank owns
     const uint64_t base = t_idx * (uint64_t) tile_steps;
     const uint64_t end = base + tile_steps <= p.step_count ? base + tile_steps : p.step_count;
@@ -374,9 +379,11 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
             }
             // ================= stage A(i): first step from the tile, partner draw, far record on its way =================
             if (i < n_terms) {
-                const uint32_t j = (uint32_t) (i % ROUNDS) * 256 + threadIdx.x;
+                uint32_t j = (uint32_t) (i % ROUNDS) * 256 + threadIdx.x;
                 b_rb = 0;
                 if (j < vi.terms && j < vi.n_in_tile) {
+                    if (p.flags & 16384u)   // experiments: the first step drawn WITH replacement inside the tile instead of every staged step once
+                        j = __umulhi((uint32_t) (xoshiro_next(g) >> 11), min(vi.terms, vi.n_in_tile));
                     uint64_t f = vi.f;
                     uint32_t count = vi.count, s_rank = rank0 + j;
                     if (!vi.one_path) {
