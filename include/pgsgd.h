@@ -126,6 +126,8 @@ typedef struct pgsgd_config {
                                          path that crosses it, while no node sees more than ~C concurrent tiles */
 #define PGSGD_FLAG_X_TILE_REPLACE 8192u  /* experiments (tile-sampling bias): tiles drawn with replacement instead of one bijection per pass */
 #define PGSGD_FLAG_X_STEP_RANDOM 16384u  /* experiments: the first step of a term drawn with replacement inside the staged tile instead of every step once */
+#define PGSGD_FLAG_X_SEGMENT_RANDOM 32768u /* experiments: every warp draws a 32-step segment of the staged tile with replacement */
+#define PGSGD_FLAG_X_STEP_SCRAMBLE 65536u /* experiments: every staged step once, neighbouring lanes far apart in the tile */
 #define PGSGD_FLAG_SUM_DELTAS   2u  /* multi-GPU: all-reduce SUM of per-iteration displacements instead of the MEAN of coordinates */
 
 typedef struct pgsgd_stats {

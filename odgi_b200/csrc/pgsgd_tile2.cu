@@ -384,6 +384,16 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
                 if (j < vi.terms && j < vi.n_in_tile) {
                     if (p.flags & 16384u)   // experiments: the first step drawn WITH replacement inside the tile instead of every staged step once
                         j = __umulhi((uint32_t) (xoshiro_next(g) >> 11), min(vi.terms, vi.n_in_tile));
+                    if (p.flags & 32768u) {   // experiments: every warp draws a 32-step segment of the tile with replacement (lanes stay neighbours)
+                        const uint32_t lim = min(vi.terms, vi.n_in_tile) >> 5;
+                        const uint32_t am = __activemask();
+                        const uint32_t sgm = __shfl_sync(am, __umulhi((uint32_t) (xoshiro_next(g) >> 11), lim), __ffs(am) - 1);
+                        if (lim) j = sgm * 32u + (threadIdx.x & 31u);
+                    }
+                    if (p.flags & 65536u) {   // experiments: every staged step once, but neighbouring lanes far apart in the tile (odd multiplier mod TILE)
+                        const uint32_t jj = (j * 1229u + (uint32_t) vi.base * 7u) & (uint32_t) (TILE - 1);
+                        if (jj < vi.terms && jj < vi.n_in_tile && vi.n_in_tile == (uint32_t) TILE && vi.terms == (uint32_t) TILE) j = jj;
+                    }
                     uint64_t f = vi.f;
                     uint32_t count = vi.count, s_rank = rank0 + j;
                     if (!vi.one_path) {

@@ -19,6 +19,10 @@ X = capi.FLAG_X_TILE_REPLACE, capi.FLAG_X_STEP_RANDOM
 VARIANTS = [("tile", capi.SAMPLING_TILE, 0), ("stream", capi.SAMPLING_STREAM, 0),
             ("tile, tiles w/ replacement", capi.SAMPLING_TILE, X[0]), ("tile, steps w/ replacement", capi.SAMPLING_TILE, X[1]),
             ("tile, both w/ replacement", capi.SAMPLING_TILE, X[0] | X[1]),
+            ("tile, warp segments w/ repl", capi.SAMPLING_TILE, capi.FLAG_X_SEGMENT_RANDOM),
+            ("tile, tiles+segments w/ repl", capi.SAMPLING_TILE, X[0] | capi.FLAG_X_SEGMENT_RANDOM),
+            ("tile, scrambled lanes", capi.SAMPLING_TILE, capi.FLAG_X_STEP_SCRAMBLE),
+            ("tile, tiles repl + scrambled", capi.SAMPLING_TILE, X[0] | capi.FLAG_X_STEP_SCRAMBLE),
             ("tile 1024", capi.SAMPLING_TILE, capi.FLAG_HALF_TILE), ("tile 4096", capi.SAMPLING_TILE, capi.FLAG_BIG_TILE),
             ("tile legacy kernel", capi.SAMPLING_TILE, capi.FLAG_LEGACY_TILE), ("tile exchange write", capi.SAMPLING_TILE, capi.FLAG_EXCH_WRITE),
             ("tile window order", capi.SAMPLING_TILE, capi.FLAG_WINDOW_TILES), ("tile sweep order", capi.SAMPLING_TILE, capi.FLAG_SWEEP_TILES)]
