@@ -25,6 +25,7 @@ PGSGD_FLAG_KEEP_ADD = 16
 SAMPLING_AUTO, SAMPLING_STREAM, SAMPLING_TILE = 0, 1, 2
 FLAG_EXCH_WRITE, FLAG_SUM_DELTAS, FLAG_PLAIN_STORE, FLAG_TMA_STAGING, FLAG_KEEP_ADD, FLAG_LEGACY_TILE, FLAG_HALF_TILE, FLAG_BIG_TILE, FLAG_SWEEP_TILES, FLAG_L2_WINDOW = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 FLAG_WINDOW_TILES, FLAG_X_TILE_REPLACE, FLAG_X_STEP_RANDOM, FLAG_X_SEGMENT_RANDOM, FLAG_X_STEP_SCRAMBLE = 4096, 8192, 16384, 32768, 65536
+FLAG_X_SCRAMBLE_PAIRS, FLAG_X_SCRAMBLE_QUADS = 131072, 262144   # with FLAG_X_STEP_SCRAMBLE: groups of 2 / 4 neighbouring lanes stay together
 MULTI_ALLREDUCE, MULTI_PEER, MULTI_HYBRID, MULTI_AUTO, MULTI_SINGLE = 0, 1, 2, 3, 4
 
 

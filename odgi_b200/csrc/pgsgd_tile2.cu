@@ -391,7 +391,9 @@ __global__ void __launch_bounds__(256, 4) pgsgd_tile2_kernel(const __grid_consta
                         if (lim) j = sgm * 32u + (threadIdx.x & 31u);
                     }
                     if (p.flags & 65536u) {   // experiments: every staged step once, but neighbouring lanes far apart in the tile (odd multiplier mod TILE)
-                        const uint32_t jj = (j * 1229u + (uint32_t) vi.base * 7u) & (uint32_t) (TILE - 1);
+                        // groups of 1 / 2 / 4 neighbouring lanes stay neighbours (flags 131072: 2, 262144: 4): a group of 2 is one 32-byte coordinate sector
+                        const uint32_t gs = (p.flags & 262144u) ? 2u : ((p.flags & 131072u) ? 1u : 0u);
+                        const uint32_t jj = (((((j >> gs) * 1229u + (uint32_t) (vi.base >> 11) * 7u) & (uint32_t) ((TILE >> gs) - 1)) << gs) | (j & ((1u << gs) - 1u)));
                         if (jj < vi.terms && jj < vi.n_in_tile && vi.n_in_tile == (uint32_t) TILE && vi.terms == (uint32_t) TILE) j = jj;
                     }
                     uint64_t f = vi.f;

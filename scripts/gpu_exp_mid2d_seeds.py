@@ -23,6 +23,8 @@ VARIANTS = [("tile", capi.SAMPLING_TILE, 0), ("stream", capi.SAMPLING_STREAM, 0)
             ("tile, tiles+segments w/ repl", capi.SAMPLING_TILE, X[0] | capi.FLAG_X_SEGMENT_RANDOM),
             ("tile, scrambled lanes", capi.SAMPLING_TILE, capi.FLAG_X_STEP_SCRAMBLE),
             ("tile, tiles repl + scrambled", capi.SAMPLING_TILE, X[0] | capi.FLAG_X_STEP_SCRAMBLE),
+            ("tile, scrambled pairs", capi.SAMPLING_TILE, capi.FLAG_X_STEP_SCRAMBLE | capi.FLAG_X_SCRAMBLE_PAIRS),
+            ("tile, scrambled quads", capi.SAMPLING_TILE, capi.FLAG_X_STEP_SCRAMBLE | capi.FLAG_X_SCRAMBLE_QUADS),
             ("tile 1024", capi.SAMPLING_TILE, capi.FLAG_HALF_TILE), ("tile 4096", capi.SAMPLING_TILE, capi.FLAG_BIG_TILE),
             ("tile legacy kernel", capi.SAMPLING_TILE, capi.FLAG_LEGACY_TILE), ("tile exchange write", capi.SAMPLING_TILE, capi.FLAG_EXCH_WRITE),
             ("tile window order", capi.SAMPLING_TILE, capi.FLAG_WINDOW_TILES), ("tile sweep order", capi.SAMPLING_TILE, capi.FLAG_SWEEP_TILES)]

@@ -14,7 +14,7 @@ T, S, G, M = capi.FLAG_X_TILE_REPLACE, capi.FLAG_X_STEP_RANDOM, capi.FLAG_X_SEGM
 print(f"workload={wl} N={g.N} S={g.S}", flush=True)
 with odgi_b200.Engine(g) as e:
     for name, flags in (("default (bijections)", 0), ("tiles w/ repl", T), ("tiles + steps w/ repl", T | S), ("tiles + warp segments w/ repl", T | G),
-                        ("warp segments w/ repl", G), ("scrambled lanes", M), ("steps w/ repl", S)):
+                        ("warp segments w/ repl", G), ("scrambled lanes", M), ("scrambled pairs", M | capi.FLAG_X_SCRAMBLE_PAIRS), ("scrambled quads", M | capi.FLAG_X_SCRAMBLE_QUADS), ("steps w/ repl", S)):
         e.set_coords_2d(X0, Y0)
         cd = capi.layout_defaults(g, sampling=capi.SAMPLING_TILE, flags=flags)
         e.run_range(cd, 2, 0, 1)
