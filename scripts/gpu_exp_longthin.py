@@ -21,6 +21,13 @@ VARIANTS = [("tile2 default", dict(sampling=2)), ("legacy tile", dict(sampling=2
             ("tile2 148 CTAs", dict(sampling=2, n_streams=148 * 256)), ("tile2 37 CTAs", dict(sampling=2, n_streams=37 * 256)),
             ("tile2 sweep", dict(sampling=2, flags=capi.FLAG_SWEEP_TILES)), ("tile2 exch write", dict(sampling=2, flags=capi.FLAG_EXCH_WRITE)),
             ("stream 37 CTAs", dict(sampling=1, n_streams=37 * 256))]
+if len(sys.argv) > 3 and sys.argv[3] == "sampling":   # the with-replacement / scrambled variants of the tile sampling (scripts/gpu_exp_mid2d_seeds.py)
+    M = capi.FLAG_X_STEP_SCRAMBLE
+    VARIANTS = [("tile2 default", dict(sampling=2)), ("stream sampling", dict(sampling=1)), ("tile2 scrambled lanes", dict(sampling=2, flags=M)),
+                ("tile2 scrambled pairs", dict(sampling=2, flags=M | capi.FLAG_X_SCRAMBLE_PAIRS)),
+                ("tile2 tiles+steps w/ repl", dict(sampling=2, flags=capi.FLAG_X_TILE_REPLACE | capi.FLAG_X_STEP_RANDOM)),
+                ("tile2 warp segments w/ repl", dict(sampling=2, flags=capi.FLAG_X_SEGMENT_RANDOM)),
+                ("tile2 scrambled + exch", dict(sampling=2, flags=M | capi.FLAG_EXCH_WRITE))]
 with odgi_b200.Engine(g) as e:
     for name, kw in VARIANTS:
         far, loc, rate = [], [], []
