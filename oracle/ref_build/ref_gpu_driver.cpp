@@ -2,7 +2,11 @@
 // Times the reference's own CUDA path, cuda::gpu_layout (src/cuda/layout.cu:290-476, compiled unmodified for
 // sm_100a by oracle/ref_build/Makefile `refgpu`), as the REPORTED GPU baseline (not the optimisation target).
 //
-//   ref_gpu_driver <in.gfa> <out.arr|-> [iter_max=30] [threads=8] [updates_x=10]
+//   ref_gpu_driver <in.gfa> <out.arr|-> [iter_max=30] [threads=8] [updates_x=10] [init.arr|-] [repeats=0]
+//
+// With init.arr (X, Y: the injected initial layout the scale bands use) and repeats > 0 it instead writes the final layouts of
+// `repeats` complete runs of iter_max iterations to <out.arr>.run<k>.arr: the reference CUDA path's own distribution of the
+// final stress (its worker seeds are fixed, layout.cu:29, so the runs differ by GPU timing only).
 //
 // The reference gives no hook around its iteration loop (layout.cu:442-447), so the loop time is obtained by
 // difference: the call is run with iter_max and with 2*iter_max; (t2 - t1) is the time of iter_max iterations
@@ -21,10 +25,15 @@
 
 using namespace odgi;
 
+static std::vector<double> g_init_x, g_init_y;   // injected initial layout (optional)
+
 static double run_once(const graph_t& graph, uint64_t iter_max, uint64_t U, uint64_t max_steps, int threads,
                        std::vector<std::atomic<double>>& X, std::vector<std::atomic<double>>& Y) {
     uint64_t N = graph.get_node_count();
     uint64_t len = 0;
+    if (g_init_x.size() == 2 * N) {
+        for (uint64_t i = 0; i < 2 * N; ++i) { X[i].store(g_init_x[i]); Y[i].store(g_init_y[i]); }
+    } else
     for (uint64_t r = 0; r < N; ++r) {   // 'd' initialisation without noise (layout_main.cpp:322-328)
         X[2 * r].store(len); Y[2 * r].store(0.01 * (double) (r % 97));
         len += graph.get_length(graph.get_handle(r + 1, false));
@@ -65,7 +74,25 @@ int main(int argc, char** argv) {
     uint64_t U = (uint64_t) (updates_x * sum_steps);
     uint64_t N = graph.get_node_count();
     std::vector<std::atomic<double>> X(2 * N), Y(2 * N);
+    if (argc > 6 && std::string(argv[6]) != "-") {
+        auto a = pgsgd::read_arrays(argv[6]);
+        g_init_x = a.at("X").vec<double>(); g_init_y = a.at("Y").vec<double>();
+        if (g_init_x.size() != 2 * N || g_init_y.size() != 2 * N) { std::cerr << "init.arr: X, Y must hold 2N doubles" << std::endl; return 2; }
+    }
+    const int repeats = argc > 7 ? std::stoi(argv[7]) : 0;
     run_once(graph, 2, U, max_steps, threads, X, Y);  // warm-up: CUDA context creation, module load
+    if (repeats > 0) {
+        for (int k = 0; k < repeats; ++k) {
+            const double t = run_once(graph, iter_max, U, max_steps, threads, X, Y);
+            std::vector<double> x(2 * N), y(2 * N);
+            for (uint64_t i = 0; i < 2 * N; ++i) { x[i] = X[i].load(); y[i] = Y[i].load(); }
+            pgsgd::ArrayWriter w(std::string(argv[2]) + ".run" + std::to_string(k) + ".arr");
+            w.add("X", x); w.add("Y", y);
+            w.close();
+            std::cout << "{\"impl\": \"reference src/cuda/layout.cu (sm_100a)\", \"run\": " << k << ", \"iter_max\": " << iter_max << ", \"call_s\": " << t << "}" << std::endl;
+        }
+        return 0;
+    }
     double t1 = run_once(graph, iter_max, U, max_steps, threads, X, Y);
     double t2 = run_once(graph, 2 * iter_max, U, max_steps, threads, X, Y);
     double loop_s = t2 - t1;
