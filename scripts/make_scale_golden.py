@@ -130,6 +130,20 @@ def stage_bands():
                 ent["initial_local"] = orc.local_stress_1d(g, x0, N_PAIRS, SEED)
             out[f"{name}.{kind}"] = ent
             print(name, kind, json.dumps(ent)[:400], flush=True)
+    # The reference's OWN CUDA path (src/cuda/layout.cu compiled unmodified for sm_100a) on the same graphs from the same injected
+    # layout, run on a B200 by scripts/gpu_exp_refcuda_stress.py: the implementation this library drops in for, and the anchor for what
+    # Hogwild with ~10^5 concurrent terms does to the final stress (its seeds are fixed, layout.cu:29: runs differ by GPU timing only).
+    rc = os.path.join(ROOT, "profiles", "r02_refcuda_stress.log")
+    if os.path.exists(rc):
+        for ln in open(rc):
+            if not ln.startswith("{") or '"impl": "reference src/cuda/layout.cu"' not in ln:
+                continue
+            o = json.loads(ln)
+            key = f"{o['graph']}.layout2d"
+            if key in out:
+                out[key]["refcuda"] = {"runs": len(o["far"]), "far": {"mean": o["far_mean"], "sd": o["far_sd"], "values": o["far"]},
+                                       "local": {"mean": o["local_mean"], "sd": o["local_sd"], "values": o["local"]},
+                                       "source": "profiles/r02_refcuda_stress.log (scripts/gpu_exp_refcuda_stress.py, oracle/_ref/ref_gpu_driver on a B200)"}
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
 

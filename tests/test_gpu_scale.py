@@ -66,8 +66,28 @@ def test_device_local_stress_equals_the_oracle():
         assert e.local_stress(1, 300_000, 78) == orc.local_stress_1d(go, x, 300_000, 78)
 
 
+SEEDS_2D = [9399220, 1234567, 42] + [1000003 * (k + 1) for k in range(13)]   # far apart: worker stream t of a run is seeded seed + t
+
+
+def _assert_mean_in_band(values, band, what, upper_only=False):
+    """SURVEY.md 8(d) on the mean — within max(1 %, 2 sigma) of the band — with the standard error of OUR mean added to the tolerance:
+    on these graphs the final stress of a GPU run scatters 2-3x wider over seeds than the band's runs do (the reference's own CUDA
+    path scatters by as much from GPU timing alone, `refcuda` in the golden file), so a mean over n seeds is only known to
+    2 * sd / sqrt(n).  Without that term the outcome would depend on which seeds the test happens to use."""
+    mean, sd = band["mean"], band["sd"]
+    v = np.asarray(values)
+    tol = max(0.01 * mean, 2 * sd) + 2 * v.std(ddof=1) / np.sqrt(len(v))
+    if upper_only:
+        assert 0.5 * mean <= v.mean() <= mean + tol, (what, v.mean(), v.std(ddof=1), mean, sd)
+    else:
+        assert abs(v.mean() - mean) <= tol, (what, v.mean(), v.std(ddof=1), mean, sd)
+
+
 @pytest.mark.parametrize("name", ["longthin", "mid"])
 def test_default_2d_run_within_the_reference_band_at_scale(name):
+    """Two anchors: the CPU reference band (reference runs + oracle runs under other seeds) and the band of the
+    reference's OWN CUDA path on a B200 (`refcuda`: the implementation this library drops in for).  16 seeds, because single runs
+    scatter widely (sd 20-30 % of the mean, for this library's two samplers and for the reference CUDA path alike)."""
     band = _bands().get(f"{name}.layout2d")
     if band is None or band["runs"] < 3:
         pytest.skip(f"no reference band (>= 3 runs) for {name}.layout2d yet (scripts/make_scale_golden.py)")
@@ -76,7 +96,7 @@ def test_default_2d_run_within_the_reference_band_at_scale(name):
     X0, Y0 = odgi_b200.layout_init(g, seed=band["init_seed"])
     far, loc = [], []
     with odgi_b200.Engine(g) as e:
-        for seed in (9399220, 1234567, 42):
+        for seed in SEEDS_2D:
             cd = capi.layout_defaults(g, seed=seed)
             e.set_coords_2d(X0, Y0)
             st = e.run_2d(cd)
@@ -88,8 +108,15 @@ def test_default_2d_run_within_the_reference_band_at_scale(name):
         X, _ = e.get_coords_2d()
     if name == "longthin":
         assert np.max(np.abs(X)) > 2 ** 24   # the regime this graph is here for
-    _assert_in_band(far, band["far"], f"{name} far")
-    _assert_in_band(loc, band["local"], f"{name} local", upper_only=True)
+    # (1) against the CPU reference: the mean, two-sided for the far stress, from above for the local stress (fp32, see _assert_in_band)
+    _assert_mean_in_band(far, band["far"], f"{name} far vs the CPU reference")
+    _assert_mean_in_band(loc, band["local"], f"{name} local vs the CPU reference", upper_only=True)
+    # (2) against the reference's own CUDA path: not worse than it — means not above its band, no run's far stress beyond its mean + 3 sigma
+    rc = band.get("refcuda")
+    if rc is not None:
+        for vals, b, what in ((far, rc["far"], "far"), (loc, rc["local"], "local")):
+            assert np.mean(vals) <= b["mean"] + max(0.01 * b["mean"], 2 * b["sd"]), (name, what, np.mean(vals), b["mean"], b["sd"])
+        assert max(far) <= rc["far"]["mean"] + max(0.01 * rc["far"]["mean"], 3 * rc["far"]["sd"]), (name, max(far), rc["far"])
 
 
 @pytest.mark.parametrize("name", ["longthin", "mid"])
