@@ -91,8 +91,9 @@ typedef struct pgsgd_config {
  *          bijections, so over an iteration every step is a first step exactly floor(U/S) (+1) times — the same
  *          uniform marginal with the first pick's sampling noise removed.  ~1 random HBM read per term or fewer.
  *  AUTO  : TILE for graphs whose step records exceed the L2 (>= 2^22 steps), that are at least PGSGD_AUTO_TILE_MIN_DEPTH steps
- *          deep per node on average (haplotype depth) and large enough for the in-flight cap, else STREAM.  (On a 6-haplotype
- *          graph tile sampling left the reference's far-stress band, from 12 haplotypes on it does not: DESIGN.md 5.) */
+ *          deep per node on average (haplotype depth) and large enough for the in-flight cap, else STREAM.  (Shallow graphs keep
+ *          the reference-exact sampler as the conservative choice; over 20 far-apart seeds the two samplers end in the same
+ *          distribution of final stress on a 6-haplotype graph: DESIGN.md 5.4.) */
 #define PGSGD_AUTO_TILE_MIN_DEPTH 8ull
 #define PGSGD_SAMPLING_AUTO   0u
 #define PGSGD_SAMPLING_STREAM 1u
