@@ -197,6 +197,7 @@ struct pgsgd_engine {
     std::vector<void*> ipc_opened;
     std::vector<uint32_t> tile_mid_node;     // node of the middle step of every tile (tile -> owner rank)
     uint32_t* d_tile_list = nullptr;
+    double* d_stage_xy[2] = {nullptr, nullptr};   // fp64 X / Y staging of set/get_coords_2d (2N each), kept: no cudaMalloc / cudaFree per transfer
     uint32_t* d_window_list = nullptr;       // PGSGD_FLAG_WINDOW_TILES: all tiles, window by window (build_window_list)
     uint64_t window_list_key = 0;            // (grid, C) the list was built for
     uint64_t my_tiles = 0, my_tile_steps = 0;
@@ -1376,7 +1377,7 @@ void pgsgd_engine_destroy(pgsgd_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     for (void* q : e->ipc_opened) cudaIpcCloseMemHandle(q);
-    cudaFree(e->d_xy_part); cudaFree(e->d_x1d_part); cudaFree(e->d_tile_list); cudaFree(e->d_window_list);
+    cudaFree(e->d_xy_part); cudaFree(e->d_x1d_part); cudaFree(e->d_tile_list); cudaFree(e->d_window_list); cudaFree(e->d_stage_xy[0]); cudaFree(e->d_stage_xy[1]);
     if (e->comm && !e->comm_cached) ncclCommDestroy(e->comm);
     cudaFree(e->d_steps); cudaFree(e->d_path_first); cudaFree(e->d_node_len); cudaFree(e->d_xy); cudaFree(e->d_xy_prev); cudaFree(e->d_x1d);
     cudaFree(e->d_trace); cudaFree(e->d_trace_count);
@@ -1394,19 +1395,23 @@ void pgsgd_engine_destroy(pgsgd_engine* e) {
 int pgsgd_engine_device(const pgsgd_engine* e) { return e ? e->device : -1; }
 uint64_t pgsgd_engine_device_bytes(const pgsgd_engine* e) { return e ? e->bytes : 0; }
 
+static int stage_xy(pgsgd_engine* e) {
+    for (int k = 0; k < 2; ++k)
+        if (!e->d_stage_xy[k]) { int rc = dev_alloc(e, &e->d_stage_xy[k], 2 * e->N); if (rc) return rc; }
+    return PGSGD_OK;
+}
+
 int pgsgd_engine_set_coords_2d(pgsgd_engine* e, const double* X, const double* Y) {
     if (!e || !X || !Y) return fail(PGSGD_ERR_ARG, "set_coords_2d: NULL argument");
     CU(cudaSetDevice(e->device));
     const double t0 = now_s();
     if (!e->d_xy) { int rc = dev_alloc(e, &e->d_xy, 4 * e->N); if (rc) return rc; }
-    double *dX = nullptr, *dY = nullptr;
-    CU(cudaMalloc(&dX, 2 * e->N * sizeof(double)));
-    if (cudaMalloc(&dY, 2 * e->N * sizeof(double)) != cudaSuccess) { cudaFree(dX); return fail(PGSGD_ERR_NOMEM, "cudaMalloc failed"); }
+    { int rc = stage_xy(e); if (rc) return rc; }
+    double *dX = e->d_stage_xy[0], *dY = e->d_stage_xy[1];
     cudaError_t err = cudaMemcpyAsync(dX, X, 2 * e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(dY, Y, 2 * e->N * sizeof(double), cudaMemcpyHostToDevice, e->stream);
     if (err == cudaSuccess) err = launch_xy_from_XY(e->d_xy, dX, dY, e->N, e->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-    cudaFree(dX); cudaFree(dY);
     if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "set_coords_2d: %s", cudaGetErrorString(err));
     e->coords_in_slices = false;
     { int rc = multi_prepare(e, 2); if (rc) return rc; }
@@ -1421,14 +1426,12 @@ int pgsgd_engine_get_coords_2d(pgsgd_engine* e, double* X, double* Y) {
     if (!e->have_2d) return fail(PGSGD_ERR_STATE, "no 2D coordinates on the device");
     CU(cudaSetDevice(e->device));
     if (e->coords_in_slices && e->peer_ready_2d) { int rc = peer_gather(e, 2); if (rc) return rc; }
-    double *dX = nullptr, *dY = nullptr;
-    CU(cudaMalloc(&dX, 2 * e->N * sizeof(double)));
-    if (cudaMalloc(&dY, 2 * e->N * sizeof(double)) != cudaSuccess) { cudaFree(dX); return fail(PGSGD_ERR_NOMEM, "cudaMalloc failed"); }
+    { int rc = stage_xy(e); if (rc) return rc; }
+    double *dX = e->d_stage_xy[0], *dY = e->d_stage_xy[1];
     cudaError_t err = launch_XY_from_xy(dX, dY, e->d_xy, e->N, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(X, dX, 2 * e->N * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(Y, dY, 2 * e->N * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-    cudaFree(dX); cudaFree(dY);
     if (err != cudaSuccess) return fail(PGSGD_ERR_CUDA, "get_coords_2d: %s", cudaGetErrorString(err));
     return PGSGD_OK;
 }
