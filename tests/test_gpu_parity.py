@@ -133,7 +133,11 @@ def _stress_band(golden_dir, key):
 def _assert_in_band(values, band):
     """|stress_gpu - mean(stress_cpu)| <= max(1 % of the reference mean, 2 sigma_cpu), applied to the mean over
     the seeds.  A SINGLE run drawn from the reference's own distribution leaves a 2-sigma band one time in ~16 (the reference
-    mean itself comes from six runs), so the per-run gate is max(1 %, 3 sigma): the same bound, one sigma wider."""
+    mean itself comes from six runs), so the per-run gate is max(1 %, 3 sigma): the same bound, one sigma wider.
+    The band = six runs of the reference (hard-coded worker seeds: thread timing only) + twelve runs of the oracle under other
+    seeds (scripts/make_stress_golden.py --oracle-seeds); with the reference runs alone a seed whose OWN expectation sits
+    0.9 % off their mean (DRB1-3123 2D, seed 42: oracle 0.06886, GPU 0.0688, reference runs 0.06825) is one noisy run away
+    from the 1 % gate."""
     mean, sd = band["mean"], band["sd"]
     assert abs(np.mean(values) - mean) <= max(0.01 * mean, 2 * sd), (values, mean, sd)
     assert all(abs(v - mean) <= max(0.01 * mean, 3 * sd) for v in values), (values, mean, sd)
