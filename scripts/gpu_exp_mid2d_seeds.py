@@ -30,12 +30,15 @@ VARIANTS = [("tile", capi.SAMPLING_TILE, 0), ("stream", capi.SAMPLING_STREAM, 0)
             ("tile window order", capi.SAMPLING_TILE, capi.FLAG_WINDOW_TILES), ("tile sweep order", capi.SAMPLING_TILE, capi.FLAG_SWEEP_TILES)]
 if len(sys.argv) > 2:
     VARIANTS = [v for v in VARIANTS if v[0] in sys.argv[2].split(";")]
+if len(sys.argv) > 3:   # "<ctas>": the same variants with that many resident CTAs (terms in flight: is the offset to the CPU runs Hogwild staleness?)
+    VARIANTS = [(f"{n}, {sys.argv[3]} CTAs", sm, fl) for n, sm, fl in VARIANTS]
+extra = dict(n_streams=int(sys.argv[3]) * 256) if len(sys.argv) > 3 else {}
 with odgi_b200.Engine(g) as e:
     for name, sampling, flags in VARIANTS:
         far, loc = [], []
         for seed in seeds:
             e.set_coords_2d(X0, Y0)
-            e.run_2d(capi.layout_defaults(g, seed=seed, sampling=sampling, flags=flags))
+            e.run_2d(capi.layout_defaults(g, seed=seed, sampling=sampling, flags=flags, **extra))
             far.append(e.path_stress(2, 4_000_000, 12345)); loc.append(e.local_stress(2, 4_000_000, 12345))
         far, loc = np.array(far), np.array(loc)
         print(f"{name:28s} far mean {far.mean():.6f} sd {far.std(ddof=1):.6f} se {far.std(ddof=1) / np.sqrt(len(far)):.6f} median {np.median(far):.6f}   "
