@@ -1,0 +1,58 @@
+"""CPU checks of the stress bands the GPU parity tests are gated on (tests/golden/stress_reference*.json): that they hold what the
+tests read, that every band rests on enough runs, and that the oracle reproduces a stored oracle-seed value (the band files are
+reproducible from scripts/make_stress_golden.py --oracle-seeds and scripts/make_scale_golden.py, not hand-edited)."""
+import json
+import os
+
+import numpy as np
+
+from odgi_b200.arrays import read_arrays
+from oracle import oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def test_small_graph_bands_hold_reference_and_oracle_seed_runs():
+    bands = _load("stress_reference.json")
+    for key in ("DRB1-3123.layout2d", "chr6.C4.layout2d", "LPA.layout2d", "DRB1-3123.sort1d", "chr6.C4.sort1d", "LPA.sort1d"):
+        b = bands[key]
+        ref, orc_runs = b["reference_only"]["values"], b["oracle_seed_runs"]["values"]
+        assert len(ref) >= 6 and len(orc_runs) >= 12 and len(set(b["oracle_seed_runs"]["seeds"])) == len(orc_runs)
+        allv = np.array(list(ref) + list(orc_runs))
+        assert np.isclose(b["mean"], allv.mean(), rtol=1e-12) and np.isclose(b["sd"], allv.std(ddof=1), rtol=1e-12)
+        assert b["n_pairs"] >= 100_000 and b["mean"] > 0
+        if key.endswith("layout2d"):
+            assert b["mean"] < b["initial"]   # (a 1D sort may end above its initial order's stress: chr6.C4, reference and oracle alike)
+
+
+def test_scale_bands_hold_reference_oracle_and_reference_cuda_runs():
+    bands = _load("stress_reference_scale.json")
+    for key in ("mid.layout2d", "longthin.layout2d", "mid.sort1d", "longthin.sort1d"):
+        b = bands[key]
+        assert b["runs"] >= 3 and b["runs"] == b["reference_runs"] + len(b["oracle_runs"]) == len(b["far"]["values"]) == len(b["local"]["values"])
+        for m in ("far", "local"):
+            v = np.array(b[m]["values"])
+            assert np.isclose(b[m]["mean"], v.mean(), rtol=1e-12) and np.isclose(b[m]["sd"], v.std(ddof=1), rtol=1e-12)
+        assert b["far"]["mean"] < b["initial_far"]
+    for key in ("mid.layout2d", "longthin.layout2d"):   # the second anchor of tests/test_gpu_scale.py
+        rc = bands[key]["refcuda"]
+        assert rc["runs"] >= 8 and len(rc["far"]["values"]) == rc["runs"] and rc["far"]["sd"] > 0
+    # the 2D bands carry oracle runs under seeds other than the reference's hard-coded ones
+    assert len(bands["mid.layout2d"]["oracle_runs"]) >= 5 and len(bands["longthin.layout2d"]["oracle_runs"]) >= 5
+
+
+def test_a_stored_oracle_seed_run_is_reproducible():
+    """DRB1-3123 2D, oracle seed 42, six interleaved streams: the stored value is what the oracle computes today"""
+    b = _load("stress_reference.json")["DRB1-3123.layout2d"]
+    i = b["oracle_seed_runs"]["seeds"].index(42)
+    g = orc.Graph.from_arrays(read_arrays(os.path.join(GOLDEN, "DRB1-3123.graph.arr.gz")))
+    cfg = orc.default_layout_config(g)
+    cfg.seed = 42
+    X, Y = orc.layout_init(g, seed=b.get("init_seed", 42))
+    _, X, Y = orc.layout_2d(g, cfg, X, Y, n_streams=b["oracle_seed_runs"]["n_streams"])
+    assert orc.path_stress_2d(g, X, Y, b["n_pairs"], b["seed"]) == b["oracle_seed_runs"]["values"][i]
