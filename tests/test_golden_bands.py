@@ -76,3 +76,27 @@ def test_a_stored_oracle_seed_run_is_reproducible():
     X, Y = orc.layout_init(g, seed=b.get("init_seed", 42))
     _, X, Y = orc.layout_2d(g, cfg, X, Y, n_streams=b["oracle_seed_runs"]["n_streams"])
     assert orc.path_stress_2d(g, X, Y, b["n_pairs"], b["seed"]) == b["oracle_seed_runs"]["values"][i]
+
+
+def test_recorded_gpu_2d_values_sit_inside_the_2d_scale_bands():
+    """profiles/r02_2d_scale_values.jsonl: the 16-seed default 2D runs of tests/test_gpu_scale.py as recorded on a B200, evaluated with
+    that test's criterion (mean against the CPU band with the standard error of our mean; not above the reference CUDA path's band)."""
+    rec_path = os.path.join(os.path.dirname(GOLDEN), "..", "profiles", "r02_2d_scale_values.jsonl")
+    if not os.path.exists(rec_path):
+        import pytest
+        pytest.skip("no recorded GPU values")
+    bands = _load("stress_reference_scale.json")
+    for ln in open(rec_path):
+        r = json.loads(ln)
+        b = bands[f"{r['graph']}.layout2d"]
+        for m, upper in (("far", False), ("local", True)):
+            mean, sd, v = b[m]["mean"], b[m]["sd"], np.array(r[m], dtype=np.float64)
+            tol = max(0.01 * mean, 2 * sd) + 2 * v.std(ddof=1) / np.sqrt(len(v))
+            if upper:
+                assert 0.5 * mean <= v.mean() <= mean + tol, (r["graph"], m, v.mean(), mean, sd)
+            else:
+                assert abs(v.mean() - mean) <= tol, (r["graph"], m, v.mean(), mean, sd)
+            rc = b["refcuda"][m]
+            assert v.mean() <= rc["mean"] + max(0.01 * rc["mean"], 2 * rc["sd"]), (r["graph"], m, v.mean(), rc["mean"], rc["sd"])
+        rc = b["refcuda"]["far"]
+        assert max(r["far"]) <= rc["mean"] + max(0.01 * rc["mean"], 3 * rc["sd"]), (r["graph"], max(r["far"]), rc)
